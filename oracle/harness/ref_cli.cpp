@@ -1,0 +1,214 @@
+// Oracle harness (test infrastructure, NOT product code).
+//
+// Drives the reference's own, unmodified insertion-site search
+// (/root/reference/cppsrc/{MOIP,Motif,Pool,SecondaryStructure}.cpp, compiled where they lie)
+// and prints what it found, so that the CUDA path and the CPU restatement in oracle/port can
+// be checked against the real thing.
+//
+//   biorseo_ref ctor  <source> <library> <seqfile> <maskfile>
+//       runs MOIP::MOIP (cppsrc/MOIP.cpp:58) end to end with the stubbed solver and dumps
+//       insertion_sites_.
+//   biorseo_ref jobs  <source> <library> <seqfile> <maskfile> [threads]
+//       runs only the search: the per-module jobs MOIP::allowed_motifs_from_{json,rin,desc}
+//       (cppsrc/MOIP.cpp:912-1213) on the reference's Pool, dispatched the way
+//       cppsrc/MOIP.cpp:146-296 does, and dumps insertion_sites_.
+//   biorseo_ref bench <source> <library> <seqfile> <maskfile> <threads> <repeat> [max_modules]
+//       as `jobs`, timed from the first Pool::push to the last join (validation, JSON parse
+//       and directory walk excluded), prints one JSON line.
+//
+// <source> is jsonfolder | rinfolder | descfolder; Motif::delay follows cppsrc/biorseo.cpp:151,156.
+// <seqfile> holds the raw query bytes (one trailing newline is dropped); <maskfile> holds the
+// pair mask as n rows of ceil(n/32) little-endian u32 words, bit v of row u = "pij(u,v) > theta".
+// Output lines: identifier \t first-second ... \t a-b ... (components, then links).
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+#include <mutex>
+#include <map>
+#include <stack>
+#include <regex>
+#include <filesystem>
+
+#define private public
+#include "MOIP.h"
+#undef private
+#include "Pool.h"
+
+using std::string;
+using std::vector;
+using json = nlohmann::json;
+
+extern const uint32_t* g_oracle_mask_words;
+extern size_t          g_oracle_mask_n;
+
+static string read_file(const string& p)
+{
+    std::ifstream f(p, std::ios::binary);
+    if (!f) { std::fprintf(stderr, "cannot open %s\n", p.c_str()); std::exit(2); }
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+static void dump_sites(const vector<Motif>& sites)
+{
+    string out;
+    for (const Motif& m : sites) {
+        out += m.get_identifier();
+        out += '\t';
+        for (size_t j = 0; j < m.comp.size(); j++) {
+            if (j) out += ' ';
+            out += std::to_string(m.comp[j].pos.first) + "-" + std::to_string(m.comp[j].pos.second);
+        }
+        out += '\t';
+        for (size_t j = 0; j < m.links_.size(); j++) {
+            if (j) out += ' ';
+            out += std::to_string(m.links_[j].nts.first) + "-" + std::to_string(m.links_[j].nts.second);
+        }
+        out += '\n';
+    }
+    std::fwrite(out.data(), 1, out.size(), stdout);
+}
+
+// The basepair table MOIP::allowed_basepair reads, built as at cppsrc/MOIP.cpp:77-90 but
+// without creating solver variables.
+static void fill_yuv(MOIP& moip, float theta)
+{
+    const size_t n       = moip.rna_.get_RNA_length();
+    const size_t missing = n * n + 1;
+    size_t       next    = 0;
+    moip.index_of_yuv_.assign(n - 6, vector<size_t>());
+    for (size_t u = 0; u + 6 < n; u++)
+        for (size_t v = u + 4; v < n; v++)
+            moip.index_of_yuv_[u].push_back(moip.rna_.get_pij(u, v) > theta ? next++ : missing);
+}
+
+struct Dispatch {
+    vector<std::function<void()>> jobs;
+    json                          library;   // keeps JSON iterators alive
+    std::mutex                    sites_mutex;
+};
+
+static void collect_jobs(MOIP& moip, const string& source, const string& lib, Dispatch& d, size_t max_modules)
+{
+    if (source == "jsonfolder") {
+        std::ifstream f(lib);
+        d.library = json::parse(f);
+        for (auto it = d.library.begin(); it != d.library.end(); ++it) {
+            if (Motif::is_valid_JSON(it)) continue;
+            if (d.jobs.size() >= max_modules) break;
+            motif_and_mutex args(it, d.sites_mutex);
+            d.jobs.push_back(std::bind(&MOIP::allowed_motifs_from_json, &moip, args));
+        }
+    } else {
+        vector<string> files;
+        for (auto& e : std::filesystem::recursive_directory_iterator(lib))
+            if (e.is_regular_file()) files.push_back(e.path().string());
+        std::sort(files.begin(), files.end());
+        for (const string& p : files) {
+            if (source == "rinfolder") {
+                if (Motif::is_valid_RIN(p)) continue;
+                if (d.jobs.size() >= max_modules) break;
+                file_and_mutex args(path(p), d.sites_mutex);
+                d.jobs.push_back(std::bind(&MOIP::allowed_motifs_from_rin, &moip, args));
+            } else {
+                if (Motif::is_valid_DESC(p)) continue;
+                if (!is_desc_insertible(p, moip.rna_.get_seq())) continue;
+                if (d.jobs.size() >= max_modules) break;
+                file_and_mutex args(path(p), d.sites_mutex);
+                d.jobs.push_back(std::bind(&MOIP::allowed_motifs_from_desc, &moip, args));
+            }
+        }
+    }
+}
+
+static double run_jobs(Dispatch& d, int threads)
+{
+    Pool                pool;
+    vector<std::thread> workers;
+    for (int i = 0; i < threads; i++) workers.emplace_back(&Pool::infinite_loop_func, &pool);
+    auto t0 = std::chrono::steady_clock::now();
+    for (auto& j : d.jobs) pool.push(j);
+    pool.done();
+    for (auto& w : workers) w.join();
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 6) {
+        std::fprintf(stderr, "usage: %s ctor|jobs|bench <source> <library> <seqfile> <maskfile> [threads] [repeat] [max_modules]\n", argv[0]);
+        return 2;
+    }
+    const string cmd = argv[1], source = argv[2], lib = argv[3];
+    string       seq = read_file(argv[4]);
+    if (!seq.empty() && seq.back() == '\n') seq.pop_back();
+    const string maskbytes = read_file(argv[5]);
+    const size_t n = seq.size(), W = (n + 31) / 32;
+    if (maskbytes.size() != n * W * 4) {
+        std::fprintf(stderr, "mask file holds %zu bytes, expected %zu\n", maskbytes.size(), n * W * 4);
+        return 2;
+    }
+    vector<uint32_t> mask(n * W);
+    std::memcpy(mask.data(), maskbytes.data(), maskbytes.size());
+    g_oracle_mask_words = mask.data();
+    g_oracle_mask_n     = n;
+
+    Motif::delay = (source == "descfolder") ? 5 : 1;
+    const float theta = 0.001f;   // default of --theta, cppsrc/biorseo.cpp:93
+    RNA         rna("query", seq, false);
+
+    if (cmd == "ctor") {
+        MOIP moip(rna, source, lib, theta, false);
+        dump_sites(moip.insertion_sites_);
+        return 0;
+    }
+
+    int    threads     = argc > 6 ? std::atoi(argv[6]) : std::max(1, (int)std::thread::hardware_concurrency() - 1);
+    int    repeat      = argc > 7 ? std::atoi(argv[7]) : 1;
+    size_t max_modules = argc > 8 ? (size_t)std::atoll(argv[8]) : (size_t)-1;
+    if (threads < 1) threads = 1;
+
+    MOIP moip;
+    moip.verbose_ = false;
+    moip.rna_     = rna;
+    fill_yuv(moip, theta);
+
+    Dispatch d;
+    collect_jobs(moip, source, lib, d, max_modules);
+
+    if (cmd == "jobs") {
+        run_jobs(d, threads);
+        dump_sites(moip.insertion_sites_);
+        return 0;
+    }
+    if (cmd == "bench") {
+        double best = 1e300, total = 0;
+        size_t sites = 0;
+        for (int r = 0; r < repeat; r++) {
+            moip.insertion_sites_.clear();
+            double t = run_jobs(d, threads);
+            best  = std::min(best, t);
+            total += t;
+            sites = moip.insertion_sites_.size();
+        }
+        std::printf("{\"seconds_best\": %.9f, \"seconds_mean\": %.9f, \"repeat\": %d, \"threads\": %d, "
+                    "\"modules\": %zu, \"n\": %zu, \"sites\": %zu, \"host_cores\": %u}\n",
+                    best, total / repeat, repeat, threads, d.jobs.size(), n, sites,
+                    std::thread::hardware_concurrency());
+        return 0;
+    }
+    std::fprintf(stderr, "unknown command %s\n", cmd.c_str());
+    return 2;
+}
