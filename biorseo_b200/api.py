@@ -1,0 +1,291 @@
+"""Thin Python view of the C ABI: host library (loaders), device library, queries, searches."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class SearchError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+
+
+def _check(rc, host=False):
+    if rc != 0:
+        lib = capi.load()
+        msg = (lib.bsh_last_error() if host else lib.bss_last_error()) or b""
+        raise SearchError(rc, msg.decode("utf-8", "replace"))
+
+
+def pack_mask(allowed):
+    """Boolean n x n matrix (upper triangle used) -> n x ceil(n/32) little-endian u32 words."""
+    allowed = np.asarray(allowed, dtype=bool)
+    n = allowed.shape[0]
+    W = (n + 31) // 32
+    bits = np.zeros((n, W * 32), dtype=np.uint8)
+    bits[:, :n] = np.triu(allowed, 1)
+    return np.packbits(bits, axis=1, bitorder="little").view("<u4").reshape(n, W).copy()
+
+
+def canonical_pair_mask(seq, span=100, keep=None, rng=None):
+    """Synthetic stand-in for `pij > theta` (the mask the reference derives from ViennaRNA,
+    cppsrc/MOIP.cpp:77-90): canonical pairs with 4 <= v-u < span and u < n-6, optionally
+    thinned by Bernoulli(keep)."""
+    s = np.frombuffer(seq.encode() if isinstance(seq, str) else bytes(seq), dtype=np.uint8)
+    n = len(s)
+    pair = np.zeros((256, 256), dtype=bool)
+    for a, b in ("AU", "UA", "GC", "CG", "GU", "UG"):
+        pair[ord(a), ord(b)] = True
+    m = pair[s[:, None], s[None, :]]
+    u, v = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    m &= (v - u >= 4) & (v - u < span) & (u < n - 6)
+    if keep is not None:
+        m &= rng.random((n, n)) < keep
+    return pack_mask(m)
+
+
+class HostLibrary:
+    """Parsed + validated motif library (C++ loaders), owner of the flat component table."""
+
+    def __init__(self, handle):
+        self._lib = capi.load()
+        self._h = handle
+
+    @classmethod
+    def load(cls, source, path):
+        lib = capi.load()
+        kind = capi.KIND_OF_SOURCE[source] if isinstance(source, str) else source
+        h = C.c_void_p()
+        _check(lib.bsh_library_load(kind, str(path).encode(), C.byref(h)), host=True)
+        return cls(h)
+
+    @classmethod
+    def from_json_modules(cls, modules):
+        """modules: iterable of (key, sequence, struct2d), in canonical (key-sorted) order."""
+        lib = capi.load()
+        h = C.c_void_p()
+        _check(lib.bsh_library_new(capi.KIND_JSON, C.byref(h)), host=True)
+        for key, seq, ss in modules:
+            lib.bsh_library_add_json(h, key.encode(), seq.encode(), ss.encode())
+        lib.bsh_library_seal(h)
+        return cls(h)
+
+    def close(self):
+        if self._h:
+            self._lib.bsh_library_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_modules(self):
+        return self._lib.bsh_library_modules(self._h)
+
+    @property
+    def n_seen(self):
+        return self._lib.bsh_library_seen(self._h)
+
+    @property
+    def delay(self):
+        return self._lib.bsh_library_delay(self._h)
+
+    def rejected(self):
+        out = []
+        for i in range(self._lib.bsh_library_rejected(self._h)):
+            ident, code = C.c_char_p(), C.c_char()
+            self._lib.bsh_library_reject(self._h, i, C.byref(ident), C.byref(code))
+            out.append((ident.value.decode("utf-8", "replace"), code.value.decode("latin1")))
+        return out
+
+    def module_id(self, m):
+        return self._lib.bsh_library_module_id(self._h, m).decode("utf-8", "replace")
+
+    def module_components(self):
+        return np.array([self._lib.bsh_library_module_components(self._h, m) for m in range(self.n_modules)], dtype=np.int64)
+
+    def raw_table(self):
+        t = capi.BssTable()
+        _check(self._lib.bsh_library_table(self._h, C.byref(t)), host=True)
+        return t
+
+    def table(self):
+        """Flat component table as numpy arrays (copies)."""
+        t = self.raw_table()
+        n_all = t.n_units + t.n_gates
+
+        def arr(ptr, count, dtype):
+            if count == 0:
+                return np.zeros(0, dtype=dtype)
+            return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+
+        ucb = arr(t.unit_comp_begin, n_all + 1, np.uint32)
+        n_comps = int(ucb[-1]) if n_all else 0
+        cpb = arr(t.comp_pat_begin, n_comps + 1, np.uint32)
+        uck = arr(t.unit_check_begin, n_all + 1, np.uint32)
+        n_checks = int(uck[-1]) if n_all else 0
+        return {
+            "n_modules": t.n_modules, "n_units": t.n_units, "n_gates": t.n_gates,
+            "unit_module": arr(t.unit_module, n_all, np.uint32), "unit_delay": arr(t.unit_delay, n_all, np.uint32),
+            "unit_gate": arr(t.unit_gate, t.n_units, np.uint32), "unit_comp_begin": ucb, "comp_pat_begin": cpb,
+            "pattern": arr(t.pattern, int(cpb[-1]) if n_comps else 0, np.uint8), "unit_check_begin": uck,
+            "checks": arr(t.checks, 4 * n_checks, np.int16).reshape(-1, 4),
+        }
+
+    def records_text(self, records):
+        """u32 records -> list of 'identifier\\tcomponents\\tlinks' lines (the oracle's dump format)."""
+        records = np.ascontiguousarray(records, dtype=np.uint32)
+        text, length = C.c_void_p(), C.c_uint64()
+        _check(self._lib.bsh_records_text(self._h, records.ctypes.data_as(C.c_void_p), records.size, C.byref(text), C.byref(length)), host=True)
+        try:
+            s = C.string_at(text, length.value).decode("utf-8", "replace")
+        finally:
+            self._lib.bsh_text_free(text)
+        return s.splitlines()
+
+    def to_device(self, device=-1):
+        h = C.c_void_p()
+        rc = self._lib.bsh_device_library(self._h, device, C.byref(h))
+        if rc != 0:
+            raise SearchError(rc, (self._lib.bsh_last_error() or b"").decode())
+        return DeviceLibrary(h, self)
+
+
+class Query:
+    """Sequences + pair masks resident in device memory."""
+
+    def __init__(self, dev_lib, seqs, masks):
+        lib = capi.load()
+        seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+        self.n_seqs = len(seqs)
+        self.lengths = np.array([len(s) for s in seqs], dtype=np.uint64)
+        self._seq_begin = np.concatenate([[0], np.cumsum(self.lengths)]).astype(np.uint64)
+        self._seqs = np.frombuffer(b"".join(seqs) + b"\0", dtype=np.uint8).copy()
+        masks = [np.ascontiguousarray(m, dtype=np.uint32).reshape(-1) for m in masks]
+        self._mask_begin = np.concatenate([[0], np.cumsum([m.size for m in masks])]).astype(np.uint64)
+        self._masks = np.concatenate(masks + [np.zeros(1, np.uint32)])
+        self.h2d_bytes = int(self._seqs.size - 1 + 4 * (self._masks.size - 1) + 16 * (self.n_seqs + 1))
+        self._lib = lib
+        self._h = C.c_void_p()
+        _check(lib.bss_query_create(dev_lib._h, self.n_seqs, self._seqs.ctypes.data_as(C.c_void_p),
+                                    self._seq_begin.ctypes.data_as(capi.u64p), self._masks.ctypes.data_as(C.c_void_p),
+                                    self._mask_begin.ctypes.data_as(capi.u64p), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.bss_query_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Sites:
+    def __init__(self, handle, n_seqs):
+        self._lib = capi.load()
+        self._h = handle
+        self.n_sites = int(self._lib.bss_sites_count(handle))
+        self.n_words = int(self._lib.bss_sites_words(handle))
+        self.n_seqs = n_seqs
+
+    def records(self):
+        ptr = self._lib.bss_sites_records(self._h)
+        if not ptr or self.n_words == 0:
+            return np.zeros(0, dtype=np.uint32)
+        return np.ctypeslib.as_array(ptr, shape=(self.n_words,)).copy()
+
+    def device_pointer(self):
+        return self._lib.bss_sites_device_records(self._h)
+
+    def seq_word_begin(self):
+        ptr = self._lib.bss_sites_seq_word_begin(self._h)
+        return np.ctypeslib.as_array(ptr, shape=(self.n_seqs + 1,)).copy()
+
+    def close(self):
+        if self._h:
+            self._lib.bss_sites_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceLibrary:
+    """Flat component table resident on one GPU + the search entry points."""
+
+    def __init__(self, handle, host):
+        self._lib = capi.load()
+        self._h = handle
+        self.host = host
+
+    def close(self):
+        if self._h:
+            self._lib.bss_library_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_units(self):
+        return self._lib.bss_library_units(self._h)
+
+    def set_stream(self, cuda_stream):
+        _check(self._lib.bss_library_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def query(self, seqs, masks):
+        return Query(self, seqs, masks)
+
+    def search_query(self, query, fetch=True):
+        h = C.c_void_p()
+        _check(self._lib.bss_search_query(self._h, query._h, 1 if fetch else 0, C.byref(h)))
+        return Sites(h, query.n_seqs)
+
+    def search_query_into(self, query, device_ptr, capacity_words, seq_begin_ptr=None):
+        """Returns (rc, n_words, n_sites); rc == BSS_ERR_OVERFLOW leaves the buffer untouched."""
+        nw, ns = C.c_uint64(), C.c_uint64()
+        rc = self._lib.bss_search_query_into(self._h, query._h, C.c_void_p(device_ptr), capacity_words,
+                                             C.c_void_p(seq_begin_ptr) if seq_begin_ptr else None, C.byref(nw), C.byref(ns))
+        if rc not in (capi.BSS_OK, capi.BSS_ERR_OVERFLOW):
+            _check(rc)
+        return rc, nw.value, ns.value
+
+    def search(self, seq, mask):
+        """One-shot: host sequence + mask in, host records out."""
+        seq = seq.encode() if isinstance(seq, str) else bytes(seq)
+        mask = np.ascontiguousarray(mask, dtype=np.uint32)
+        buf = np.frombuffer(seq + b"\0", dtype=np.uint8)
+        h = C.c_void_p()
+        _check(self._lib.bss_search(self._h, buf.ctypes.data_as(C.c_void_p), len(seq), mask.ctypes.data_as(C.c_void_p), C.byref(h)))
+        return Sites(h, 1)
+
+    def search_batch(self, seqs, masks):
+        seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+        seq_begin = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.uint64)
+        blob = np.frombuffer(b"".join(seqs) + b"\0", dtype=np.uint8)
+        masks = [np.ascontiguousarray(m, dtype=np.uint32).reshape(-1) for m in masks]
+        mask_begin = np.concatenate([[0], np.cumsum([m.size for m in masks])]).astype(np.uint64)
+        allm = np.concatenate(masks + [np.zeros(1, np.uint32)])
+        h = C.c_void_p()
+        _check(self._lib.bss_search_batch(self._h, len(seqs), blob.ctypes.data_as(C.c_void_p), seq_begin.ctypes.data_as(capi.u64p),
+                                          allm.ctypes.data_as(C.c_void_p), mask_begin.ctypes.data_as(capi.u64p), C.byref(h)))
+        return Sites(h, len(seqs))
+
+    def stats(self):
+        s = capi.BssStats()
+        _check(self._lib.bss_last_stats(self._h, C.byref(s)))
+        return {name: getattr(s, name) for name, _ in capi.BssStats._fields_}

@@ -1,0 +1,558 @@
+// C ABI of the insertion-site search (include/biorseo_b200.h): library build, query
+// upload, search orchestration (count -> scan -> emit), result download. No CPU search
+// exists here: without a CUDA device every search entry point fails.
+#include "biorseo_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bss_device.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& what)
+{
+    g_error = what;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where)
+{
+    return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? BSS_ERR_NO_DEVICE : BSS_ERR_CUDA,
+                std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+#define BSS_CUDA(call)                                              \
+    do {                                                            \
+        cudaError_t e_ = (call);                                    \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);         \
+    } while (0)
+
+// Grow-only device / pinned-host buffers.
+struct DeviceBuffer {
+    void*  ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuffer {
+    void*  ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+bool compatible(uint8_t a, uint8_t b) { return a == '.' || b == '.' || a == b; }
+
+// Can two matches of this pattern overlap, i.e. is the pattern compatible with itself at
+// some shift 1..k-1 ?
+bool can_self_overlap(const uint8_t* p, uint32_t k)
+{
+    for (uint32_t s = 1; s < k; s++) {
+        bool ok = true;
+        for (uint32_t j = 0; ok && j + s < k; j++) ok = compatible(p[j], p[j + s]);
+        if (ok) return true;
+    }
+    return false;
+}
+
+}   // namespace
+
+struct bss_library {
+    int          device     = 0;
+    int          sm_count   = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t  ev[4]      = {nullptr, nullptr, nullptr, nullptr};
+    bss::DevLibrary       dev{};
+    DeviceBuffer          d_blob, d_unit_off;
+    uint32_t              n_modules = 0, n_units = 0;
+    std::vector<uint32_t> module_components;
+    // work buffers, reused across searches
+    DeviceBuffer d_counts, d_chunk_sites, d_chunk_words, d_totals, d_seq_word_begin;
+    PinnedBuffer h_totals;
+    // one spare set of result buffers, recycled by bss_sites_free
+    DeviceBuffer spare_records;
+    PinnedBuffer spare_host;
+    bss_stats    stats{};
+};
+
+struct bss_query {
+    int           device = 0;
+    bss::DevQuery dev{};
+    DeviceBuffer  storage;
+    uint64_t      total_len = 0;
+    uint64_t      h2d_bytes = 0;
+};
+
+struct bss_sites {
+    bss_library*          lib = nullptr;
+    uint64_t              n_sites = 0, n_words = 0;
+    DeviceBuffer          d_records;
+    PinnedBuffer          h_records;
+    bool                  fetched = false;
+    std::vector<uint64_t> seq_word_begin;
+};
+
+extern "C" {
+
+int bss_abi_version(void) { return BSS_ABI_VERSION; }
+
+const char* bss_last_error(void) { return g_error.c_str(); }
+
+int bss_device_count(void)
+{
+    int         n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int bss_library_create(const bss_table* t, int device, bss_library** out)
+{
+    if (!t || !out) return fail(BSS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const uint32_t n_all = t->n_units + t->n_gates;
+    if (n_all && (!t->unit_module || !t->unit_delay || !t->unit_comp_begin || !t->comp_pat_begin || !t->unit_check_begin))
+        return fail(BSS_ERR_INVALID, "null table array");
+    if (t->n_units && !t->unit_gate) return fail(BSS_ERR_INVALID, "null unit_gate");
+
+    // alphabet: distinct literal pattern bytes
+    int code_of[256];
+    std::fill(code_of, code_of + 256, -1);
+    std::vector<uint8_t> alphabet;
+    const uint32_t n_comps = n_all ? t->unit_comp_begin[n_all] : 0;
+    const uint32_t n_pat   = n_comps ? t->comp_pat_begin[n_comps] : 0;
+    if (n_pat && !t->pattern) return fail(BSS_ERR_INVALID, "null pattern array");
+    for (uint32_t i = 0; i < n_pat; i++) {
+        const uint8_t b = t->pattern[i];
+        if (b == '.' || code_of[b] >= 0) continue;
+        if (b == '\n' || b == '\r') return fail(BSS_ERR_INVALID, "pattern contains a line terminator");
+        code_of[b] = (int)alphabet.size();
+        alphabet.push_back(b);
+    }
+    if (alphabet.size() > BSS_MAX_ALPHABET) return fail(BSS_ERR_LIMIT, "more than BSS_MAX_ALPHABET distinct pattern bytes");
+
+    // unit descriptors
+    std::vector<uint32_t> blob, unit_off(n_all + 1, 0);
+    std::vector<uint32_t> module_components(t->n_modules, 0);
+    uint32_t              cmax = 1;
+    for (uint32_t u = 0; u < n_all; u++) {
+        unit_off[u] = (uint32_t)blob.size();
+        const uint32_t c0 = t->unit_comp_begin[u], c1 = t->unit_comp_begin[u + 1];
+        const uint32_t k0 = t->unit_check_begin[u], k1 = t->unit_check_begin[u + 1];
+        if (c1 < c0 || k1 < k0) return fail(BSS_ERR_INVALID, "non-monotonic table offsets");
+        const uint32_t C = c1 - c0, NK = k1 - k0;
+        if (C < 1 || C > BSS_MAX_COMPONENTS) return fail(BSS_ERR_LIMIT, "unit with 0 or more than BSS_MAX_COMPONENTS components");
+        if (NK > BSS_MAX_CHECKS) return fail(BSS_ERR_LIMIT, "unit with more than BSS_MAX_CHECKS checks");
+        if (NK && !t->checks) return fail(BSS_ERR_INVALID, "null checks array");
+        if (t->unit_delay[u] > 0xFFFFu) return fail(BSS_ERR_LIMIT, "delay above 65535");
+        if (t->unit_module[u] >= t->n_modules) return fail(BSS_ERR_INVALID, "unit_module out of range");
+        uint32_t gate = bss::kNoGate;
+        if (u < t->n_units) {
+            gate = t->unit_gate[u];
+            if (gate != bss::kNoGate && (gate < t->n_units || gate >= n_all)) return fail(BSS_ERR_INVALID, "unit_gate out of range");
+            uint32_t& mc = module_components[t->unit_module[u]];
+            if (mc != 0 && mc != C) return fail(BSS_ERR_INVALID, "units of one module disagree on the component count");
+            mc = C;
+        }
+        cmax = std::max(cmax, C);
+
+        // order checks by the level at which both ends are known
+        std::vector<uint32_t> order(NK);
+        std::vector<int>      level(NK);
+        for (uint32_t i = 0; i < NK; i++) {
+            const int16_t* c = t->checks + 4 * (size_t)(k0 + i);
+            if (c[0] < -1 || c[0] >= (int)C || c[2] < -1 || c[2] >= (int)C) return fail(BSS_ERR_INVALID, "check anchor out of range");
+            level[i] = std::max(0, std::max((int)c[0], (int)c[2]));
+            order[i] = i;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return level[a] < level[b]; });
+
+        uint32_t pat_total = 0;
+        for (uint32_t c = c0; c < c1; c++) {
+            const uint32_t k = t->comp_pat_begin[c + 1] - t->comp_pat_begin[c];
+            if (t->comp_pat_begin[c + 1] < t->comp_pat_begin[c] || k > BSS_MAX_PATTERN) return fail(BSS_ERR_LIMIT, "component pattern longer than BSS_MAX_PATTERN");
+            pat_total += k;
+        }
+        const uint32_t pat_words = (pat_total + 3) / 4;
+        const uint32_t head      = 4 + 2 * C;
+        const size_t   base      = blob.size();
+        blob.resize(base + head + pat_words + 2 * (size_t)NK, 0);
+        uint32_t* b  = blob.data() + base;
+        const uint8_t* p0 = t->pattern + t->comp_pat_begin[c0];
+        const uint32_t kfirst = t->comp_pat_begin[c0 + 1] - t->comp_pat_begin[c0];
+        b[0] = t->unit_module[u];
+        b[1] = C | (NK << 8) | (t->unit_delay[u] << 16);
+        b[2] = gate;
+        b[3] = (can_self_overlap(p0, kfirst) ? 1u : 0u) | ((head + pat_words) << 16);
+        uint8_t* pat_bytes = reinterpret_cast<uint8_t*>(b + head);
+        uint32_t byte_off  = 0, next_check = 0;
+        for (uint32_t c = 0; c < C; c++) {
+            const uint32_t pb = t->comp_pat_begin[c0 + c], k = t->comp_pat_begin[c0 + c + 1] - pb;
+            b[4 + 2 * c] = k | ((head * 4 + byte_off) << 8);
+            for (uint32_t j = 0; j < k; j++) {
+                const uint8_t ch = t->pattern[pb + j];
+                pat_bytes[byte_off + j] = ch == '.' ? (uint8_t)bss::kWildcard : (uint8_t)code_of[ch];
+            }
+            byte_off += k;
+            const uint32_t begin = next_check;
+            while (next_check < NK && level[order[next_check]] == (int)c) next_check++;
+            b[5 + 2 * c] = begin | (next_check << 8);
+        }
+        uint32_t* chk = b + head + pat_words;
+        for (uint32_t i = 0; i < NK; i++) {
+            const int16_t* c = t->checks + 4 * (size_t)(k0 + order[i]);
+            chk[2 * i]     = ((uint32_t)(uint8_t)(int8_t)c[0]) | (((uint32_t)(uint16_t)c[1]) << 8);
+            chk[2 * i + 1] = ((uint32_t)(uint8_t)(int8_t)c[2]) | (((uint32_t)(uint16_t)c[3]) << 8);
+        }
+        if (blob.size() > 0x7FFFFFFFu) return fail(BSS_ERR_LIMIT, "library too large");
+    }
+    unit_off[n_all] = (uint32_t)blob.size();
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BSS_ERR_NO_DEVICE, "no CUDA device: the insertion-site search has no CPU path");
+    }
+    if (device < 0) BSS_CUDA(cudaGetDevice(&device));
+    if (device >= ndev) return fail(BSS_ERR_INVALID, "device index out of range");
+    BSS_CUDA(cudaSetDevice(device));
+
+    bss_library* lib = new bss_library();
+    lib->device      = device;
+    lib->n_modules   = t->n_modules;
+    lib->n_units     = t->n_units;
+    lib->module_components = module_components;
+    auto bail = [&](int code) { bss_library_destroy(lib); return code; };
+#define BSS_CUDA_LIB(call)                                                   \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) return bail(cuda_fail(e_, #call));            \
+    } while (0)
+    BSS_CUDA_LIB(cudaDeviceGetAttribute(&lib->sm_count, cudaDevAttrMultiProcessorCount, device));
+    BSS_CUDA_LIB(cudaStreamCreateWithFlags(&lib->own_stream, cudaStreamNonBlocking));
+    lib->stream = lib->own_stream;
+    for (auto& ev : lib->ev) BSS_CUDA_LIB(cudaEventCreate(&ev));
+    BSS_CUDA_LIB(lib->d_blob.reserve(std::max<size_t>(4, blob.size() * 4)));
+    BSS_CUDA_LIB(lib->d_unit_off.reserve(unit_off.size() * 4));
+    if (!blob.empty()) BSS_CUDA_LIB(cudaMemcpy(lib->d_blob.ptr, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+    BSS_CUDA_LIB(cudaMemcpy(lib->d_unit_off.ptr, unit_off.data(), unit_off.size() * 4, cudaMemcpyHostToDevice));
+    BSS_CUDA_LIB(lib->h_totals.reserve(64));
+    BSS_CUDA_LIB(lib->d_totals.reserve(64));
+#undef BSS_CUDA_LIB
+    lib->dev.blob      = static_cast<const uint32_t*>(lib->d_blob.ptr);
+    lib->dev.unit_off  = static_cast<const uint32_t*>(lib->d_unit_off.ptr);
+    lib->dev.n_units   = t->n_units;
+    lib->dev.n_symbols = (uint32_t)alphabet.size();
+    lib->dev.cmax      = cmax;
+    std::memset(lib->dev.alphabet, 0, sizeof lib->dev.alphabet);
+    std::copy(alphabet.begin(), alphabet.end(), lib->dev.alphabet);
+    *out = lib;
+    return BSS_OK;
+}
+
+void bss_library_destroy(bss_library* lib)
+{
+    if (!lib) return;
+    cudaSetDevice(lib->device);
+    if (lib->own_stream) cudaStreamSynchronize(lib->own_stream);
+    for (auto& ev : lib->ev)
+        if (ev) cudaEventDestroy(ev);
+    lib->d_blob.release(); lib->d_unit_off.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
+    lib->d_chunk_words.release(); lib->d_totals.release(); lib->d_seq_word_begin.release(); lib->h_totals.release();
+    lib->spare_records.release(); lib->spare_host.release();
+    if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
+    delete lib;
+}
+
+int bss_library_set_stream(bss_library* lib, void* cuda_stream)
+{
+    if (!lib) return fail(BSS_ERR_INVALID, "null library");
+    lib->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : lib->own_stream;
+    return BSS_OK;
+}
+
+uint32_t bss_library_units(const bss_library* lib) { return lib ? lib->n_units : 0; }
+uint32_t bss_library_modules(const bss_library* lib) { return lib ? lib->n_modules : 0; }
+uint32_t bss_library_module_components(const bss_library* lib, uint32_t module)
+{
+    return (lib && module < lib->module_components.size()) ? lib->module_components[module] : 0;
+}
+
+int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
+                     const uint64_t* mask_begin, bss_query** out)
+{
+    if (!lib || !out || !seq_begin || !mask_begin || (n_seqs && (!seqs || !masks))) return fail(BSS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    uint32_t max_len = 0;
+    for (uint32_t q = 0; q < n_seqs; q++) {
+        if (seq_begin[q + 1] < seq_begin[q] || mask_begin[q + 1] < mask_begin[q]) return fail(BSS_ERR_INVALID, "non-monotonic offsets");
+        const uint64_t n = seq_begin[q + 1] - seq_begin[q];
+        if (n > BSS_MAX_SEQ_LEN) return fail(BSS_ERR_LIMIT, "sequence longer than BSS_MAX_SEQ_LEN");
+        if (mask_begin[q + 1] - mask_begin[q] != n * ((n + 31) / 32)) return fail(BSS_ERR_INVALID, "pair mask is not n rows of ceil(n/32) words");
+        max_len = std::max<uint32_t>(max_len, (uint32_t)n);
+    }
+    const uint64_t total_len = n_seqs ? seq_begin[n_seqs] - seq_begin[0] : 0, total_mask = n_seqs ? mask_begin[n_seqs] - mask_begin[0] : 0;
+    const char* s0 = seqs + (n_seqs ? seq_begin[0] : 0);
+    if (std::memchr(s0, '\n', total_len) || std::memchr(s0, '\r', total_len))
+        return fail(BSS_ERR_BAD_SEQUENCE, "query contains a line terminator");
+
+    BSS_CUDA(cudaSetDevice(lib->device));
+    bss_query* q = new bss_query();
+    q->device    = lib->device;
+    // one allocation: [seq_begin | mask_begin | masks | seqs]
+    const size_t off_sb = 0, off_mb = off_sb + 8 * (size_t)(n_seqs + 1), off_mask = off_mb + 8 * (size_t)(n_seqs + 1),
+                 off_seq = off_mask + 4 * total_mask, bytes = off_seq + total_len + 16;
+    cudaError_t e = q->storage.reserve(bytes);
+    if (e != cudaSuccess) { delete q; return cuda_fail(e, "cudaMalloc(query)"); }
+    char* d = static_cast<char*>(q->storage.ptr);
+    std::vector<uint64_t> sb(n_seqs + 1), mb(n_seqs + 1);
+    for (uint32_t i = 0; i <= n_seqs; i++) { sb[i] = seq_begin[i] - seq_begin[0]; mb[i] = mask_begin[i] - mask_begin[0]; }
+    cudaStream_t st = lib->stream;
+    e = cudaMemcpyAsync(d + off_sb, sb.data(), 8 * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_mb, mb.data(), 8 * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && total_mask) e = cudaMemcpyAsync(d + off_mask, masks + mask_begin[0], 4 * total_mask, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && total_len) e = cudaMemcpyAsync(d + off_seq, s0, total_len, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // sb / mb are stack-owned staging
+    if (e != cudaSuccess) { q->storage.release(); delete q; return cuda_fail(e, "query upload"); }
+    q->dev.seq_begin  = reinterpret_cast<const uint64_t*>(d + off_sb);
+    q->dev.mask_begin = reinterpret_cast<const uint64_t*>(d + off_mb);
+    q->dev.masks      = reinterpret_cast<const uint32_t*>(d + off_mask);
+    q->dev.seqs       = reinterpret_cast<const uint8_t*>(d + off_seq);
+    q->dev.n_seqs     = n_seqs;
+    q->dev.max_len    = max_len;
+    q->total_len      = total_len;
+    q->h2d_bytes      = 16 * (uint64_t)(n_seqs + 1) + 4 * total_mask + total_len;
+    *out = q;
+    return BSS_OK;
+}
+
+void bss_query_destroy(bss_query* q)
+{
+    if (!q) return;
+    cudaSetDevice(q->device);
+    q->storage.release();
+    delete q;
+}
+
+}   // extern "C"
+
+namespace {
+
+// count + scan, then the totals come back to the host. On success `plan` and `work` describe
+// the pending emit.
+int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work, uint64_t& n_words, uint64_t& n_sites)
+{
+    BSS_CUDA(cudaSetDevice(lib->device));
+    plan = bss::make_plan(lib->dev, q->dev.n_seqs, q->dev.max_len, lib->sm_count);
+    if (plan.smem_bytes > 200 * 1024) return fail(BSS_ERR_LIMIT, "query too long for the shared-memory working set");
+    const uint64_t n_items = (uint64_t)q->dev.n_seqs * lib->n_units;
+    BSS_CUDA(lib->d_counts.reserve(std::max<uint64_t>(4, n_items * 4)));
+    BSS_CUDA(lib->d_chunk_sites.reserve(8 * (size_t)(plan.n_chunks + 1)));
+    BSS_CUDA(lib->d_chunk_words.reserve(8 * (size_t)(plan.n_chunks + 1)));
+    BSS_CUDA(lib->d_seq_word_begin.reserve(8 * (size_t)(q->dev.n_seqs + 1)));
+    work.counts         = static_cast<uint32_t*>(lib->d_counts.ptr);
+    work.chunk_sites    = static_cast<uint64_t*>(lib->d_chunk_sites.ptr);
+    work.chunk_words    = static_cast<uint64_t*>(lib->d_chunk_words.ptr);
+    work.totals         = static_cast<uint64_t*>(lib->d_totals.ptr);
+    work.seq_word_begin = static_cast<uint64_t*>(lib->d_seq_word_begin.ptr);
+    cudaStream_t st = lib->stream;
+    lib->stats      = bss_stats{};
+    BSS_CUDA(cudaMemsetAsync(work.totals, 0, 32, st));
+    BSS_CUDA(cudaMemsetAsync(work.seq_word_begin, 0, 8 * (size_t)(q->dev.n_seqs + 1), st));
+    BSS_CUDA(cudaEventRecord(lib->ev[0], st));
+    BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, st));
+    BSS_CUDA(cudaEventRecord(lib->ev[1], st));
+    BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));
+    BSS_CUDA(cudaEventRecord(lib->ev[2], st));
+    BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 24, cudaMemcpyDeviceToHost, st));
+    BSS_CUDA(cudaStreamSynchronize(st));
+    const uint64_t* tot = static_cast<const uint64_t*>(lib->h_totals.ptr);
+    n_words             = tot[0];
+    n_sites             = tot[1];
+    lib->stats.kernel_launches   = (plan.n_chunks ? 1u : 0u) + 1u;
+    lib->stats.placements_tested = q->total_len * lib->n_units;
+    lib->stats.n_sites           = n_sites;
+    lib->stats.n_words           = n_words;
+    lib->stats.d2h_bytes         = 24;
+    if (tot[2] & 1) return fail(BSS_ERR_COUNT, "a unit has 2^32 or more sites on one sequence");
+    return BSS_OK;
+}
+
+int run_emit(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, uint32_t* d_records, uint64_t n_words)
+{
+    cudaStream_t st = lib->stream;
+    if (n_words && plan.n_chunks) {
+        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, st));
+        lib->stats.kernel_launches++;
+    }
+    BSS_CUDA(cudaEventRecord(lib->ev[3], st));
+    return BSS_OK;
+}
+
+int finish_stats(bss_library* lib)
+{
+    BSS_CUDA(cudaEventSynchronize(lib->ev[3]));
+    cudaEventElapsedTime(&lib->stats.count_ms, lib->ev[0], lib->ev[1]);
+    cudaEventElapsedTime(&lib->stats.scan_ms, lib->ev[1], lib->ev[2]);
+    cudaEventElapsedTime(&lib->stats.emit_ms, lib->ev[2], lib->ev[3]);
+    cudaEventElapsedTime(&lib->stats.total_ms, lib->ev[0], lib->ev[3]);
+    return BSS_OK;
+}
+
+}   // namespace
+
+extern "C" {
+
+int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites** out)
+{
+    if (!lib || !q || !out) return fail(BSS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (q->device != lib->device) return fail(BSS_ERR_INVALID, "query and library live on different devices");
+    bss::Plan plan;
+    bss::Work work;
+    uint64_t  n_words = 0, n_sites = 0;
+    int       rc = run_count(lib, q, plan, work, n_words, n_sites);
+    if (rc != BSS_OK) return rc;
+
+    bss_sites* s = new bss_sites();
+    s->lib       = lib;
+    s->n_words   = n_words;
+    s->n_sites   = n_sites;
+    std::swap(s->d_records, lib->spare_records);
+    std::swap(s->h_records, lib->spare_host);
+    auto bail = [&](int code) { bss_sites_free(s); return code; };
+    cudaError_t e = s->d_records.reserve(std::max<uint64_t>(16, n_words * 4));
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(records)"));
+    rc = run_emit(lib, q, plan, work, static_cast<uint32_t*>(s->d_records.ptr), n_words);
+    if (rc != BSS_OK) return bail(rc);
+    s->seq_word_begin.assign(q->dev.n_seqs + 1, 0);
+    cudaStream_t st = lib->stream;
+    if (fetch) {
+        e = s->h_records.reserve(std::max<uint64_t>(16, n_words * 4));
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost(records)"));
+        if (n_words) e = cudaMemcpyAsync(s->h_records.ptr, s->d_records.ptr, n_words * 4, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "records download"));
+        s->fetched = true;
+        lib->stats.d2h_bytes += n_words * 4;
+    }
+    e = cudaMemcpyAsync(s->seq_word_begin.data(), work.seq_word_begin, 8 * (size_t)(q->dev.n_seqs + 1), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "result download"));
+    lib->stats.d2h_bytes += 8 * (uint64_t)(q->dev.n_seqs + 1);
+    rc = finish_stats(lib);
+    if (rc != BSS_OK) return bail(rc);
+    *out = s;
+    return BSS_OK;
+}
+
+int bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_records, uint64_t capacity_words,
+                          uint64_t* d_seq_word_begin, uint64_t* n_words_out, uint64_t* n_sites_out)
+{
+    if (!lib || !q || !n_words_out || !n_sites_out) return fail(BSS_ERR_INVALID, "null argument");
+    if (q->device != lib->device) return fail(BSS_ERR_INVALID, "query and library live on different devices");
+    bss::Plan plan;
+    bss::Work work;
+    uint64_t  n_words = 0, n_sites = 0;
+    int       rc = run_count(lib, q, plan, work, n_words, n_sites);
+    *n_words_out = n_words;
+    *n_sites_out = n_sites;
+    if (rc != BSS_OK) return rc;
+    if (n_words > capacity_words || (n_words && !d_records)) return fail(BSS_ERR_OVERFLOW, "output buffer too small");
+    rc = run_emit(lib, q, plan, work, d_records, n_words);
+    if (rc != BSS_OK) return rc;
+    if (d_seq_word_begin)
+        BSS_CUDA(cudaMemcpyAsync(d_seq_word_begin, work.seq_word_begin, 8 * (size_t)(q->dev.n_seqs + 1), cudaMemcpyDeviceToDevice, lib->stream));
+    BSS_CUDA(cudaStreamSynchronize(lib->stream));
+    return finish_stats(lib);
+}
+
+int bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
+                     const uint64_t* mask_begin, bss_sites** out)
+{
+    if (!out) return fail(BSS_ERR_INVALID, "null argument");
+    *out         = nullptr;
+    bss_query* q = nullptr;
+    int        rc = bss_query_create(lib, n_seqs, seqs, seq_begin, masks, mask_begin, &q);
+    if (rc != BSS_OK) return rc;
+    rc = bss_search_query(lib, q, 1, out);
+    if (rc == BSS_OK) lib->stats.h2d_bytes = q->h2d_bytes;
+    bss_query_destroy(q);
+    return rc;
+}
+
+int bss_search(bss_library* lib, const char* seq, uint32_t n, const uint32_t* mask, bss_sites** out)
+{
+    const uint64_t seq_begin[2]  = {0, n};
+    const uint64_t mask_begin[2] = {0, (uint64_t)n * ((n + 31) / 32)};
+    return bss_search_batch(lib, 1, seq, seq_begin, mask, mask_begin, out);
+}
+
+uint64_t        bss_sites_count(const bss_sites* s) { return s ? s->n_sites : 0; }
+uint64_t        bss_sites_words(const bss_sites* s) { return s ? s->n_words : 0; }
+const uint32_t* bss_sites_records(const bss_sites* s) { return (s && s->fetched) ? static_cast<const uint32_t*>(s->h_records.ptr) : nullptr; }
+const uint32_t* bss_sites_device_records(const bss_sites* s) { return s ? static_cast<const uint32_t*>(s->d_records.ptr) : nullptr; }
+const uint64_t* bss_sites_seq_word_begin(const bss_sites* s) { return s ? s->seq_word_begin.data() : nullptr; }
+
+void bss_sites_free(bss_sites* s)
+{
+    if (!s) return;
+    if (s->lib) {
+        cudaSetDevice(s->lib->device);
+        // keep the largest buffers around for the next search
+        if (s->d_records.cap > s->lib->spare_records.cap) std::swap(s->d_records, s->lib->spare_records);
+        if (s->h_records.cap > s->lib->spare_host.cap) std::swap(s->h_records, s->lib->spare_host);
+    }
+    s->d_records.release();
+    s->h_records.release();
+    delete s;
+}
+
+int bss_last_stats(const bss_library* lib, bss_stats* out)
+{
+    if (!lib || !out) return fail(BSS_ERR_INVALID, "null argument");
+    *out = lib->stats;
+    return BSS_OK;
+}
+
+}   // extern "C"

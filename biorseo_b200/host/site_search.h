@@ -1,0 +1,50 @@
+// Drop-in for the library branches of the reference's MOIP constructor
+// (cppsrc/MOIP.cpp:146-296): "read the query, the allowed_basepair predicate, the library
+// path and Motif::delay; fill insertion_sites_". The module library is parsed once, compiled
+// into a flat device table, and every (module, placement) is searched on the GPU through
+// the C ABI in include/biorseo_b200.h. See INTEGRATION.md for the patch to MOIP.cpp.
+#ifndef BIORSEO_B200_SITE_SEARCH_H_
+#define BIORSEO_B200_SITE_SEARCH_H_
+
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "Motif.h"
+#include "module_library.h"
+
+namespace bsh {
+
+// Packs allowed(u, v), u < v, into n rows of ceil(n/32) words (bit v of row u). The
+// predicate is the reference's MOIP::allowed_basepair (cppsrc/MOIP.cpp:896-910).
+std::vector<uint32_t> build_pair_mask(size_t n, const std::function<bool(size_t, size_t)>& allowed);
+
+class InsertionSiteSearch
+{
+  public:
+    InsertionSiteSearch() {}
+    ~InsertionSiteSearch();
+    InsertionSiteSearch(const InsertionSiteSearch&) = delete;
+    InsertionSiteSearch& operator=(const InsertionSiteSearch&) = delete;
+
+    // `source` is the reference's "jsonfolder" | "rinfolder" | "descfolder"
+    // (cppsrc/biorseo.cpp:150-165). Also sets Motif::delay like the reference's main().
+    bool open(const std::string& source, const std::string& source_path, int device, std::string& err);
+
+    // Appends every insertion site of the library on `seq` to `sites`, in canonical
+    // (module, placement) order. There is no CPU fallback: fails when no GPU is usable.
+    bool run(const std::string& seq, const std::vector<uint32_t>& pair_mask, std::vector<Motif>& sites, std::string& err);
+    bool run(const std::string& seq, const std::function<bool(size_t, size_t)>& allowed, std::vector<Motif>& sites, std::string& err)
+    {
+        return run(seq, build_pair_mask(seq.size(), allowed), sites, err);
+    }
+
+    const ModuleLibrary& library() const { return library_; }
+
+  private:
+    ModuleLibrary library_;
+    bss_library*  device_library_ = nullptr;
+};
+
+}   // namespace bsh
+#endif

@@ -1,0 +1,174 @@
+/*
+ * biorseo_b200.h — C ABI of the B200 insertion-site search.
+ *
+ * This is the drop-in boundary for ONE path of persalteas/biorseo: the motif
+ * insertion-site search that runs inside the MOIP constructor
+ * (reference cppsrc/MOIP.cpp:146-296 dispatch, :912-1213 per-module jobs,
+ * cppsrc/Motif.cpp:432-494 placement enumerator). The reference has no FFI for this
+ * path; the seam is "sequence + allowed_basepair + module library in, insertion sites
+ * out". Everything below is plain C: pointers, sizes, status codes. No C++ or torch
+ * types cross this boundary, nothing throws, nothing calls exit().
+ *
+ * There is no CPU implementation behind these entry points: every bss_search* call runs
+ * hand-written sm_100a CUDA kernels and fails with BSS_ERR_NO_DEVICE / BSS_ERR_CUDA when
+ * no usable GPU is present.
+ *
+ * Vocabulary
+ *   module   one entry of a motif library (a JSON entry, a CaRNAval RIN file, a .desc file)
+ *   unit     one searchable pattern set of a module. JSON/RIN: exactly one per module.
+ *            DESC: one per "variant" produced by widening short components
+ *            (cppsrc/MOIP.cpp:966-1058).
+ *   component one strand of a unit: a byte pattern, '.' matching any byte
+ *            (cppsrc/Motif.cpp:438: the pattern is compiled as a regex of literals and dots).
+ *   check    one base-pair compatibility test between two positions derived from a
+ *            placement (JSON/RIN links, DESC closing pairs; cppsrc/MOIP.cpp:1072-1079,
+ *            1131-1137, 1194-1205).
+ *   site     one surviving placement: (module, start of every component).
+ */
+#ifndef BIORSEO_B200_H_
+#define BIORSEO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSS_ABI_VERSION 1
+
+/* ---- status codes (0 = success, negative = failure) ---- */
+#define BSS_OK                 0
+#define BSS_ERR_INVALID      (-1)  /* NULL / malformed argument or table                              */
+#define BSS_ERR_NO_DEVICE    (-2)  /* no CUDA device: this library has no CPU path                    */
+#define BSS_ERR_CUDA         (-3)  /* CUDA runtime failure, see bss_last_error()                      */
+#define BSS_ERR_LIMIT        (-4)  /* table or query exceeds a documented limit (BSS_MAX_*)            */
+#define BSS_ERR_BAD_SEQUENCE (-5)  /* query contains '\n' or '\r' (regex '.' would not match them)     */
+#define BSS_ERR_OVERFLOW     (-6)  /* caller-provided output too small; required size is reported      */
+#define BSS_ERR_COUNT        (-7)  /* one unit has >= 2^32 sites on one sequence                       */
+
+/* ---- documented limits ---- */
+#define BSS_MAX_COMPONENTS   16    /* components per unit                                              */
+#define BSS_MAX_PATTERN     255    /* bytes per component pattern                                      */
+#define BSS_MAX_CHECKS      255    /* checks per unit                                                  */
+#define BSS_MAX_ALPHABET     32    /* distinct literal pattern bytes per library                       */
+#define BSS_MAX_SEQ_LEN   16000    /* query length in bytes                                            */
+#define BSS_ANCHOR_ABSOLUTE (-1)   /* check endpoint that is a fixed sequence position                 */
+
+/*
+ * Flat component table: what the host loaders (JSON / RIN / DESC parsers + validators,
+ * reference cppsrc/Motif.cpp:218-385, cppsrc/MOIP.cpp:932-1066,1108-1122,1158-1172) hand
+ * to the device. All arrays are caller-owned host memory, read once by bss_library_create.
+ *
+ * Units [0, n_units) are searched and emit sites. Units [n_units, n_units + n_gates) are
+ * "gates": pattern-only units that emit nothing; a searched unit whose unit_gate names one
+ * is skipped on a sequence where the gate has no placement at all (the regex pre-filter
+ * is_desc_insertible, cppsrc/Motif.cpp:387-430).
+ *
+ * Placement semantics (cppsrc/Motif.cpp:432-494): component c, of length k_c, is placed at
+ * p_c; p_0 runs over the leftmost non-overlapping matches of pattern 0 from position 0, and
+ * p_{c+1} over the leftmost non-overlapping matches of pattern c+1 in the suffix that starts
+ * at p_c + k_c - 1 + delay, which must start inside the sequence. A zero-length pattern
+ * matches at every position 0..n.
+ *
+ * A check (a_anchor, a_off, b_anchor, b_off) passes when allowed(u, v) with
+ * u = p[a_anchor] + a_off (or just a_off when a_anchor == BSS_ANCHOR_ABSOLUTE), v likewise;
+ * allowed(u, v) = both inside [0, n) and mask bit (min, max) set. A site is emitted when all
+ * checks of its unit pass.
+ */
+typedef struct bss_table {
+    uint32_t        n_modules;        /* number of library modules that own units                   */
+    uint32_t        n_units;          /* searched units                                             */
+    uint32_t        n_gates;          /* gate units, stored after the searched ones                 */
+    const uint32_t* unit_module;      /* [n_units + n_gates] module index written into each site    */
+    const uint32_t* unit_delay;       /* [n_units + n_gates] Motif::delay for this unit             */
+    const uint32_t* unit_gate;        /* [n_units] index of the gate unit, or UINT32_MAX            */
+    const uint32_t* unit_comp_begin;  /* [n_units + n_gates + 1] first component of each unit       */
+    const uint32_t* comp_pat_begin;   /* [n_components + 1] first pattern byte of each component    */
+    const uint8_t*  pattern;          /* pattern bytes; '.' is the wildcard                         */
+    const uint32_t* unit_check_begin; /* [n_units + n_gates + 1] first check of each unit           */
+    const int16_t*  checks;           /* [n_checks][4] = a_anchor, a_off, b_anchor, b_off           */
+} bss_table;
+
+/* Opaque handles. A library owns device memory, one CUDA stream and growable work
+ * buffers; it is immutable after creation and is used by one host thread at a time
+ * (the reference calls this path once, from the main thread: cppsrc/biorseo.cpp:175). */
+typedef struct bss_library bss_library;
+typedef struct bss_query   bss_query;   /* sequences + pair masks resident in device memory */
+typedef struct bss_sites   bss_sites;   /* one search result                                */
+
+typedef struct bss_stats {
+    uint64_t placements_tested;   /* sum over (sequence, unit) of sequence length              */
+    uint64_t n_sites;             /* sites emitted                                             */
+    uint64_t n_words;             /* u32 words emitted                                         */
+    uint64_t h2d_bytes;           /* bytes copied host->device by the last call                */
+    uint64_t d2h_bytes;           /* bytes copied device->host by the last call                */
+    uint32_t kernel_launches;     /* kernels launched by the last search                       */
+    float    count_ms;            /* device time of the match+count kernel (CUDA events)       */
+    float    scan_ms;             /* device time of the offset scan kernel                     */
+    float    emit_ms;             /* device time of the emit kernel                            */
+    float    total_ms;            /* first launch to last kernel end                           */
+} bss_stats;
+
+/* ---- library ---- */
+/* device < 0 selects the current CUDA device. Replaces: the per-run library walk +
+ * per-module job construction of cppsrc/MOIP.cpp:159-188, 211-234, 259-288. */
+int  bss_library_create(const bss_table* table, int device, bss_library** out);
+void bss_library_destroy(bss_library* lib);
+/* Use an externally owned stream (e.g. the caller's current stream) instead of the
+ * library's own; pass NULL to return to the internal stream. */
+int  bss_library_set_stream(bss_library* lib, void* cuda_stream);
+uint32_t bss_library_units(const bss_library* lib);
+uint32_t bss_library_modules(const bss_library* lib);
+/* Number of components of the units of `module` (identical for all its units). */
+uint32_t bss_library_module_components(const bss_library* lib, uint32_t module);
+
+/* ---- queries ---- */
+/* n_seqs sequences, concatenated in `seqs`; sequence q occupies
+ * [seq_begin[q], seq_begin[q+1]). Its pair mask is n_q rows of ceil(n_q/32) little-endian
+ * u32 words at masks + mask_begin[q]; bit v of row u (u < v) set means the reference's
+ * allowed_basepair(u, v) holds (cppsrc/MOIP.cpp:896-910; theta, the v-u >= 4 and u < n-6
+ * rules are already applied by the caller's loop cppsrc/MOIP.cpp:77-90). Bits on or below
+ * the diagonal are ignored. Copies everything to the device. */
+int  bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin,
+                      const uint32_t* masks, const uint64_t* mask_begin, bss_query** out);
+void bss_query_destroy(bss_query* q);
+
+/* ---- search ---- */
+/* Replaces Pool + MOIP::allowed_motifs_from_{desc,rin,json} + find_next_ones_in for every
+ * (sequence, unit). Sites come back in canonical order (sequence, unit, depth-first
+ * placement order) as u32 records [module, p_0 .. p_{C-1}]. */
+
+/* Search a resident query. fetch != 0 also copies the records to pinned host memory
+ * (bss_sites_records); fetch == 0 leaves them on the device (bss_sites_device_records). */
+int  bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites** out);
+
+/* Search a resident query into caller-owned DEVICE memory (e.g. a tensor that will feed an
+ * NCCL all-gather). On BSS_ERR_OVERFLOW nothing is written and *n_words holds the size needed.
+ * d_seq_word_begin may be NULL, else receives n_seqs + 1 u64 word offsets (device memory). */
+int  bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_records, uint64_t capacity_words,
+                           uint64_t* d_seq_word_begin, uint64_t* n_words, uint64_t* n_sites);
+
+/* One-shot, host buffers in, host records out: upload, search, download. */
+int  bss_search(bss_library* lib, const char* seq, uint32_t n, const uint32_t* mask, bss_sites** out);
+int  bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin,
+                      const uint32_t* masks, const uint64_t* mask_begin, bss_sites** out);
+
+/* ---- results ---- */
+uint64_t        bss_sites_count(const bss_sites* s);
+uint64_t        bss_sites_words(const bss_sites* s);
+const uint32_t* bss_sites_records(const bss_sites* s);         /* pinned host memory or NULL   */
+const uint32_t* bss_sites_device_records(const bss_sites* s);  /* device memory                */
+const uint64_t* bss_sites_seq_word_begin(const bss_sites* s);  /* [n_seqs + 1] host            */
+void            bss_sites_free(bss_sites* s);
+
+/* ---- diagnostics ---- */
+int         bss_last_stats(const bss_library* lib, bss_stats* out);
+const char* bss_last_error(void);   /* thread-local, never NULL */
+int         bss_abi_version(void);
+int         bss_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIORSEO_B200_H_ */

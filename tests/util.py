@@ -1,0 +1,57 @@
+"""Shared helpers of the test-suite: run the oracles, write inputs, compare site lists."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "biorseo_ref")      # the reference's own code
+PORT_BIN = os.path.join(ROOT, "oracle", "_build", "biorseo_port")  # plain C++ restatement
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def have_ref():
+    return os.access(REF_BIN, os.X_OK)
+
+
+def have_port():
+    return os.access(PORT_BIN, os.X_OK)
+
+
+def write_query(folder, seq, mask):
+    seq_path = os.path.join(folder, "seq.txt")
+    mask_path = os.path.join(folder, "mask.bin")
+    with open(seq_path, "wb") as f:
+        f.write(seq.encode() if isinstance(seq, str) else bytes(seq))
+        f.write(b"\n")
+    np.ascontiguousarray(mask, dtype="<u4").tofile(mask_path)
+    return seq_path, mask_path
+
+
+def run_oracle(binary, mode, source, library, seq, mask, threads=2, timeout=600):
+    """Runs an oracle CLI; returns its dump as a sorted list of lines (a multiset of sites)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        seq_path, mask_path = write_query(tmp, seq, mask)
+        cmd = [binary, mode, source, str(library), seq_path, mask_path]
+        if mode == "jobs":
+            cmd.append(str(threads))
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    if res.returncode != 0:
+        raise RuntimeError(f"{' '.join(cmd)} failed ({res.returncode}): {res.stderr[-2000:]}")
+    return sorted(line for line in res.stdout.split("\n") if line)
+
+
+def run_ref(source, library, seq, mask, mode="jobs"):
+    return run_oracle(REF_BIN, mode, source, library, seq, mask)
+
+
+def run_port(source, library, seq, mask):
+    return run_oracle(PORT_BIN, "jobs", source, library, seq, mask)
+
+
+def best_oracle(source, library, seq, mask):
+    """The reference binary when present, else the port."""
+    if have_ref():
+        return run_ref(source, library, seq, mask)
+    return run_port(source, library, seq, mask)
