@@ -138,8 +138,10 @@ def json_fuzz_modules(n_modules, seed):
     for i in range(n_modules):
         n_strands = int(rng.integers(1, 5))
         lengths = [int(rng.integers(1, 7)) for _ in range(n_strands)]
-        if rng.random() < 0.08:
-            lengths[int(rng.integers(0, n_strands))] = 0
+        if rng.random() < 0.08 and n_strands > 1:
+            # an empty strand, but never the last one: a trailing '&' is dropped by the reference's
+            # splitter while struct2d keeps it, and the reference then reads out of bounds
+            lengths[int(rng.integers(0, n_strands - 1))] = 0
         total = sum(lengths)
         alphabet = "ACGU" if rng.random() < 0.8 else "ACGUTacgut"
         nts = "".join(alphabet[j] for j in rng.integers(0, len(alphabet), total))
@@ -175,7 +177,8 @@ def json_fuzz_modules(n_modules, seed):
             seq = seq + "X"               # 'x' (length mismatch)
         elif r < 0.18 and len(seq) > 0:
             j = int(rng.integers(0, len(seq)))
-            seq = seq[:j] + "N" + seq[j + 1:]   # 'r' unless it hit a '&' (then lengths differ in strands only)
+            if seq[j] != "&":
+                seq = seq[:j] + "N" + seq[j + 1:]   # 'r'
         elif r < 0.22 and len(st) > 0:
             j = int(rng.integers(0, len(st)))
             st = st[:j] + ")" + st[j + 1:]      # usually 'n'

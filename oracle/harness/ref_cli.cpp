@@ -12,6 +12,8 @@
 //       runs only the search: the per-module jobs MOIP::allowed_motifs_from_{json,rin,desc}
 //       (cppsrc/MOIP.cpp:912-1213) on the reference's Pool, dispatched the way
 //       cppsrc/MOIP.cpp:146-296 does, and dumps insertion_sites_.
+//   biorseo_ref fno   <delay> <seq> <component>...
+//       the placement enumerator find_next_ones_in (cppsrc/Motif.cpp:432-494) alone.
 //   biorseo_ref bench <source> <library> <seqfile> <maskfile> <threads> <repeat> [max_modules]
 //       as `jobs`, timed from the first Pool::push to the last join (validation, JSON parse
 //       and directory walk excluded), prints one JSON line.
@@ -145,8 +147,24 @@ static double run_jobs(Dispatch& d, int threads)
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// biorseo_ref fno <delay> <seq> <component>...  : the reference's find_next_ones_in
+// (cppsrc/Motif.cpp:432-494) on its own; one placement per line, "first-second ...".
+static int run_fno(int argc, char** argv)
+{
+    Motif::delay = (uint)std::atoi(argv[2]);
+    vector<string> comps;
+    for (int i = 4; i < argc; i++) comps.push_back(argv[i]);
+    for (const vector<Component>& v : find_next_ones_in(argv[3], 0, comps)) {
+        string line;
+        for (size_t j = 0; j < v.size(); j++) line += (j ? " " : "") + std::to_string(v[j].pos.first) + "-" + std::to_string(v[j].pos.second);
+        std::puts(line.c_str());
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 5 && string(argv[1]) == "fno") return run_fno(argc, argv);
     if (argc < 6) {
         std::fprintf(stderr, "usage: %s ctor|jobs|bench <source> <library> <seqfile> <maskfile> [threads] [repeat] [max_modules]\n", argv[0]);
         return 2;
