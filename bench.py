@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — motif insertion-site search throughput on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: every unit of this
+rank's library shard searched on the query (count -> scan -> emit kernels) and, when N > 1,
+the all-gather-v of the site lists. One JSON line is printed by rank 0.
+
+Workloads (BASELINE.json configs):
+  c4        2000-nt query x 50 000 multi-strand JSON motifs per GPU (half 2-4 strands of 5-8 nt,
+            half 3 strands of 3-4 nt), banded canonical pair mask thinned by Bernoulli(0.3)
+            [default: BASELINE config "2000-nt x 50k motifs, search stress"; the sharded sweep
+            1/2/4/8 GPUs runs it per rank = weak scaling]
+  c4a / c4b the two halves on their own (search-bound / enumeration-bound)
+  c4b_all   c4b with the all-allowed mask: every placement survives, output-bound
+  c3        10 000 x 120-nt queries x 1 000-motif JSON library (batch mode)
+  c2        230-nt query x 400 synthetic CaRNAval RINs
+  c1        73-nt example query x 1 000-motif JSON library
+value     = motif x position placements tested per second, inputs resident in HBM, device time
+            (CUDA events on the launching stream), max over ranks.
+e2e       = the same through the host-buffer C ABI call (bss_search*): upload of sequence + mask
+            and download of the site records inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "motif_x_position_placements_tested_per_s"
+UNIT = "placements/s"
+
+
+# ----------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------
+def make_workload(name, rank):
+    """Returns dict(seqs, masks, modules | rin_folder, source, describe). The library shard of
+    `rank` is generated from seed + rank, so the global library is the same for every N."""
+    from biorseo_b200 import synth
+    w = {"name": name, "source": "jsonfolder"}
+    if name in ("c4", "c4a", "c4b", "c4b_all"):
+        seq = synth.sequence(2000, 4)
+        kind = {"c4": "mixed", "c4a": "c4a", "c4b": "c4b", "c4b_all": "c4b"}[name]
+        w["seqs"] = [seq]
+        w["masks"] = [synth.mask_all(2000) if name == "c4b_all" else synth.mask_canonical(seq, seed=204, keep=0.3, span=100)]
+        w["modules"] = synth.json_modules(50000, 104 + 1000 * rank, kind)
+        w["describe"] = f"2000-nt x 50000 JSON motifs/GPU ({kind}), mask=" + ("all-allowed" if name == "c4b_all" else "banded canonical, Bernoulli 0.3")
+    elif name == "c3":
+        n_seqs = 10000
+        w["seqs"] = [synth.sequence(120, 3 + i) for i in range(n_seqs)]
+        rng = np.random.default_rng(203)
+        w["masks"] = [synth.mask_canonical(s, seed=int(rng.integers(1 << 30)), keep=0.3) for s in w["seqs"]]
+        w["modules"] = synth.json_modules(1000, 101, "c1")
+        w["describe"] = "10000 x 120-nt queries x 1000 JSON motifs (c1 library), banded canonical masks"
+    elif name == "c2":
+        seq = synth.sequence(230, 2)
+        w["seqs"], w["masks"] = [seq], [synth.mask_canonical(seq, seed=202, keep=0.3)]
+        w["source"] = "rinfolder"
+        w["rin"] = (400, 102)
+        w["describe"] = "230-nt query x 400 synthetic CaRNAval RINs"
+    elif name == "c1":
+        seq = "GGGGUAUCGCCAAGCGGUAAGGCACCGGAUUCUGAUUCCGGAGGUCGAGGUUCGAAUCCUCGUACCCCAGCCA"   # data/fasta/example.fa
+        w["seqs"], w["masks"] = [seq], [synth.mask_canonical(seq, seed=201, keep=0.3)]
+        w["modules"] = synth.json_modules(1000, 101, "c1")
+        w["describe"] = "73-nt example.fa query x 1000 JSON motifs (c1 library)"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return w
+
+
+def host_library(w, tmp):
+    import biorseo_b200 as b
+    from biorseo_b200 import synth
+    if w["source"] == "rinfolder":
+        n, seed = w["rin"]
+        path = synth.write_rin_folder(os.path.join(tmp, "rin"), n, seed, invalid_fraction=0.0, max_components=4, min_len=2)
+        return b.HostLibrary.load("rinfolder", path), path
+    return b.HostLibrary.from_json_modules(w["modules"]), None
+
+
+def algorithmic_bytes(table, seq_lens, n_words):
+    """B_in = per-unit table bytes + per-query (packed sequence + pair mask),
+    B_out = 4 bytes per emitted word (u32 module + u32 start per component)."""
+    n_units = int(table["n_units"])
+    ucb = table["unit_comp_begin"].astype(np.int64)
+    cpb = table["comp_pat_begin"].astype(np.int64)
+    k = np.diff(cpb)[: int(ucb[n_units])]
+    checks = int(table["unit_check_begin"][n_units])
+    b_in = 4 * n_units + int((4 + (k + 3) // 4 + (k + 7) // 8).sum()) + 8 * checks
+    b_in += int(sum((n + 3) // 4 + (n * n + 7) // 8 for n in seq_lens))
+    return b_in, 4 * int(n_words)
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 6 and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own Pool-threaded search (oracle/_ref), or
+# the C++ port of it when the compiled reference is absent
+# ----------------------------------------------------------------------------------------
+def cpu_search(w, sample_modules, repeat, threads=None):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    from biorseo_b200 import synth
+    kind = "reference" if util.have_ref() else "port"
+    binary = util.REF_BIN if kind == "reference" else util.PORT_BIN
+    if not os.access(binary, os.X_OK):
+        return None
+    cores = os.cpu_count() or 1
+    threads = threads or max(1, cores - 1)          # the reference's own choice, cppsrc/MOIP.cpp:250
+    seq, mask = w["seqs"][0], w["masks"][0]
+    with tempfile.TemporaryDirectory() as tmp:
+        if w["source"] == "rinfolder":
+            n, seed = w["rin"]
+            lib = synth.write_rin_folder(os.path.join(tmp, "rin"), min(n, sample_modules), seed, invalid_fraction=0.0, max_components=4, min_len=2)
+            n_modules = min(n, sample_modules)
+        else:
+            mods = w["modules"][:sample_modules]
+            lib = synth.write_json(os.path.join(tmp, "lib.json"), mods)
+            n_modules = len(mods)
+        seq_path, mask_path = util.write_query(tmp, seq, mask)
+        t0 = time.perf_counter()
+        if kind == "reference":
+            out = subprocess.run([binary, "bench", w["source"], lib, seq_path, mask_path, str(threads), str(repeat)],
+                                 capture_output=True, text=True, check=True).stdout
+            res = json.loads(out.strip().splitlines()[-1])
+            seconds, sites, n_modules = res["seconds_mean"], res["sites"], res["modules"]
+        else:   # single-threaded port, whole process timed
+            threads = 1
+            t1 = time.perf_counter()
+            for _ in range(repeat):
+                out = subprocess.run([binary, "jobs", w["source"], lib, seq_path, mask_path], capture_output=True, text=True, check=True).stdout
+            seconds, sites = (time.perf_counter() - t1) / repeat, out.count("\n")
+        wall = time.perf_counter() - t0
+    tested = n_modules * len(seq) * 1   # one query of the workload
+    return {"value": tested / seconds, "unit": UNIT, "cores": threads, "host_cores": cores, "kind": kind,
+            "sample": f"first {n_modules} modules of the library x query 0 ({len(seq)} nt), {repeat} pass(es), "
+                      f"push->join timed ({seconds:.3f} s/pass, {wall:.1f} s total)",
+            "sites_per_s": sites / seconds, "seconds_per_pass": seconds}
+
+
+def sample_size(name):
+    return {"c4": 1500, "c4a": 20000, "c4b": 800, "c4b_all": 800, "c3": 1000, "c2": 400, "c1": 1000}[name]
+
+
+# ----------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads reported under 'also'")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w = make_workload(args.workload, 0)
+        res = cpu_search(w, sample_size(args.workload), repeat=max(1, args.steps))
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/biorseo_ref nor oracle/_build/biorseo_port is built"}))
+            return
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * res["seconds_per_pass"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32", "data": "synthetic", "impl": "reference",
+                "config": {"workload": args.workload, "describe": w["describe"]},
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "sites_per_s": res["sites_per_s"], "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import biorseo_b200 as b
+    from biorseo_b200 import sharded
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def run_workload(name, steps, warmup, with_e2e=True, with_collective=True):
+        w = make_workload(name, rank)
+        with tempfile.TemporaryDirectory() as tmp:
+            host, _ = host_library(w, tmp)
+        table = host.table()
+        dev = host.to_device(local_rank)
+        dev.set_module_base(rank * host.n_modules)
+        stream = torch.cuda.current_stream()
+        dev.set_stream(stream.cuda_stream)
+        query = dev.query(w["seqs"], w["masks"])
+        seq_lens = [len(s) for s in w["seqs"]]
+        tested_per_step = sum(seq_lens) * int(table["n_units"])
+
+        # size the output once (capacity negotiation of the C ABI), then reuse it every step
+        rc, n_words, n_sites = dev.search_query_into(query, 0, 0)
+        records = torch.empty(max(n_words, 1), dtype=torch.int32, device="cuda")
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+        def step():
+            rc, nw, ns = dev.search_query_into(query, records.data_ptr(), records.numel())
+            assert rc == 0 and nw == n_words
+            if world > 1 and with_collective:
+                sharded.allgatherv(records[:nw])
+            return dev.stats()
+
+        for _ in range(warmup):
+            step()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        step_ms, kernel_ms = [], {"count_ms": [], "scan_ms": [], "emit_ms": []}
+        launches = 0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush.fill_(1)                      # evict the previous step's lines from L2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            st = step()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            for k in kernel_ms:
+                kernel_ms[k].append(st[k])
+            launches += st["kernel_launches"]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.summary()
+
+        total_ms = float(sum(step_ms))
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        res = {"workload": w, "table": table, "value": world * tested_per_step * steps / (total_ms * 1e-3),
+               "ms_per_step": total_ms / steps, "sites": n_sites, "words": n_words, "launches": launches, "clocks": clocks,
+               "kernel_ms": {k: float(np.mean(v)) for k, v in kernel_ms.items()}, "wall_s": wall, "tested_per_step": tested_per_step,
+               "sites_per_s": world * n_sites * steps / (total_ms * 1e-3), "seq_lens": seq_lens}
+
+        if with_e2e:
+            # end to end through the host-buffer C ABI: pinned host inputs -> device -> pinned host records
+            for _ in range(2):
+                dev.search_batch(w["seqs"], w["masks"]).close()
+            e2e_steps = max(3, min(steps, 10))
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                s = dev.search_batch(w["seqs"], w["masks"])
+                assert s.n_words == n_words
+                s.close()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            st = dev.stats()
+            res["e2e"] = {"value": world * tested_per_step * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(query.h2d_bytes),
+                          "d2h_bytes_per_step": int(st["d2h_bytes"]), "ms_per_step": 1e3 * dt / e2e_steps,
+                          "path": "bss_search_batch: host buffers in, pinned host records out"}
+        query.close()
+        dev.close()
+        return res
+
+    main_res = run_workload(args.workload, args.steps, args.warmup)
+    w, table = main_res["workload"], main_res["table"]
+
+    # roofline of the dominant kernel (HBM: this path has no contraction, tensor cores are not used)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    def roofline(res):
+        km = res["kernel_ms"]
+        name = max(km, key=km.get)
+        b_in, b_out = algorithmic_bytes(res["table"], res["seq_lens"], res["words"])
+        # the count kernel reads the inputs, the emit kernel reads them again and writes the sites
+        algo = {"count_ms": b_in, "scan_ms": 0, "emit_ms": b_in + b_out}[name]
+        achieved = algo / (km[name] * 1e-3) / 1e9 if km[name] > 0 else 0.0
+        return {"bound": "hbm", "kernel": {"count_ms": "search_kernel<G,false> (match+count)", "scan_ms": "scan_kernel",
+                                           "emit_ms": "search_kernel<G,true> (emit)"}[name],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": algo, "kernel_ms": km[name], "peak_source": peak_src,
+                "all_kernels_ms": km}
+
+    line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": args.workload, "describe": w["describe"], "units_per_gpu": int(table["n_units"]),
+                       "parallelism": f"library-sharded x{world}, all-gather-v of site records" if world > 1 else "single GPU",
+                       "l2": "flushed between steps (256 MiB write, outside the timed events)"},
+            "sites_per_s": main_res["sites_per_s"], "sites_per_step_per_gpu": main_res["sites"],
+            "roofline": roofline(main_res), "clocks": main_res["clocks"], "e2e": main_res.get("e2e"),
+            "gpu_launches": main_res["launches"], "wall_s_timed_region": main_res["wall_s"]}
+
+    if rank == 0 and world == 1 and not args.no_extra:
+        also = {}
+        for name in ("c4b_all", "c3", "c2"):
+            if name == args.workload:
+                continue
+            try:
+                r = run_workload(name, max(3, args.steps // 4), 3, with_e2e=True)
+                also[name] = {"describe": r["workload"]["describe"], "value": r["value"], "ms_per_step": r["ms_per_step"],
+                              "sites_per_s": r["sites_per_s"], "sites_per_step": r["sites"], "e2e": r.get("e2e"), "roofline": roofline(r)}
+            except Exception as exc:   # a secondary workload must never take the headline down
+                also[name] = {"error": str(exc)[:200]}
+        line["also"] = also
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_search(w, sample_size(args.workload), repeat=1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "sites_per_s")} if cb else None
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

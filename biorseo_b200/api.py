@@ -229,6 +229,22 @@ class DeviceLibrary:
         self._h = handle
         self.host = host
 
+    @classmethod
+    def from_table(cls, table, device=-1):
+        """Builds the device library straight from flat-table arrays (dict as HostLibrary.table())."""
+        lib = capi.load()
+        keep = {k: np.ascontiguousarray(table[k], dtype=dt) for k, dt in
+                [("unit_module", np.uint32), ("unit_delay", np.uint32), ("unit_gate", np.uint32), ("unit_comp_begin", np.uint32),
+                 ("comp_pat_begin", np.uint32), ("pattern", np.uint8), ("unit_check_begin", np.uint32), ("checks", np.int16)]}
+        t = capi.BssTable()
+        t.n_modules, t.n_units, t.n_gates = int(table["n_modules"]), int(table["n_units"]), int(table["n_gates"])
+        for name, arr in keep.items():
+            ctype = {np.dtype(np.uint32): C.c_uint32, np.dtype(np.uint8): C.c_uint8, np.dtype(np.int16): C.c_int16}[arr.dtype]
+            setattr(t, name, arr.ctypes.data_as(C.POINTER(ctype)) if arr.size else None)
+        h = C.c_void_p()
+        _check(lib.bss_library_create(C.byref(t), device, C.byref(h)))
+        return cls(h, None)
+
     def close(self):
         if self._h:
             self._lib.bss_library_destroy(self._h)
@@ -246,6 +262,9 @@ class DeviceLibrary:
 
     def set_stream(self, cuda_stream):
         _check(self._lib.bss_library_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_module_base(self, base):
+        _check(self._lib.bss_library_set_module_base(self._h, int(base)))
 
     def query(self, seqs, masks):
         return Query(self, seqs, masks)

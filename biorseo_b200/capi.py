@@ -40,6 +40,7 @@ SIGNATURES = {
     "bss_library_create": (C.c_int, [C.POINTER(BssTable), C.c_int, C.POINTER(C.c_void_p)]),
     "bss_library_destroy": (None, [C.c_void_p]),
     "bss_library_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bss_library_set_module_base": (C.c_int, [C.c_void_p, C.c_uint32]),
     "bss_library_units": (C.c_uint32, [C.c_void_p]),
     "bss_library_modules": (C.c_uint32, [C.c_void_p]),
     "bss_library_module_components": (C.c_uint32, [C.c_void_p, C.c_uint32]),

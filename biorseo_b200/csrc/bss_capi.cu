@@ -312,6 +312,13 @@ int bss_library_set_stream(bss_library* lib, void* cuda_stream)
     return BSS_OK;
 }
 
+int bss_library_set_module_base(bss_library* lib, uint32_t base)
+{
+    if (!lib) return fail(BSS_ERR_INVALID, "null library");
+    lib->dev.module_base = base;
+    return BSS_OK;
+}
+
 uint32_t bss_library_units(const bss_library* lib) { return lib ? lib->n_units : 0; }
 uint32_t bss_library_modules(const bss_library* lib) { return lib ? lib->n_modules : 0; }
 uint32_t bss_library_module_components(const bss_library* lib, uint32_t module)

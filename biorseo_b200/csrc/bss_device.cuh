@@ -30,6 +30,7 @@ struct DevLibrary {
     uint32_t        n_units;     // searched units
     uint32_t        n_symbols;   // alphabet size
     uint32_t        cmax;        // max components per unit (gates included)
+    uint32_t        module_base; // added to every module index written into a record (library shards)
     uint8_t         alphabet[32];
 };
 

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const DevLibrary lib, 
             blob = g_blob;
             Gr::sync();
         }
-        const uint32_t module = blob[0];
+        const uint32_t module = blob[0] + lib.module_base;
         const int      C      = (int)(blob[1] & 0xFFu);
         const int      delay  = (int)(blob[1] >> 16);
         const uint32_t gate   = blob[2];

@@ -189,15 +189,16 @@ def json_fuzz_modules(n_modules, seed):
 # --------------------------------------------------------------------------------------
 # CaRNAval RIN files
 # --------------------------------------------------------------------------------------
-def write_rin_folder(folder, n_modules, seed, invalid_fraction=0.1):
-    """Writes <folder>/Subfiles/<i>.txt. 2-6 components of 1-6 nt; links a<=b over motif
-    nucleotide indices."""
+def write_rin_folder(folder, n_modules, seed, invalid_fraction=0.1, max_components=6, min_len=1):
+    """Writes <folder>/Subfiles/<i>.txt. 2-max_components components of min_len-6 nt; links
+    a<=b over motif nucleotide indices. (Many one-nucleotide components make the number of
+    placements, which the reference materialises before filtering, explode with n.)"""
     rng = np.random.default_rng(seed)
     sub = os.path.join(folder, "Subfiles")
     os.makedirs(sub, exist_ok=True)
     for i in range(n_modules):
-        n_comp = int(rng.integers(2, 7))
-        lengths = [int(rng.integers(1, 7)) for _ in range(n_comp)]
+        n_comp = int(rng.integers(2, max_components + 1))
+        lengths = [int(rng.integers(min_len, 7)) for _ in range(n_comp)]
         r = rng.random()
         if r < invalid_fraction / 2:
             lengths = [1, 1, 1]   # too short: 'l'

@@ -118,6 +118,9 @@ void bss_library_destroy(bss_library* lib);
 /* Use an externally owned stream (e.g. the caller's current stream) instead of the
  * library's own; pass NULL to return to the internal stream. */
 int  bss_library_set_stream(bss_library* lib, void* cuda_stream);
+/* Library shards (one per GPU): `base` is added to every module index written into a record,
+ * so that records of different shards can be concatenated in canonical global order. */
+int  bss_library_set_module_base(bss_library* lib, uint32_t base);
 uint32_t bss_library_units(const bss_library* lib);
 uint32_t bss_library_modules(const bss_library* lib);
 /* Number of components of the units of `module` (identical for all its units). */

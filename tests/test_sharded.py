@@ -1,0 +1,85 @@
+"""N > 1 host logic on CPU: world_size-2 gloo. Each rank owns a contiguous module range of
+the library; its site list (here produced by the flat-table interpreter — the GPU is not
+needed to test the plumbing) is exchanged with the same all-gather-v the NCCL path uses, and
+the rank-order concatenation must equal the single-rank canonical list."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import biorseo_b200 as b
+from biorseo_b200 import sharded, synth
+
+import flat_interp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, seq, mask, modules, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        begin, end = sharded.shard_range(len(modules), world, rank)
+        host = b.HostLibrary.from_json_modules(modules[begin:end])
+        rec = flat_interp.search_table(host.table(), seq, mask).astype(np.int64)
+        # module indices are shard-local on the device; the library's module base makes them global
+        comps = host.module_components()
+        at = 0
+        while at < rec.size:
+            width = 1 + int(comps[rec[at]])
+            rec[at] += begin
+            at += width
+        if rank == 1:
+            rec = rec[:0] if os.environ.get("BSS_TEST_EMPTY_RANK") else rec
+        gathered, counts = sharded.allgatherv(torch.from_numpy(rec.astype(np.int32)))
+        assert sum(counts) == gathered.numel()
+        np.save(os.path.join(out_dir, f"rank{rank}.npy"), gathered.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("empty_rank", [False, True])
+def test_allgatherv_concatenation_is_canonical(tmp_path, empty_rank):
+    seq = synth.sequence(90, 77)
+    mask = synth.mask_all(90)
+    modules = synth.json_modules(61, 5, "c1")
+    if empty_rank:
+        os.environ["BSS_TEST_EMPTY_RANK"] = "1"
+    try:
+        mp.spawn(_worker, args=(2, _free_port(), seq, mask, modules, str(tmp_path)), nprocs=2, join=True)
+    finally:
+        os.environ.pop("BSS_TEST_EMPTY_RANK", None)
+    r0, r1 = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
+    assert np.array_equal(r0, r1)
+    host = b.HostLibrary.from_json_modules(modules)
+    full = flat_interp.search_table(host.table(), seq, mask).astype(np.int32)
+    if empty_rank:
+        begin, _ = sharded.shard_range(len(modules), 2, 1)
+        comps, at, keep = host.module_components(), 0, []
+        while at < full.size:
+            width = 1 + int(comps[full[at]])
+            if full[at] < begin:
+                keep.extend(full[at:at + width])
+            at += width
+        full = np.array(keep, dtype=np.int32)
+    assert full.size > 0
+    assert np.array_equal(r0, full)
+
+
+def test_shard_ranges_partition_the_library():
+    for n in (0, 1, 7, 50000, 50003):
+        for world in (1, 2, 4, 8):
+            ranges = [sharded.shard_range(n, world, r) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(a[1] == b_[0] for a, b_ in zip(ranges, ranges[1:]))
+            sizes = [e - s for s, e in ranges]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,5 +1,6 @@
 """Shared helpers of the test-suite: run the oracles, write inputs, compare site lists."""
 import os
+import resource
 import subprocess
 import tempfile
 
@@ -29,14 +30,20 @@ def write_query(folder, seq, mask):
     return seq_path, mask_path
 
 
-def run_oracle(binary, mode, source, library, seq, mask, threads=2, timeout=600):
+def _bounded():
+    # The reference materialises every placement before filtering it; keep a runaway case
+    # from taking the box down.
+    resource.setrlimit(resource.RLIMIT_AS, (6 << 30, 6 << 30))
+
+
+def run_oracle(binary, mode, source, library, seq, mask, threads=2, timeout=120):
     """Runs an oracle CLI; returns its dump as a sorted list of lines (a multiset of sites)."""
     with tempfile.TemporaryDirectory() as tmp:
         seq_path, mask_path = write_query(tmp, seq, mask)
         cmd = [binary, mode, source, str(library), seq_path, mask_path]
         if mode == "jobs":
             cmd.append(str(threads))
-        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, preexec_fn=_bounded)
     if res.returncode != 0:
         raise RuntimeError(f"{' '.join(cmd)} failed ({res.returncode}): {res.stderr[-2000:]}")
     return sorted(line for line in res.stdout.split("\n") if line)
