@@ -218,17 +218,15 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
         const size_t   base      = blob.size();
         blob.resize(base + head + pat_words + 2 * (size_t)NK, 0);
         uint32_t* b  = blob.data() + base;
-        const uint8_t* p0 = t->pattern + t->comp_pat_begin[c0];
-        const uint32_t kfirst = t->comp_pat_begin[c0 + 1] - t->comp_pat_begin[c0];
         b[0] = t->unit_module[u];
         b[1] = C | (NK << 8) | (t->unit_delay[u] << 16);
         b[2] = gate;
-        b[3] = (can_self_overlap(p0, kfirst) ? 1u : 0u) | ((head + pat_words) << 16);
+        b[3] = (head + pat_words) << 16;
         uint8_t* pat_bytes = reinterpret_cast<uint8_t*>(b + head);
         uint32_t byte_off  = 0, next_check = 0;
         for (uint32_t c = 0; c < C; c++) {
             const uint32_t pb = t->comp_pat_begin[c0 + c], k = t->comp_pat_begin[c0 + c + 1] - pb;
-            b[4 + 2 * c] = k | ((head * 4 + byte_off) << 8);
+            b[4 + 2 * c] = k | ((head * 4 + byte_off) << 8) | (can_self_overlap(t->pattern + pb, k) ? bss::kCompOverlap : 0u);
             for (uint32_t j = 0; j < k; j++) {
                 const uint8_t ch = t->pattern[pb + j];
                 pat_bytes[byte_off + j] = ch == '.' ? (uint8_t)bss::kWildcard : (uint8_t)code_of[ch];
@@ -241,8 +239,18 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
         uint32_t* chk = b + head + pat_words;
         for (uint32_t i = 0; i < NK; i++) {
             const int16_t* c = t->checks + 4 * (size_t)(k0 + order[i]);
-            chk[2 * i]     = ((uint32_t)(uint8_t)(int8_t)c[0]) | (((uint32_t)(uint16_t)c[1]) << 8);
-            chk[2 * i + 1] = ((uint32_t)(uint8_t)(int8_t)c[2]) | (((uint32_t)(uint16_t)c[3]) << 8);
+            const int      lv = level[order[i]];
+            // word 0: the end known before level lv is entered; word 1: the end on component lv
+            const bool a_on = c[0] == lv, b_on = c[2] == lv;
+            const int16_t *first = c, *second = c + 2;
+            uint32_t       flags = 0;
+            if (a_on != b_on) {
+                if (a_on) std::swap(first, second);
+            } else {
+                flags = bss::kCheckFixed;
+            }
+            chk[2 * i]     = ((uint32_t)(uint8_t)(int8_t)first[0]) | (((uint32_t)(uint16_t)first[1]) << 8) | flags;
+            chk[2 * i + 1] = ((uint32_t)(uint8_t)(int8_t)second[0]) | (((uint32_t)(uint16_t)second[1]) << 8);
         }
         if (blob.size() > 0x7FFFFFFFu) return fail(BSS_ERR_LIMIT, "library too large");
     }
@@ -347,9 +355,10 @@ int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
     BSS_CUDA(cudaSetDevice(lib->device));
     bss_query* q = new bss_query();
     q->device    = lib->device;
-    // one allocation: [seq_begin | mask_begin | masks | seqs]
-    const size_t off_sb = 0, off_mb = off_sb + 8 * (size_t)(n_seqs + 1), off_mask = off_mb + 8 * (size_t)(n_seqs + 1),
-                 off_seq = off_mask + 4 * total_mask, bytes = off_seq + total_len + 16;
+    // one allocation: [seq_begin | mask_begin | band | masks | seqs]
+    const size_t off_sb = 0, off_mb = off_sb + 8 * (size_t)(n_seqs + 1), off_band = off_mb + 8 * (size_t)(n_seqs + 1),
+                 off_mask = off_band + 4 * (((size_t)n_seqs + 3) & ~(size_t)3), off_seq = off_mask + 4 * total_mask,
+                 bytes = off_seq + total_len + 16;
     cudaError_t e = q->storage.reserve(bytes);
     if (e != cudaSuccess) { delete q; return cuda_fail(e, "cudaMalloc(query)"); }
     char* d = static_cast<char*>(q->storage.ptr);
@@ -360,14 +369,17 @@ int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
     if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_mb, mb.data(), 8 * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && total_mask) e = cudaMemcpyAsync(d + off_mask, masks + mask_begin[0], 4 * total_mask, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && total_len) e = cudaMemcpyAsync(d + off_seq, s0, total_len, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // sb / mb are stack-owned staging
-    if (e != cudaSuccess) { q->storage.release(); delete q; return cuda_fail(e, "query upload"); }
     q->dev.seq_begin  = reinterpret_cast<const uint64_t*>(d + off_sb);
     q->dev.mask_begin = reinterpret_cast<const uint64_t*>(d + off_mb);
+    q->dev.band       = reinterpret_cast<const int32_t*>(d + off_band);
     q->dev.masks      = reinterpret_cast<const uint32_t*>(d + off_mask);
     q->dev.seqs       = reinterpret_cast<const uint8_t*>(d + off_seq);
     q->dev.n_seqs     = n_seqs;
     q->dev.max_len    = max_len;
+    // widest pair the mask allows, per sequence: bounds the window a tied component is searched in
+    if (e == cudaSuccess) e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // sb / mb are stack-owned staging
+    if (e != cudaSuccess) { q->storage.release(); delete q; return cuda_fail(e, "query upload"); }
     q->total_len      = total_len;
     q->h2d_bytes      = 16 * (uint64_t)(n_seqs + 1) + 4 * total_mask + total_len;
     *out = q;

@@ -7,15 +7,21 @@
 // Shape of the computation. One CTA owns one chunk = (sequence, contiguous range of units).
 // It first turns the query into per-symbol occurrence bit rows in shared memory
 // (bit q of row a = "sequence byte q is alphabet symbol a"). A group of G lanes
-// (G = 4..32, picked from the sequence length) then owns one (sequence, unit) item:
+// (G = 4..32, picked from the sequence length) then draws (sequence, unit) items from the
+// chunk's counter and, for each:
 //   1. match:  for every component, M_c = AND_j (occ[pattern_j] >> j), 32 positions per
 //              lane and step, with a one-bit-per-word summary for fast "next match" queries;
-//   2. walk:   lanes split the matches of component 0 by mask word and enumerate the
-//              placements below each in depth-first order, following the reference's
-//              "leftmost non-overlapping matches of the next pattern in the suffix after
-//              this component" rule, testing every base-pair check as soon as both of its
-//              ends are placed (pruning is result-neutral: SURVEY.md appendix B);
-//   3. count / emit: pass 1 counts sites per item, a scan turns counts into offsets,
+//   2. thin:   components whose matches overlap on this sequence get T_c, the leftmost
+//              non-overlapping matches of every run of overlapping matches. The reference's
+//              candidates for a component in the suffix starting at t (sregex_iterator) are
+//              then: a greedy walk over M_c from t until it lands on a bit of T_c, and T_c
+//              itself from there on;
+//   3. walk:   lanes split the candidates of component 0 by mask word and enumerate the
+//              placements below each depth-first. Every base-pair check is tested as soon as
+//              both of its ends are placed, and a level whose component is tied by a check to
+//              an already placed position only scans the window the pair mask's band allows
+//              (pruning is result-neutral: SURVEY.md appendix B);
+//   4. count / emit: pass 1 counts sites per item, a scan turns counts into offsets,
 //              pass 2 repeats the walk and writes [module, p_0..p_{C-1}] records at their
 //              final, canonical (sequence, unit, depth-first) position. No sort, no atomics
 //              on the output.
@@ -28,12 +34,12 @@ namespace {
 __device__ __forceinline__ int unpack_anchor(uint32_t w) { return (int)(int8_t)(w & 0xFFu); }
 __device__ __forceinline__ int unpack_off(uint32_t w) { return (int)(int16_t)((w >> 8) & 0xFFFFu); }
 
-// First set bit at or after position t in a component's match mask, or -1.
-__device__ __forceinline__ int next_match(const uint32_t* __restrict__ M, const uint32_t* __restrict__ S, int W, int WS, int t)
+// First set bit at or after position t (t >= 0) of a bitset with a one-bit-per-word summary, or -1.
+__device__ __forceinline__ int next_bit(const uint32_t* __restrict__ B, const uint32_t* __restrict__ S, int W, int WS, int t)
 {
     int w = t >> 5;
     if (w >= W) return -1;
-    uint32_t x = M[w] & (0xFFFFFFFFu << (t & 31));
+    uint32_t x = B[w] & (0xFFFFFFFFu << (t & 31));
     if (x) return (w << 5) + __ffs(x) - 1;
     if (++w >= W) return -1;
     int      sw = w >> 5;
@@ -43,18 +49,32 @@ __device__ __forceinline__ int next_match(const uint32_t* __restrict__ M, const 
         s = S[sw];
     }
     w = (sw << 5) + __ffs(s) - 1;
-    return (w << 5) + __ffs(M[w]) - 1;
+    return (w << 5) + __ffs(B[w]) - 1;
+}
+
+__device__ __forceinline__ bool test_bit(const uint32_t* __restrict__ B, int q) { return (B[q >> 5] >> (q & 31)) & 1u; }
+
+// Word w of (B << s): bit q of the result is bit q - s of B.
+__device__ __forceinline__ uint32_t shifted_up(const uint32_t* __restrict__ B, int w, int s)
+{
+    const int      i  = w - (s >> 5);
+    const uint32_t hi = i >= 0 ? B[i] : 0u, lo = i >= 1 ? B[i - 1] : 0u;
+    return __funnelshift_l(lo, hi, s & 31);
 }
 
 struct ItemCtx {
     const uint32_t* blob;     // unit descriptor (shared or global memory)
-    const uint32_t* M;        // [C][W] match masks
-    const uint32_t* S;        // [C][WS] summaries
+    const uint32_t* M;        // [C][W] every match of every component
+    const uint32_t* T;        // [C][W] thinned matches, valid for the components in `ovl`
+    const uint32_t* SM;       // [C][WS] summaries of M
+    const uint32_t* ST;       // [C][WS] summaries of T
     const uint32_t* mask;     // pair mask of the sequence, row stride mstride words
-    uint32_t*       stack_p;  // this thread's column of the position stack, stride kThreads
-    uint32_t*       stack_t;  // this thread's column of the cursor stack
-    int             W, WS, n, mstride, C, delay;
+    uint32_t*       stack;    // this thread's column (stride kThreads): position | last position of the window << 16
+    uint32_t        ovl;      // bit c: matches of component c overlap on this sequence
+    int             W, WS, n, mstride, C, delay, band;
 };
+
+__device__ __forceinline__ int placed(const ItemCtx& cx, int level) { return (int)(cx.stack[level * kThreads] & 0xFFFFu); }
 
 // All checks that become decidable once component `level` is placed.
 __device__ __forceinline__ bool checks_pass(const ItemCtx& cx, int level)
@@ -65,8 +85,8 @@ __device__ __forceinline__ bool checks_pass(const ItemCtx& cx, int level)
     for (int i = cb; i < ce; i++) {
         const uint32_t ea = chk[2 * i], eb = chk[2 * i + 1];
         const int      aa = unpack_anchor(ea), ba = unpack_anchor(eb);
-        const int      u  = (aa < 0 ? 0 : (int)cx.stack_p[aa * kThreads]) + unpack_off(ea);
-        const int      v  = (ba < 0 ? 0 : (int)cx.stack_p[ba * kThreads]) + unpack_off(eb);
+        const int      u  = (aa < 0 ? 0 : placed(cx, aa)) + unpack_off(ea);
+        const int      v  = (ba < 0 ? 0 : placed(cx, ba)) + unpack_off(eb);
         const int      a = min(u, v), b = max(u, v);
         if (a < 0 || b >= cx.n || a == b) return false;
         if (!((__ldg(cx.mask + (size_t)a * cx.mstride + (b >> 5)) >> (b & 31)) & 1u)) return false;
@@ -74,46 +94,117 @@ __device__ __forceinline__ bool checks_pass(const ItemCtx& cx, int level)
     return true;
 }
 
+// Next candidate of component `level` at or after max(after, lo). `after` is where the
+// reference's iterator would resume (suffix start, or one pattern length after the previous
+// match). While the level's bit is set in `greedy` the chain is still a greedy walk over all
+// matches that has not met the thinned set yet.
+__device__ __forceinline__ int chain_next(const ItemCtx& cx, int level, int after, int lo, uint32_t& greedy)
+{
+    const uint32_t bit = 1u << level;
+    const int      W = cx.W, WS = cx.WS;
+    if (greedy & bit) {
+        const uint32_t *M = cx.M + level * W, *SM = cx.SM + level * WS, *T = cx.T + level * W;
+        const int       k = max(1, (int)(cx.blob[4 + 2 * level] & 0xFFu));
+        int             q = next_bit(M, SM, W, WS, after);
+        while (q >= 0) {
+            if (test_bit(T, q)) {   // from here on the chain is the thinned set
+                greedy &= ~bit;
+                return q >= lo ? q : next_bit(T, cx.ST + level * WS, W, WS, lo);
+            }
+            if (q >= lo) return q;
+            q = next_bit(M, SM, W, WS, q + k);
+        }
+        return -1;
+    }
+    const bool thinned = (cx.ovl >> level) & 1u;
+    return next_bit((thinned ? cx.T : cx.M) + level * W, (thinned ? cx.ST : cx.SM) + level * WS, W, WS, max(after, lo));
+}
+
+// First candidate of component `level` in the suffix starting at t. Checks that tie this
+// component to an already known position u restrict it to |v - u| <= band.
+__device__ __forceinline__ int enter_level(const ItemCtx& cx, int level, int t, uint32_t& greedy)
+{
+    int            lo = t, hi = cx.n;
+    const uint32_t range = cx.blob[5 + 2 * level];
+    const int      cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
+    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
+    for (int i = cb; i < ce; i++) {
+        const uint32_t ea = chk[2 * i];
+        if (ea & kCheckFixed) continue;
+        const int aa = unpack_anchor(ea);
+        const int u  = (aa < 0 ? 0 : placed(cx, aa)) + unpack_off(ea);
+        if (u < 0 || u >= cx.n || cx.band < 0) return -1;
+        const int ob = unpack_off(chk[2 * i + 1]);
+        lo = max(lo, u - cx.band - ob);
+        hi = min(hi, u + cx.band - ob);
+    }
+    if (lo > hi) return -1;
+    const uint32_t bit = 1u << level;
+    greedy             = (greedy & ~bit) | (cx.ovl & bit);
+    const int q        = chain_next(cx, level, t, lo, greedy);
+    if (q < 0 || q > hi) return -1;
+    cx.stack[level * kThreads] = (uint32_t)q | ((uint32_t)hi << 16);
+    return q;
+}
+
+__device__ __forceinline__ int advance_level(const ItemCtx& cx, int level, uint32_t& greedy)
+{
+    const uint32_t e = cx.stack[level * kThreads];
+    const int      q = (int)(e & 0xFFFFu), hi = (int)(e >> 16);
+    const int      k = max(1, (int)(cx.blob[4 + 2 * level] & 0xFFu));   // matches of one pattern never overlap
+    const int      q2 = chain_next(cx, level, q + k, 0, greedy);
+    if (q2 < 0 || q2 > hi) return -1;
+    cx.stack[level * kThreads] = (uint32_t)q2 | ((uint32_t)hi << 16);
+    return q2;
+}
+
 // Enumerates every site whose component 0 sits at p0. Returns the number of sites; when
-// EMIT, also writes their records starting at out (rec_words each).
+// EMIT, also writes their records starting at out (C + 1 words each).
 template <bool EMIT>
 __device__ __forceinline__ uint64_t walk_subtree(const ItemCtx& cx, int p0, uint32_t module, uint32_t* __restrict__ out)
 {
     const int C = cx.C;
-    cx.stack_p[0] = (uint32_t)p0;
+    cx.stack[0] = (uint32_t)p0;
     if (!checks_pass(cx, 0)) return 0;
-    uint64_t found = 0;
     if (C == 1) {
         if (EMIT) { out[0] = module; out[1] = (uint32_t)p0; }
         return 1;
     }
+    uint32_t greedy = 0;
+    int      level  = 1, q;
     {
-        const int k0 = (int)(cx.blob[4] & 0xFFu);
-        const int t  = p0 + k0 - 1 + cx.delay;
+        const int t = p0 + (int)(cx.blob[4] & 0xFFu) - 1 + cx.delay;
         if (t < 0 || t >= cx.n) return 0;   // no room for the next component
-        cx.stack_t[1 * kThreads] = (uint32_t)t;
+        q = enter_level(cx, 1, t, greedy);
     }
-    int level = 1;
-    while (level >= 1) {
-        const int k = (int)(cx.blob[4 + 2 * level] & 0xFFu);
-        const int q = next_match(cx.M + level * cx.W, cx.S + level * cx.WS, cx.W, cx.WS, (int)cx.stack_t[level * kThreads]);
-        if (q < 0) { level--; continue; }
-        cx.stack_t[level * kThreads] = (uint32_t)(q + (k > 0 ? k : 1));   // matches of one pattern never overlap
-        cx.stack_p[level * kThreads] = (uint32_t)q;
-        if (!checks_pass(cx, level)) continue;
-        if (level == C - 1) {
-            if (EMIT) {
-                uint32_t* rec = out + found * (uint64_t)(C + 1);
-                rec[0] = module;
-                for (int c = 0; c < C; c++) rec[1 + c] = cx.stack_p[c * kThreads];
-            }
-            found++;
+    uint64_t found = 0;
+    for (;;) {
+        if (q < 0) {   // this level is exhausted: back to the next candidate of its parent
+            if (--level == 0) break;
+            q = advance_level(cx, level, greedy);
             continue;
         }
-        const int t = q + k - 1 + cx.delay;
-        if (t < 0 || t >= cx.n) { level--; continue; }   // later matches leave even less room
-        level++;
-        cx.stack_t[level * kThreads] = (uint32_t)t;
+        if (checks_pass(cx, level)) {
+            if (level == C - 1) {
+                if (EMIT) {
+                    uint32_t* rec = out + found * (uint64_t)(C + 1);
+                    rec[0] = module;
+                    for (int c = 0; c < C; c++) rec[1 + c] = (uint32_t)placed(cx, c);
+                }
+                found++;
+            } else {
+                const int t = q + (int)(cx.blob[4 + 2 * level] & 0xFFu) - 1 + cx.delay;
+                if (t < 0 || t >= cx.n) {   // later matches of this level leave even less room
+                    if (--level == 0) break;
+                    q = advance_level(cx, level, greedy);
+                    continue;
+                }
+                level++;
+                q = enter_level(cx, level, t, greedy);
+                continue;
+            }
+        }
+        q = advance_level(cx, level, greedy);
     }
     return found;
 }
@@ -129,6 +220,7 @@ struct Group {
         return G == 32 ? b : ((b >> shift()) & ((1u << G) - 1u));
     }
     static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+    static __device__ __forceinline__ uint32_t first(uint32_t v) { return __shfl_sync(mask(), v, 0, G); }
     template <typename T>
     static __device__ __forceinline__ T sum(T v)
     {
@@ -163,7 +255,7 @@ __device__ __forceinline__ bool match_components(const uint32_t* blob, const uin
     for (int c = 0; c < C; c++) {
         const uint32_t desc = blob[4 + 2 * c];
         const int      k    = (int)(desc & 0xFFu);
-        const uint8_t* pat  = bytes + (desc >> 8);
+        const uint8_t* pat  = bytes + ((desc >> 8) & 0xFFFFu);
         const int      last = n - k;   // last position where the pattern still fits (k = 0: position n)
         bool           any  = false;
         for (int w0 = 0; w0 < W; w0 += G) {
@@ -190,6 +282,69 @@ __device__ __forceinline__ bool match_components(const uint32_t* blob, const uin
     return true;
 }
 
+// Thinned match sets. A run is a maximal series of matches in which consecutive matches are
+// less than k apart; T_c holds, for every run, its leftmost non-overlapping matches counted
+// from the start of the run. Only components whose pattern can overlap a shifted copy of
+// itself (kCompOverlap) and whose matches do overlap on this sequence get one; their bit is
+// set in the returned mask.
+template <int G>
+__device__ __forceinline__ uint32_t thin_components(const uint32_t* blob, const uint32_t* M, const uint32_t* SM, uint32_t* T,
+                                                    uint32_t* ST, int W, int WS)
+{
+    using Gr     = Group<G>;
+    const int C  = (int)(blob[1] & 0xFFu);
+    uint32_t ovl = 0;
+    for (int c = 0; c < C; c++) {
+        const uint32_t desc = blob[4 + 2 * c];
+        if (!(desc & kCompOverlap)) continue;
+        const int       k  = (int)(desc & 0xFFu);
+        const uint32_t* Mc = M + c * W;
+        const uint32_t* Sc = SM + c * WS;
+        uint32_t*       Tc = T + c * W;
+        bool            any = false;
+        for (int w0 = 0; w0 < W; w0 += G) {   // run starts: matches without a match in the k-1 positions before them
+            const int w = w0 + (int)Gr::lane();
+            uint32_t  m = 0, starts = 0;
+            if (w < W) {
+                m             = Mc[w];
+                uint32_t near = 0;
+                if (m)
+                    for (int s = 1; s < k; s++) near |= shifted_up(Mc, w, s);
+                starts = m & ~near;
+                Tc[w]  = starts;
+            }
+            any |= Gr::ballot(m != starts) != 0;
+        }
+        if (!any) continue;
+        ovl |= 1u << c;
+        Gr::sync();
+        // Greedy picks inside every run. A lane that reads a word after another lane has
+        // added picks to it restarts from a pick, which reproduces the same chain.
+        for (int w = (int)Gr::lane(); w < W; w += G) {
+            for (uint32_t x = Tc[w]; x; x &= x - 1) {
+                int prev = (w << 5) + __ffs(x) - 1, last = prev;
+                for (;;) {
+                    const int m = next_bit(Mc, Sc, W, WS, prev + 1);
+                    if (m < 0 || m - prev >= k) break;
+                    if (m - last >= k) {
+                        atomicOr(&Tc[m >> 5], 1u << (m & 31));
+                        last = m;
+                    }
+                    prev = m;
+                }
+            }
+        }
+        Gr::sync();
+        for (int w0 = 0; w0 < W; w0 += G) {
+            const int      w    = w0 + (int)Gr::lane();
+            const uint32_t bits = Gr::ballot(w < W && Tc[w] != 0);
+            if (Gr::lane() == 0) ST[c * WS + (w0 >> 5)] = bits;
+        }
+    }
+    Gr::sync();
+    return ovl;
+}
+
 // Greedy earliest placement: does the gate unit have any placement on this sequence?
 template <int G>
 __device__ __forceinline__ bool gate_open(const uint32_t* gblob, const uint32_t* occ, int WP, uint32_t* M, uint32_t* S, int W,
@@ -199,30 +354,314 @@ __device__ __forceinline__ bool gate_open(const uint32_t* gblob, const uint32_t*
     const int C = (int)(gblob[1] & 0xFFu), delay = (int)(gblob[1] >> 16);
     int       t = 0;
     for (int c = 0; c < C; c++) {
-        const int q = next_match(M + c * W, S + c * WS, W, WS, t);
+        const int q = next_bit(M + c * W, S + c * WS, W, WS, t);
         if (q < 0) return false;
         t = q + (int)(gblob[4 + 2 * c] & 0xFFu) - 1 + delay;
     }
     return true;
 }
 
+// ----------------------------------------------------------------------------------------
+// Rank-space walk (long sequences, one warp per item).
+//
+// The placements of a unit, before the base-pair checks, form a nested structure: the
+// candidates of component c+1 below a candidate of component c are a few "greedy" matches
+// followed by a contiguous range of the sorted match list of component c+1 (restricted to the
+// band window of the checks that tie c+1 to c). Counting them is a backward dynamic programme
+// over the match lists (N = placements below each match, PS = prefix sums of N), and the r-th
+// placement in depth-first order is found by one binary search per component. A warp therefore
+// enumerates 32 consecutive ranks at a time, one per lane, tests the checks, and compacts the
+// survivors with ballot/popc: no divergence, no per-lane stacks, and the records of one batch
+// are written as one contiguous, coalesced block in canonical order.
+// ----------------------------------------------------------------------------------------
+struct RankCtx {
+    ItemCtx   cx;
+    uint16_t* mpos;    // [cap] match positions, lists of the components back to back
+    uint32_t* N;       // [cap] placements below each match (components c+1.. only)
+    uint32_t* PS;      // [cap + C] per component a_c + 1 prefix sums of N over the thinned matches
+    uint16_t* MWP;     // [C][W] matches before each mask word
+    uint16_t* lbeg;    // [C + 1] first list entry of each component
+};
+
+__device__ __forceinline__ int list_len(const RankCtx& rc, int c) { return (int)rc.lbeg[c + 1] - (int)rc.lbeg[c]; }
+
+// Number of matches of component c at positions < x.
+__device__ __forceinline__ int match_rank(const RankCtx& rc, int c, int x)
+{
+    if (x <= 0) return 0;
+    const int w = x >> 5;
+    if (w >= rc.cx.W) return list_len(rc, c);
+    return (int)rc.MWP[c * rc.cx.W + w] + __popc(rc.cx.M[c * rc.cx.W + w] & ((1u << (x & 31)) - 1u));
+}
+
+__device__ __forceinline__ bool is_thinned(const RankCtx& rc, int c, int pos)
+{
+    return !((rc.cx.ovl >> c) & 1u) || test_bit(rc.cx.T + c * rc.cx.W, pos);
+}
+
+// Candidates of component c below a candidate of component c-1 placed at p: `nex` greedy
+// matches starting at position `efirst` (successive ones one pattern length apart at least),
+// then the thinned matches among list entries [ja, jb).
+struct Kids {
+    int efirst, nex, ja, jb;
+};
+
+__device__ __forceinline__ Kids kids_of(const RankCtx& rc, int c, int p)
+{
+    const ItemCtx& cx = rc.cx;
+    Kids           kd{-1, 0, 0, 0};
+    const int      t = p + (int)(cx.blob[4 + 2 * (c - 1)] & 0xFFu) - 1 + cx.delay;
+    if (t < 0 || t >= cx.n) return kd;
+    const int kc = (int)(cx.blob[4 + 2 * c] & 0xFFu);
+    // an empty pattern at position 0 leaves "no room" (unsigned wrap in the reference) and ends the level
+    if (c < cx.C - 1 && kc == 0 && cx.delay == 0 && t == 0) return kd;
+    int            lo = t, hi = cx.n;
+    const uint32_t range = cx.blob[5 + 2 * c];
+    const int      cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
+    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
+    for (int i = cb; i < ce; i++) {   // windows of the checks that tie c to c-1 or to a fixed position
+        const uint32_t ea = chk[2 * i];
+        if (ea & kCheckFixed) continue;
+        const int aa = unpack_anchor(ea);
+        if (aa >= 0 && aa != c - 1) continue;
+        const int u = (aa < 0 ? 0 : p) + unpack_off(ea);
+        if (u < 0 || u >= cx.n || cx.band < 0) return kd;
+        const int ob = unpack_off(chk[2 * i + 1]);
+        lo = max(lo, u - cx.band - ob);
+        hi = min(hi, u + cx.band - ob);
+    }
+    if (lo > hi) return kd;
+    if ((cx.ovl >> c) & 1u) {
+        const uint32_t *M = cx.M + c * cx.W, *SM = cx.SM + c * cx.WS, *T = cx.T + c * cx.W;
+        const int       ke = max(1, kc);
+        int             q  = next_bit(M, SM, cx.W, cx.WS, t);
+        while (q >= 0 && !test_bit(T, q)) {
+            if (q > hi) return kd;
+            if (q >= lo) {
+                if (!kd.nex) kd.efirst = q;
+                kd.nex++;
+            }
+            q = next_bit(M, SM, cx.W, cx.WS, q + ke);
+        }
+        if (q < 0) return kd;
+        lo = max(lo, q);
+    }
+    kd.ja = match_rank(rc, c, lo);
+    kd.jb = max(kd.ja, match_rank(rc, c, hi + 1));
+    return kd;
+}
+
+// Largest j in [ja, jb) with PS[j] <= target (PS is non-decreasing; entries of weight 0 are never chosen
+// because target < PS[jb]).
+__device__ __forceinline__ int rank_search(const uint32_t* __restrict__ PS, int ja, int jb, uint32_t target)
+{
+    int lo = ja, hi = jb;   // invariant: PS[lo] <= target < PS[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (PS[mid] <= target) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Match lists of the components + word prefix counts. False when they do not fit.
+__device__ __forceinline__ bool rank_build_lists(const RankCtx& rc, int cap)
+{
+    const ItemCtx& cx   = rc.cx;
+    const int      lane = threadIdx.x & 31;
+    int            base = 0;
+    for (int c = 0; c < cx.C; c++) {
+        if (lane == 0) rc.lbeg[c] = (uint16_t)base;
+        int running = 0;
+        for (int w0 = 0; w0 < cx.W; w0 += 32) {
+            const int      w   = w0 + lane;
+            const uint32_t m   = w < cx.W ? cx.M[c * cx.W + w] : 0u;
+            const int      cnt = __popc(m);
+            int            inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += up;
+            }
+            const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            if (base + running + total > cap) return false;
+            int at = running + inc - cnt;
+            if (w < cx.W) rc.MWP[c * cx.W + w] = (uint16_t)at;
+            for (uint32_t x = m; x; x &= x - 1) rc.mpos[base + at++] = (uint16_t)((w << 5) + __ffs(x) - 1);
+            running += total;
+        }
+        base += running;
+    }
+    if (lane == 0) rc.lbeg[cx.C] = (uint16_t)base;
+    __syncwarp();
+    return true;
+}
+
+// Backward dynamic programme. Returns the number of placements before the checks, or
+// UINT64_MAX when a count does not fit 31 bits (the caller falls back to the depth-first walk).
+__device__ __forceinline__ uint64_t rank_count(const RankCtx& rc)
+{
+    const ItemCtx& cx   = rc.cx;
+    const int      lane = threadIdx.x & 31;
+    bool           overflow = false;
+    uint64_t       total    = 0;
+    for (int c = cx.C - 1; c >= 0; c--) {
+        const int       b  = rc.lbeg[c], a = list_len(rc, c);
+        uint32_t*       PS = rc.PS + b + c;
+        const uint32_t* PSn = rc.PS + rc.lbeg[c + 1] + c + 1;   // next component's
+        uint64_t        running = 0;
+        if (lane == 0) PS[0] = 0;
+        for (int j0 = 0; j0 < a; j0 += 32) {
+            const int j = j0 + lane;
+            uint64_t  n = 0;
+            int       p = 0;
+            if (j < a) {
+                p = rc.mpos[b + j];
+                if (c == cx.C - 1) {
+                    n = 1;
+                } else {
+                    const Kids kd = kids_of(rc, c + 1, p);
+                    const int  ke = max(1, (int)(cx.blob[4 + 2 * (c + 1)] & 0xFFu));
+                    int        e  = kd.efirst;
+                    for (int x = 0; x < kd.nex; x++) {
+                        n += rc.N[rc.lbeg[c + 1] + match_rank(rc, c + 1, e)];
+                        e = next_bit(cx.M + (c + 1) * cx.W, cx.SM + (c + 1) * cx.WS, cx.W, cx.WS, e + ke);
+                    }
+                    n += PSn[kd.jb] - PSn[kd.ja];
+                }
+                if (n >= 0x80000000ull) overflow = true;
+                rc.N[b + j] = (uint32_t)n;
+                if (!is_thinned(rc, c, p)) n = 0;   // only ever reached as a greedy match, never through a range
+            }
+            uint64_t inc = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += up;
+            }
+            if (j < a) PS[j + 1] = (uint32_t)(running + inc);
+            running += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            if (running >= 0x80000000ull) overflow = true;
+        }
+        total = running;
+        __syncwarp();
+    }
+    if (__any_sync(0xFFFFFFFFu, overflow)) return ~0ull;
+    return total;
+}
+
+// Positions of the placement of depth-first rank r into this lane's stack column.
+__device__ __forceinline__ void rank_unrank(const RankCtx& rc, uint32_t r)
+{
+    const ItemCtx& cx = rc.cx;
+    int            p;
+    {
+        const uint32_t* PS = rc.PS;
+        const int       j  = rank_search(PS, 0, list_len(rc, 0), r);
+        r -= PS[j];
+        p = rc.mpos[j];
+        cx.stack[0] = (uint32_t)p;
+    }
+    for (int c = 1; c < cx.C; c++) {
+        const Kids      kd = kids_of(rc, c, p);
+        const int       b  = rc.lbeg[c];
+        const uint32_t* PS = rc.PS + b + c;
+        bool            done = false;
+        if (kd.nex) {
+            const int ke = max(1, (int)(cx.blob[4 + 2 * c] & 0xFFu));
+            int       e  = kd.efirst;
+            for (int x = 0; x < kd.nex; x++) {
+                const uint32_t n = rc.N[b + match_rank(rc, c, e)];
+                if (r < n) { p = e; done = true; break; }
+                r -= n;
+                e = next_bit(cx.M + c * cx.W, cx.SM + c * cx.WS, cx.W, cx.WS, e + ke);
+            }
+        }
+        if (!done) {
+            const int j = rank_search(PS, kd.ja, kd.jb, PS[kd.ja] + r);
+            r -= PS[j] - PS[kd.ja];
+            p = rc.mpos[b + j];
+        }
+        cx.stack[c * kThreads] = (uint32_t)p;
+    }
+}
+
+__device__ __forceinline__ bool all_checks_pass(const ItemCtx& cx)
+{
+    const int       nk  = (int)((cx.blob[1] >> 8) & 0xFFu);
+    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
+    for (int i = 0; i < nk; i++) {
+        const uint32_t ea = chk[2 * i], eb = chk[2 * i + 1];
+        const int      aa = unpack_anchor(ea), ba = unpack_anchor(eb);
+        const int      u  = (aa < 0 ? 0 : placed(cx, aa)) + unpack_off(ea);
+        const int      v  = (ba < 0 ? 0 : placed(cx, ba)) + unpack_off(eb);
+        const int      a = min(u, v), b = max(u, v);
+        if (a < 0 || b >= cx.n || a == b) return false;
+        if (!((__ldg(cx.mask + (size_t)a * cx.mstride + (b >> 5)) >> (b & 31)) & 1u)) return false;
+    }
+    return true;
+}
+
+// Enumerates ranks [0, total) 32 at a time. Returns the number of sites; when EMIT, writes
+// their records from `out` on, staged through `stage` (32 * (C + 1) words) so that every
+// batch leaves as one contiguous block.
+template <bool EMIT>
+__device__ __forceinline__ uint64_t rank_walk(const RankCtx& rc, uint32_t total, uint32_t module, uint32_t* __restrict__ out,
+                                              uint32_t* stage)
+{
+    const ItemCtx& cx   = rc.cx;
+    const uint32_t lane = threadIdx.x & 31;
+    const int      R    = cx.C + 1;
+    uint64_t       found = 0;
+    for (uint32_t f0 = 0; f0 < total; f0 += 32) {
+        const uint32_t f  = f0 + lane;
+        bool           ok = f < total;
+        if (ok) {
+            rank_unrank(rc, f);
+            ok = all_checks_pass(cx);
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+        if (EMIT && bal) {
+            if (ok) {
+                uint32_t* rec = stage + __popc(bal & ((1u << lane) - 1u)) * R;
+                rec[0]        = module;
+                for (int c = 0; c < cx.C; c++) rec[1 + c] = (uint32_t)placed(cx, c);
+            }
+            __syncwarp();
+            const uint32_t words = (uint32_t)__popc(bal) * R;
+            uint32_t*      dst   = out + found * (uint64_t)R;
+            for (uint32_t i = lane; i < words; i += 32) dst[i] = stage[i];
+            __syncwarp();
+        }
+        found += __popc(bal);
+    }
+    return found;
+}
+
 struct Smem {
     uint32_t* occ;       // [n_symbols][WP]
     uint32_t* blob;      // [groups][kBlobStage]
     uint32_t* M;         // [groups][cmax][W]
-    uint32_t* S;         // [groups][cmax][WS]
-    uint32_t* T;         // [groups][W]   thinned chain of component 0 / per-word site counts
-    uint32_t* stack_p;   // [cmax][kThreads]
-    uint32_t* stack_t;   // [cmax][kThreads]
+    uint32_t* T;         // [groups][cmax][W]
+    uint32_t* SM;        // [groups][cmax][WS]
+    uint32_t* ST;        // [groups][cmax][WS]
+    uint32_t* stack;     // [cmax][kThreads]
+    uint32_t* rank;      // [groups][rank_words] rank-space scratch (32-lane groups only)
     uint64_t* item_off;  // [units_per_chunk] (emit only)
 };
 
+// Rank-space scratch of one group, in words: N, PS, staging, then the u16 arrays.
+__host__ __device__ inline uint32_t rank_words(uint32_t cmax, uint32_t W, uint32_t cap)
+{
+    if (cap == 0) return 0;
+    return cap + (cap + cmax + 1) + 32 * (cmax + 1) + (cap + 1) / 2 + (cmax * W + 1) / 2 + (cmax + 2) / 2;
+}
+
 __host__ __device__ inline uint32_t smem_words(uint32_t n_symbols, uint32_t cmax, uint32_t W, uint32_t WS, uint32_t groups,
-                                               uint32_t units_per_chunk)
+                                               uint32_t units_per_chunk, uint32_t cap)
 {
     uint32_t words = n_symbols * (W + kOccPad);
-    words += groups * (kBlobStage + cmax * W + cmax * WS + W);
-    words += 2 * cmax * kThreads;
+    words += groups * (kBlobStage + 2 * cmax * (W + WS) + rank_words(cmax, W, cap));
+    words += cmax * kThreads;
     words = (words + 1) & ~1u;
     words += 2 * units_per_chunk;
     return words;
@@ -233,13 +672,14 @@ __device__ __forceinline__ Smem carve(uint32_t* base, const DevLibrary& lib, con
 {
     const uint32_t groups = kThreads / G, WP = plan.W + kOccPad;
     Smem           s;
-    s.occ     = base;               base += lib.n_symbols * WP;
-    s.blob    = base;               base += groups * kBlobStage;
-    s.M       = base;               base += groups * lib.cmax * plan.W;
-    s.S       = base;               base += groups * lib.cmax * plan.WS;
-    s.T       = base;               base += groups * plan.W;
-    s.stack_p = base;               base += lib.cmax * kThreads;
-    s.stack_t = base;               base += lib.cmax * kThreads;
+    s.occ   = base;               base += lib.n_symbols * WP;
+    s.blob  = base;               base += groups * kBlobStage;
+    s.M     = base;               base += groups * lib.cmax * plan.W;
+    s.T     = base;               base += groups * lib.cmax * plan.W;
+    s.SM    = base;               base += groups * lib.cmax * plan.WS;
+    s.ST    = base;               base += groups * lib.cmax * plan.WS;
+    s.stack = base;               base += lib.cmax * kThreads;
+    s.rank  = base;               base += groups * rank_words(lib.cmax, plan.W, plan.list_cap);
     uintptr_t p = reinterpret_cast<uintptr_t>(base);
     p           = (p + 7) & ~(uintptr_t)7;
     s.item_off  = reinterpret_cast<uint64_t*>(p);
@@ -270,6 +710,7 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const DevLibrary lib, 
 {
     using Gr = Group<G>;
     extern __shared__ __align__(16) uint32_t smem_raw[];
+    __shared__ uint32_t next_unit;
     const uint32_t chunk = blockIdx.x;
     if (EMIT && work.chunk_sites[chunk] == 0) return;   // nothing to write for this chunk
 
@@ -280,19 +721,21 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const DevLibrary lib, 
     const int      n  = (int)(query.seq_begin[qi + 1] - sb);
     const uint8_t* seq = query.seqs + sb;
     const uint32_t* pair_mask = query.masks + query.mask_begin[qi];
+    const int      band = query.band[qi];
     const int      W = (int)plan.W, WS = (int)plan.WS, WP = W + kOccPad;
     const int      Wq = (n + 32) >> 5;
 
     Smem sm = carve<G>(smem_raw, lib, plan);
+    if (threadIdx.x == 0) next_unit = u0;
     build_occurrence(sm.occ, lib, seq, n, W);
 
-    constexpr uint32_t groups = kThreads / G;
-    const uint32_t     gid    = threadIdx.x / G;
-    uint32_t*          g_blob = sm.blob + gid * kBlobStage;
-    uint32_t*          g_M    = sm.M + gid * lib.cmax * W;
-    uint32_t*          g_S    = sm.S + gid * lib.cmax * WS;
-    uint32_t*          g_T    = sm.T + gid * W;
-    const uint64_t     item0  = (uint64_t)qi * lib.n_units;
+    const uint32_t gid    = threadIdx.x / G;
+    uint32_t*      g_blob = sm.blob + gid * kBlobStage;
+    uint32_t*      g_M    = sm.M + gid * lib.cmax * W;
+    uint32_t*      g_T    = sm.T + gid * lib.cmax * W;
+    uint32_t*      g_SM   = sm.SM + gid * lib.cmax * WS;
+    uint32_t*      g_ST   = sm.ST + gid * lib.cmax * WS;
+    const uint64_t item0  = (uint64_t)qi * lib.n_units;
 
     if (EMIT) {
         // Word offset of every item of the chunk: exclusive scan of count * record length.
@@ -317,18 +760,18 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const DevLibrary lib, 
 
     uint64_t my_sites = 0, my_words = 0;   // accumulated by lane 0 of each group (count pass)
 
-    for (uint32_t u = u0 + gid; u < u1; u += groups) {
-        uint32_t count_known = 0;
-        if (EMIT) {
-            count_known = work.counts[item0 + u];
-            if (count_known == 0) continue;
-        }
+    for (;;) {
+        uint32_t u = 0;
+        if (Gr::lane() == 0) u = atomicAdd(&next_unit, 1u);
+        u = Gr::first(u);
+        if (u >= u1) break;
+        if (EMIT && work.counts[item0 + u] == 0) continue;
+
         // stage the unit descriptor
         const uint32_t  boff  = __ldg(lib.unit_off + u);
         const uint32_t  blen  = __ldg(lib.unit_off + u + 1) - boff;
         const uint32_t* gblob = lib.blob + boff;
         const uint32_t* blob  = gblob;
-        Gr::sync();
         if (blen <= kBlobStage) {
             for (uint32_t i = Gr::lane(); i < blen; i += G) g_blob[i] = __ldg(gblob + i);
             blob = g_blob;
@@ -342,31 +785,50 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const DevLibrary lib, 
         bool alive = true;
         if (!EMIT && gate != kNoGate) {   // an emitted item has already passed its gate
             const uint32_t* gb = lib.blob + __ldg(lib.unit_off + gate);
-            alive              = gate_open<G>(gb, sm.occ, WP, g_M, g_S, W, WS, n);
+            alive              = gate_open<G>(gb, sm.occ, WP, g_M, g_SM, W, WS, n);
             Gr::sync();
         }
-        if (alive) alive = match_components<G>(blob, sm.occ, WP, g_M, g_S, W, WS, n);
+        // An empty first pattern at position 0 with delay 0 leaves "no room" (unsigned wrap in
+        // the reference, cppsrc/Motif.cpp:461) and ends the enumeration before it starts.
+        if (C > 1 && (blob[4] & 0xFFu) == 0 && delay == 0) alive = false;
+        if (alive) alive = match_components<G>(blob, sm.occ, WP, g_M, g_SM, W, WS, n);
 
         uint64_t item_sites = 0;
         if (alive) {
-            // Component 0: its matches from position 0, leftmost and non-overlapping.
-            const uint32_t* first = g_M;
-            if (blob[3] & 1u) {
-                for (int w = Gr::lane(); w < W; w += G) g_T[w] = 0;
-                Gr::sync();
-                if (Gr::lane() == 0) {
-                    const int k0 = (int)(blob[4] & 0xFFu);
-                    for (int q = next_match(g_M, g_S, W, WS, 0); q >= 0; q = next_match(g_M, g_S, W, WS, q + (k0 > 0 ? k0 : 1)))
-                        g_T[q >> 5] |= 1u << (q & 31);
-                }
-                Gr::sync();
-                first = g_T;
-            }
-
             ItemCtx cx;
-            cx.blob = blob; cx.M = g_M; cx.S = g_S; cx.mask = pair_mask;
-            cx.stack_p = sm.stack_p + threadIdx.x; cx.stack_t = sm.stack_t + threadIdx.x;
-            cx.W = W; cx.WS = WS; cx.n = n; cx.mstride = (n + 31) >> 5; cx.C = C; cx.delay = delay;
+            cx.blob = blob; cx.M = g_M; cx.T = g_T; cx.SM = g_SM; cx.ST = g_ST; cx.mask = pair_mask;
+            cx.stack = sm.stack + threadIdx.x;
+            cx.ovl   = thin_components<G>(blob, g_M, g_SM, g_T, g_ST, W, WS);
+            cx.W = W; cx.WS = WS; cx.n = n; cx.mstride = (n + 31) >> 5; cx.C = C; cx.delay = delay; cx.band = band;
+
+            bool ranked = false;
+            if constexpr (G == 32) {
+                if (plan.list_cap) {
+                    const uint32_t cap = plan.list_cap;
+                    uint32_t*      rw  = sm.rank + gid * rank_words(lib.cmax, plan.W, cap);
+                    RankCtx        rc;
+                    rc.cx   = cx;
+                    rc.N    = rw;                        rw += cap;
+                    rc.PS   = rw;                        rw += cap + lib.cmax + 1;
+                    uint32_t* stage = rw;                rw += 32 * (lib.cmax + 1);
+                    rc.mpos = reinterpret_cast<uint16_t*>(rw);   rw += (cap + 1) / 2;
+                    rc.MWP  = reinterpret_cast<uint16_t*>(rw);   rw += (lib.cmax * plan.W + 1) / 2;
+                    rc.lbeg = reinterpret_cast<uint16_t*>(rw);
+                    if (rank_build_lists(rc, (int)cap)) {
+                        const uint64_t total = rank_count(rc);
+                        if (total != ~0ull) {
+                            ranked = true;
+                            if (total) {
+                                uint32_t* out = EMIT ? records + sm.item_off[u - u0] : nullptr;
+                                item_sites    = rank_walk<EMIT>(rc, (uint32_t)total, module, out, stage);
+                            }
+                        }
+                    }
+                }
+            }
+            if (!ranked) {
+            // Component 0: its chain from position 0 starts on a run start, i.e. it is the thinned set.
+            const uint32_t* first = (cx.ovl & 1u) ? g_T : g_M;
 
             if (!EMIT) {
                 uint64_t mine = 0;
@@ -397,7 +859,9 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const DevLibrary lib, 
                 }
                 item_sites = carry;
             }
+            }
         }
+        Gr::sync();   // the group's scratch is reused by its next item
         if (!EMIT && Gr::lane() == 0) {
             if (item_sites > 0xFFFFFFFFull) atomicOr((unsigned long long*)(work.totals + 2), 1ull);
             work.counts[item0 + u] = (uint32_t)item_sites;
@@ -469,6 +933,32 @@ __global__ void __launch_bounds__(1024) scan_kernel(const Plan plan, const Work 
     }
 }
 
+// band[q] = max v - u over the set bits (u, v), u < v < n, of the pair mask of sequence q.
+// One warp per mask row; grid = (sequences, row slices).
+__global__ void __launch_bounds__(256) band_kernel(const DevQuery query, int32_t* __restrict__ band)
+{
+    const uint32_t qi = blockIdx.x;
+    const int      n  = (int)(query.seq_begin[qi + 1] - query.seq_begin[qi]);
+    const int      Wm = (n + 31) >> 5;
+    const uint32_t* mask = query.masks + query.mask_begin[qi];
+    const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int            best = -1;
+    for (int u = blockIdx.y * 8 + warp; u < n; u += gridDim.y * 8) {
+        for (int w = Wm - 1 - lane; w >= (u >> 5); w -= 32) {   // from the far end of the row
+            uint32_t x = __ldg(mask + (size_t)u * Wm + w);
+            if (w == (u >> 5)) x &= (u & 31) == 31 ? 0u : (0xFFFFFFFFu << ((u & 31) + 1));
+            if (w == Wm - 1 && (n & 31)) x &= (1u << (n & 31)) - 1u;
+            if (x) {
+                best = max(best, (w << 5) + 31 - __clz(x) - u);
+                break;   // words further left of this lane's are closer to the diagonal
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, d));
+    if (lane == 0 && best >= 0) atomicMax(band + qi, best);
+}
+
 template <bool EMIT>
 cudaError_t launch_search(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
                           cudaStream_t s)
@@ -500,18 +990,33 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
     p.WS = (p.W + 31) / 32;
     p.group = p.W <= 4 ? 4 : p.W <= 8 ? 8 : p.W <= 16 ? 16 : 32;
     const uint32_t groups = kThreads / p.group;
-    // Enough chunks to give every SM several CTAs, but whole multiples of the groups in a CTA.
-    const uint32_t target = (uint32_t)sm_count * 8u;
+    // Several waves of CTAs, so that the hardware scheduler evens out chunks of unequal cost;
+    // a chunk holds at least a few items per group to amortise its occurrence rows.
+    const uint32_t target = (uint32_t)sm_count * 24u;
     uint32_t       per_seq = n_seqs >= target ? 1u : (target + n_seqs - 1) / (n_seqs ? n_seqs : 1);
     uint32_t       upc     = (lib.n_units + per_seq - 1) / (per_seq ? per_seq : 1);
     upc                    = ((upc + groups - 1) / groups) * groups;
-    if (upc < groups) upc = groups;
+    if (upc < 4 * groups) upc = 4 * groups;
     if (upc > kMaxChunkUnits) upc = kMaxChunkUnits;
     p.units_per_chunk = upc;
     p.chunks_per_seq  = lib.n_units ? (lib.n_units + upc - 1) / upc : 0;
     p.n_chunks        = p.chunks_per_seq * n_seqs;
-    p.smem_bytes      = 4u * smem_words(lib.n_symbols, lib.cmax, p.W, p.WS, groups, upc);
+    p.list_cap        = p.group == 32 ? 384u : 0u;
+    p.smem_bytes      = 4u * smem_words(lib.n_symbols, lib.cmax, p.W, p.WS, groups, upc, p.list_cap);
     return p;
+}
+
+cudaError_t launch_band(const DevQuery& q, int32_t* band, cudaStream_t s)
+{
+    if (q.n_seqs == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(band, 0xFF, sizeof(int32_t) * (size_t)q.n_seqs, s);   // -1: no pair allowed
+    if (e != cudaSuccess) return e;
+    // one warp per row, 8 rows per CTA and pass: slice long sequences over several CTAs
+    uint32_t slices = q.n_seqs >= 1024 ? 1u : (q.max_len + 63) / 64;
+    slices          = slices < 1 ? 1u : slices > 64 ? 64u : slices;
+    dim3 grid(q.n_seqs, slices);
+    band_kernel<<<grid, 256, 0, s>>>(q, band);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s)

@@ -192,3 +192,103 @@ def test_full_size_c4_properties_and_reference_sample(tmp_path, kind, mask_kind)
         h.close()
     sub_dev.close()
     dev.close()
+
+
+# ---------------------------------------------------------------------------------------
+# random flat tables: chains of overlapping matches x band windows x every check shape
+# ---------------------------------------------------------------------------------------
+def _random_table(rng, n_units, alphabet, max_comp, max_len, min_len=1, short_limit=None):
+    """short_limit: units holding a pattern shorter than min_len + 1 get at most that many components
+    (keeps the number of placements the Python interpreter has to enumerate bounded)."""
+    pats, comp_begin, unit_comp_begin, unit_check_begin, checks, delays = [], [0], [0], [0], [], []
+    for _ in range(n_units):
+        C = int(rng.integers(1, max_comp + 1))
+        lens = []
+        for _c in range(C):
+            k = int(rng.integers(0 if rng.random() < 0.05 else min_len, max_len + 1))
+            if short_limit is not None and k <= min_len and _c >= short_limit:
+                k = max_len
+            p = [alphabet[i] for i in rng.integers(0, len(alphabet), k)]
+            p = [0x2E if rng.random() < 0.15 else x for x in p]
+            pats.extend(p)
+            comp_begin.append(len(pats))
+            lens.append(k)
+        unit_comp_begin.append(len(comp_begin) - 1)
+        for _k in range(int(rng.integers(0, 4))):
+            kind = rng.random()
+            a = int(rng.integers(0, C))
+            b = int(rng.integers(0, C))
+            if kind < 0.15:
+                a = -1
+            elif kind < 0.25:
+                b = a
+            ao = int(rng.integers(0, 40)) if a < 0 else int(rng.integers(-2, max(lens[a], 1) + 2))
+            bo = int(rng.integers(0, 40)) if b < 0 else int(rng.integers(-2, max(lens[b], 1) + 2))
+            checks.append((a, ao, b, bo))
+        unit_check_begin.append(len(checks))
+        delays.append(int(rng.integers(0, 6)))
+    return {
+        "n_modules": n_units, "n_units": n_units, "n_gates": 0,
+        "unit_module": np.arange(n_units, dtype=np.uint32), "unit_delay": np.array(delays, np.uint32),
+        "unit_gate": np.full(n_units, 0xFFFFFFFF, np.uint32), "unit_comp_begin": np.array(unit_comp_begin, np.uint32),
+        "comp_pat_begin": np.array(comp_begin, np.uint32), "pattern": np.array(pats, np.uint8) if pats else np.zeros(0, np.uint8),
+        "unit_check_begin": np.array(unit_check_begin, np.uint32),
+        "checks": np.array(checks, np.int16).reshape(-1, 4),
+    }
+
+
+def _banded_random_mask(n, seed, span, density):
+    rng = np.random.default_rng(seed)
+    u, v = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    return b.pack_mask((rng.random((n, n)) < density) & (v > u) & (v - u <= span))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_tables_against_interpreter(seed):
+    rng = np.random.default_rng(900 + seed)
+    alphabet = [ord(c) for c in ("AG" if seed % 3 == 0 else "ACG" if seed % 3 == 1 else "ACGU")]
+    n = int([37, 64, 97, 130, 200, 33][seed % 6])
+    table = _random_table(rng, 60, alphabet, max_comp=4 if n < 100 else 3, max_len=4)
+    # low-complexity queries: long runs and periodic stretches make matches overlap
+    body = [alphabet[i] for i in rng.integers(0, len(alphabet), n)]
+    for _ in range(4):
+        at, run = int(rng.integers(0, n)), int(rng.integers(3, 12))
+        unit = [alphabet[i] for i in rng.integers(0, len(alphabet), int(rng.integers(1, 3)))]
+        for j in range(run):
+            if at + j < n:
+                body[at + j] = unit[j % len(unit)]
+    seq = bytes(body)
+    span = [n, 12, 30, 5][seed % 4]
+    mask = _banded_random_mask(n, seed, span, [1.0, 0.6, 0.3][seed % 3])
+    dev = b.DeviceLibrary.from_table(table)
+    got = dev.search(seq, mask)
+    expect = flat_interp.search_table(table, seq, mask)
+    assert np.array_equal(got.records(), expect)
+    got.close()
+    dev.close()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_tables_long_sequences(seed):
+    """Sequences long enough for 32-lane groups: the rank-space walk (match lists, counting
+    programme, unranking) and its fall-back to the depth-first walk when the lists are too long."""
+    rng = np.random.default_rng(1700 + seed)
+    alphabet = [ord(c) for c in ("ACGU" if seed % 2 == 0 else "ACG")]
+    n = int([520, 640, 777, 900, 1025][seed % 5])
+    table = _random_table(rng, 40, alphabet, max_comp=3, max_len=5, min_len=2 if seed % 3 else 1, short_limit=1)
+    body = [alphabet[i] for i in rng.integers(0, len(alphabet), n)]
+    for _ in range(10):
+        at, run = int(rng.integers(0, n)), int(rng.integers(3, 14))
+        unit = [alphabet[i] for i in rng.integers(0, len(alphabet), int(rng.integers(1, 3)))]
+        for j in range(run):
+            if at + j < n:
+                body[at + j] = unit[j % len(unit)]
+    seq = bytes(body)
+    span = [n, 25, 60, 8][seed % 4]
+    mask = _banded_random_mask(n, seed, span, [1.0, 0.5, 0.25][seed % 3])
+    dev = b.DeviceLibrary.from_table(table)
+    got = dev.search(seq, mask)
+    expect = flat_interp.search_table(table, seq, mask)
+    assert np.array_equal(got.records(), expect)
+    got.close()
+    dev.close()
