@@ -100,11 +100,12 @@ struct bss_library {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t  ev[4]      = {nullptr, nullptr, nullptr, nullptr};
     bss::DevLibrary       dev{};
-    DeviceBuffer          d_blob, d_unit_off;
+    DeviceBuffer          d_blob, d_unit_off, d_unit_rlen;
     uint32_t              n_modules = 0, n_units = 0;
     std::vector<uint32_t> module_components;
     // work buffers, reused across searches
-    DeviceBuffer d_counts, d_chunk_sites, d_chunk_words, d_totals, d_seq_word_begin;
+    DeviceBuffer d_counts, d_chunk_sites, d_chunk_words, d_totals, d_seq_word_begin, d_alive, d_lane_counts;
+    uint32_t     n_alive = 0;   // items with sites of the last count pass
     PinnedBuffer h_totals;
     // one spare set of result buffers, recycled by bss_sites_free
     DeviceBuffer spare_records;
@@ -116,6 +117,9 @@ struct bss_query {
     int           device = 0;
     bss::DevQuery dev{};
     DeviceBuffer  storage;
+    // the occurrence table is built for one alphabet: the creating library's
+    uint32_t      n_symbols = 0, pair_rows = 0;
+    uint8_t       alphabet[32] = {};
     uint64_t      total_len = 0;
     uint64_t      h2d_bytes = 0;
 };
@@ -207,13 +211,31 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
         }
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return level[a] < level[b]; });
 
-        uint32_t pat_total = 0;
+        // match programs: one (occurrence row, shift) step per literal symbol, or per pair of
+        // adjacent literal symbols when the alphabet is small enough for pair rows
+        const bool     pairs = alphabet.size() <= bss::kPairAlphabet;
+        const uint32_t ns    = (uint32_t)alphabet.size();
+        std::vector<uint16_t>              program;
+        std::vector<std::pair<uint32_t, uint32_t>> prog_range(C);   // first step, number of steps
         for (uint32_t c = c0; c < c1; c++) {
-            const uint32_t k = t->comp_pat_begin[c + 1] - t->comp_pat_begin[c];
-            if (t->comp_pat_begin[c + 1] < t->comp_pat_begin[c] || k > BSS_MAX_PATTERN) return fail(BSS_ERR_LIMIT, "component pattern longer than BSS_MAX_PATTERN");
-            pat_total += k;
+            const uint32_t pb = t->comp_pat_begin[c], k = t->comp_pat_begin[c + 1] - pb;
+            if (t->comp_pat_begin[c + 1] < pb || k > BSS_MAX_PATTERN) return fail(BSS_ERR_LIMIT, "component pattern longer than BSS_MAX_PATTERN");
+            const uint8_t* p = t->pattern + pb;
+            const uint32_t first_step = (uint32_t)program.size();
+            for (uint32_t j = 0; j < k;) {
+                if (p[j] == '.') { j++; continue; }
+                uint32_t row = (uint32_t)code_of[p[j]], shift = j;
+                if (pairs && j + 1 < k && p[j + 1] != '.') {
+                    row = ns + row * ns + (uint32_t)code_of[p[j + 1]];
+                    j += 2;
+                } else {
+                    j += 1;
+                }
+                program.push_back((uint16_t)(row | ((shift & 31u) << 7) | ((shift >> 5) << 12)));
+            }
+            prog_range[c - c0] = {first_step, (uint32_t)program.size() - first_step};
         }
-        const uint32_t pat_words = (pat_total + 3) / 4;
+        const uint32_t pat_words = ((uint32_t)program.size() + 1) / 2;
         const uint32_t head      = 4 + 2 * C;
         const size_t   base      = blob.size();
         blob.resize(base + head + pat_words + 2 * (size_t)NK, 0);
@@ -222,19 +244,14 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
         b[1] = C | (NK << 8) | (t->unit_delay[u] << 16);
         b[2] = gate;
         b[3] = (head + pat_words) << 16;
-        uint8_t* pat_bytes = reinterpret_cast<uint8_t*>(b + head);
-        uint32_t byte_off  = 0, next_check = 0;
+        if (!program.empty()) std::memcpy(b + head, program.data(), program.size() * sizeof(uint16_t));
+        uint32_t next_check = 0;
         for (uint32_t c = 0; c < C; c++) {
             const uint32_t pb = t->comp_pat_begin[c0 + c], k = t->comp_pat_begin[c0 + c + 1] - pb;
-            b[4 + 2 * c] = k | ((head * 4 + byte_off) << 8) | (can_self_overlap(t->pattern + pb, k) ? bss::kCompOverlap : 0u);
-            for (uint32_t j = 0; j < k; j++) {
-                const uint8_t ch = t->pattern[pb + j];
-                pat_bytes[byte_off + j] = ch == '.' ? (uint8_t)bss::kWildcard : (uint8_t)code_of[ch];
-            }
-            byte_off += k;
+            b[4 + 2 * c] = k | ((head * 2 + prog_range[c].first) << 8) | (can_self_overlap(t->pattern + pb, k) ? bss::kCompOverlap : 0u);
             const uint32_t begin = next_check;
             while (next_check < NK && level[order[next_check]] == (int)c) next_check++;
-            b[5 + 2 * c] = begin | (next_check << 8);
+            b[5 + 2 * c] = begin | (next_check << 8) | (prog_range[c].second << 16);
         }
         uint32_t* chk = b + head + pat_words;
         for (uint32_t i = 0; i < NK; i++) {
@@ -248,6 +265,11 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
                 if (a_on) std::swap(first, second);
             } else {
                 flags = bss::kCheckFixed;
+            }
+            if (!flags && first[0] >= 0 && first[0] < second[0] && t->unit_delay[u] >= 1) {
+                const uint32_t ka = t->comp_pat_begin[c0 + first[0] + 1] - t->comp_pat_begin[c0 + first[0]];
+                const uint32_t kb = t->comp_pat_begin[c0 + second[0] + 1] - t->comp_pat_begin[c0 + second[0]];
+                if (first[1] >= 0 && (uint32_t)first[1] < ka && second[1] >= 0 && (uint32_t)second[1] < kb) flags |= bss::kCheckOrdered;
             }
             chk[2 * i]     = ((uint32_t)(uint8_t)(int8_t)first[0]) | (((uint32_t)(uint16_t)first[1]) << 8) | flags;
             chk[2 * i + 1] = ((uint32_t)(uint8_t)(int8_t)second[0]) | (((uint32_t)(uint16_t)second[1]) << 8);
@@ -285,14 +307,22 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     BSS_CUDA_LIB(lib->d_unit_off.reserve(unit_off.size() * 4));
     if (!blob.empty()) BSS_CUDA_LIB(cudaMemcpy(lib->d_blob.ptr, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
     BSS_CUDA_LIB(cudaMemcpy(lib->d_unit_off.ptr, unit_off.data(), unit_off.size() * 4, cudaMemcpyHostToDevice));
+    {
+        std::vector<uint8_t> rlen(std::max<uint32_t>(1, t->n_units), 0);
+        for (uint32_t u = 0; u < t->n_units; u++) rlen[u] = (uint8_t)(t->unit_comp_begin[u + 1] - t->unit_comp_begin[u] + 1);
+        BSS_CUDA_LIB(lib->d_unit_rlen.reserve(rlen.size()));
+        BSS_CUDA_LIB(cudaMemcpy(lib->d_unit_rlen.ptr, rlen.data(), rlen.size(), cudaMemcpyHostToDevice));
+    }
     BSS_CUDA_LIB(lib->h_totals.reserve(64));
     BSS_CUDA_LIB(lib->d_totals.reserve(64));
 #undef BSS_CUDA_LIB
     lib->dev.blob      = static_cast<const uint32_t*>(lib->d_blob.ptr);
     lib->dev.unit_off  = static_cast<const uint32_t*>(lib->d_unit_off.ptr);
+    lib->dev.unit_rlen = static_cast<const uint8_t*>(lib->d_unit_rlen.ptr);
     lib->dev.n_units   = t->n_units;
     lib->dev.n_symbols = (uint32_t)alphabet.size();
     lib->dev.cmax      = cmax;
+    lib->dev.pair_rows = alphabet.size() <= bss::kPairAlphabet ? 1u : 0u;
     std::memset(lib->dev.alphabet, 0, sizeof lib->dev.alphabet);
     std::copy(alphabet.begin(), alphabet.end(), lib->dev.alphabet);
     *out = lib;
@@ -306,7 +336,7 @@ void bss_library_destroy(bss_library* lib)
     if (lib->own_stream) cudaStreamSynchronize(lib->own_stream);
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
-    lib->d_blob.release(); lib->d_unit_off.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
+    lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
     lib->d_chunk_words.release(); lib->d_totals.release(); lib->d_seq_word_begin.release(); lib->h_totals.release();
     lib->spare_records.release(); lib->spare_host.release();
     if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
@@ -355,10 +385,13 @@ int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
     BSS_CUDA(cudaSetDevice(lib->device));
     bss_query* q = new bss_query();
     q->device    = lib->device;
-    // one allocation: [seq_begin | mask_begin | band | masks | seqs]
+    // one allocation: [seq_begin | mask_begin | band | occurrence table | masks | seqs]
+    const uint32_t ns = lib->dev.n_symbols, occ_rows = ns + (lib->dev.pair_rows ? ns * ns : 0u);
+    const uint32_t occ_stride = (max_len + 32) / 32 + bss::kOccPad;
+    const size_t   occ_words  = (size_t)n_seqs * occ_rows * occ_stride;
     const size_t off_sb = 0, off_mb = off_sb + 8 * (size_t)(n_seqs + 1), off_band = off_mb + 8 * (size_t)(n_seqs + 1),
-                 off_mask = off_band + 4 * (((size_t)n_seqs + 3) & ~(size_t)3), off_seq = off_mask + 4 * total_mask,
-                 bytes = off_seq + total_len + 16;
+                 off_occ = off_band + 4 * (((size_t)n_seqs + 3) & ~(size_t)3), off_mask = off_occ + 4 * ((occ_words + 3) & ~(size_t)3),
+                 off_seq = off_mask + 4 * total_mask, bytes = off_seq + total_len + 16;
     cudaError_t e = q->storage.reserve(bytes);
     if (e != cudaSuccess) { delete q; return cuda_fail(e, "cudaMalloc(query)"); }
     char* d = static_cast<char*>(q->storage.ptr);
@@ -374,8 +407,16 @@ int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
     q->dev.band       = reinterpret_cast<const int32_t*>(d + off_band);
     q->dev.masks      = reinterpret_cast<const uint32_t*>(d + off_mask);
     q->dev.seqs       = reinterpret_cast<const uint8_t*>(d + off_seq);
+    q->dev.occ        = reinterpret_cast<const uint32_t*>(d + off_occ);
+    q->dev.occ_rows   = occ_rows;
+    q->dev.occ_stride = occ_stride;
     q->dev.n_seqs     = n_seqs;
     q->dev.max_len    = max_len;
+    q->n_symbols      = ns;
+    q->pair_rows      = lib->dev.pair_rows;
+    std::memcpy(q->alphabet, lib->dev.alphabet, sizeof q->alphabet);
+    // per-symbol (and per-symbol-pair) occurrence bit rows of every sequence, matched against by every unit
+    if (e == cudaSuccess) e = bss::launch_occ(lib->dev, q->dev, reinterpret_cast<uint32_t*>(d + off_occ), st);
     // widest pair the mask allows, per sequence: bounds the window a tied component is searched in
     if (e == cudaSuccess) e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // sb / mb are stack-owned staging
@@ -402,11 +443,21 @@ namespace {
 // the pending emit.
 int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work, uint64_t& n_words, uint64_t& n_sites)
 {
+    if (q->n_symbols != lib->dev.n_symbols || q->pair_rows != lib->dev.pair_rows || std::memcmp(q->alphabet, lib->dev.alphabet, sizeof q->alphabet))
+        return fail(BSS_ERR_INVALID, "the query was created for a library with a different pattern alphabet");
     BSS_CUDA(cudaSetDevice(lib->device));
     plan = bss::make_plan(lib->dev, q->dev.n_seqs, q->dev.max_len, lib->sm_count);
-    if (plan.smem_bytes > 200 * 1024) return fail(BSS_ERR_LIMIT, "query too long for the shared-memory working set");
+    if (plan.smem_bytes_emit > 200 * 1024) return fail(BSS_ERR_LIMIT, "query too long for the shared-memory working set");
     const uint64_t n_items = (uint64_t)q->dev.n_seqs * lib->n_units;
+    if (n_items >= 0xFFFFFFFFull) return fail(BSS_ERR_LIMIT, "more than 2^32 (sequence, unit) items in one search: split the batch");
     BSS_CUDA(lib->d_counts.reserve(std::max<uint64_t>(4, n_items * 4)));
+    BSS_CUDA(lib->d_alive.reserve(std::max<uint64_t>(4, n_items * 4)));
+    // one row of 32 counts per alive item of the rank-space walk; beyond the cap the emit pass counts again
+    const uint64_t lane_cap = plan.list_cap ? std::min<uint64_t>(n_items, 4u << 20) : 0;
+    BSS_CUDA(lib->d_lane_counts.reserve(std::max<uint64_t>(4, lane_cap * 128)));
+    work.alive       = static_cast<uint32_t*>(lib->d_alive.ptr);
+    work.lane_counts = static_cast<uint32_t*>(lib->d_lane_counts.ptr);
+    work.lane_cap    = (uint32_t)lane_cap;
     BSS_CUDA(lib->d_chunk_sites.reserve(8 * (size_t)(plan.n_chunks + 1)));
     BSS_CUDA(lib->d_chunk_words.reserve(8 * (size_t)(plan.n_chunks + 1)));
     BSS_CUDA(lib->d_seq_word_begin.reserve(8 * (size_t)(q->dev.n_seqs + 1)));
@@ -424,16 +475,17 @@ int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& 
     BSS_CUDA(cudaEventRecord(lib->ev[1], st));
     BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));
     BSS_CUDA(cudaEventRecord(lib->ev[2], st));
-    BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 24, cudaMemcpyDeviceToHost, st));
+    BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 32, cudaMemcpyDeviceToHost, st));
     BSS_CUDA(cudaStreamSynchronize(st));
     const uint64_t* tot = static_cast<const uint64_t*>(lib->h_totals.ptr);
     n_words             = tot[0];
     n_sites             = tot[1];
+    lib->n_alive        = (uint32_t)tot[3];
     lib->stats.kernel_launches   = (plan.n_chunks ? 1u : 0u) + 1u;
     lib->stats.placements_tested = q->total_len * lib->n_units;
     lib->stats.n_sites           = n_sites;
     lib->stats.n_words           = n_words;
-    lib->stats.d2h_bytes         = 24;
+    lib->stats.d2h_bytes         = 32;
     if (tot[2] & 1) return fail(BSS_ERR_COUNT, "a unit has 2^32 or more sites on one sequence");
     return BSS_OK;
 }
@@ -442,7 +494,7 @@ int run_emit(bss_library* lib, const bss_query* q, const bss::Plan& plan, const 
 {
     cudaStream_t st = lib->stream;
     if (n_words && plan.n_chunks) {
-        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, st));
+        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, lib->n_alive, st));
         lib->stats.kernel_launches++;
     }
     BSS_CUDA(cudaEventRecord(lib->ev[3], st));

@@ -11,31 +11,38 @@ constexpr uint32_t kWildcard   = 0xFFu;        // pattern symbol code of '.'
 constexpr int      kOccPad     = 10;           // zero words after each occurrence row (patterns up to 255+32 bytes)
 constexpr int      kBlobStage  = 64;           // unit descriptor words staged in shared memory per group
 constexpr uint32_t kNoGate     = 0xFFFFFFFFu;
+constexpr uint32_t kPairAlphabet = 8;          // largest alphabet that gets pair rows (row index must stay below 128)
 constexpr uint32_t kMaxChunkUnits = 2048;      // units per chunk (bounds the per-CTA offset table)
 constexpr uint32_t kCompOverlap = 1u << 24;    // component flag: the pattern is compatible with a shifted copy of itself
 constexpr uint32_t kCheckFixed  = 1u << 24;    // check flag: no end moves at the check's level, or both do
+constexpr uint32_t kCheckOrdered = 1u << 25;   // check flag: 0 <= u < v < n holds for every placement (u = word 0's end)
 
 // Unit descriptor ("blob"), u32 words, one per unit, addressed by unit_off[unit]:
 //   [0] module index
 //   [1] C | n_checks << 8 | delay << 16
 //   [2] gate unit or kNoGate
 //   [3] word offset of the checks << 16
-//   [4 + 2c]   k_c | pattern byte offset << 8 (16 bits, from the start of the blob) | kCompOverlap
-//   [5 + 2c]   first check ready at level c | one past the last << 8
-//   pattern symbol codes (1 byte each, kWildcard = '.'), padded to a word
+//   [4 + 2c]   k_c | offset of the match program << 8 (16 bits, in u16 units from the start of the blob) | kCompOverlap
+//   [5 + 2c]   first check ready at level c | one past the last << 8 | steps of the match program << 16
+//   match programs, one u16 per step: occurrence row (7 bits) | shift & 31 << 7 | shift >> 5 << 12;
+//       the match mask of the component is the AND of its rows shifted down by their shifts
 //   checks, 2 words each, ordered by the level at which both ends are placed. Word 0 is the
 //   end that is known BEFORE the check's level is entered (an earlier component or an absolute
 //   position), word 1 the end on the component placed at the check's level:
 //       anchor(int8) | off(int16) << 8 | flags << 24
 //   kCheckFixed (on word 0) marks checks without that shape (both ends on the level's own
 //   component, or both absolute): they are evaluated per candidate but give no band window.
+//   kCheckOrdered (on word 0): both ends sit inside their components, word 0's component comes
+//   first and delay >= 1, so u < v and both are inside the sequence without testing.
 struct DevLibrary {
     const uint32_t* blob;
     const uint32_t* unit_off;    // [n_units + n_gates + 1] word offsets into blob
+    const uint8_t*  unit_rlen;   // [n_units] words per record of the unit: components + 1
     uint32_t        n_units;     // searched units
     uint32_t        n_symbols;   // alphabet size
     uint32_t        cmax;        // max components per unit (gates included)
     uint32_t        module_base; // added to every module index written into a record (library shards)
+    uint32_t        pair_rows;   // 1: the match programs use pair rows (alphabet of at most kPairAlphabet symbols)
     uint8_t         alphabet[32];
 };
 
@@ -45,6 +52,9 @@ struct DevQuery {
     const uint32_t* masks;
     const uint64_t* mask_begin;   // [n_seqs + 1], in words
     const int32_t*  band;         // [n_seqs] max v-u over the set bits above the diagonal, -1 when there is none
+    const uint32_t* occ;          // [n_seqs][occ_rows][occ_stride] occurrence table (see occ_kernel)
+    uint32_t        occ_rows;     // n_symbols, plus n_symbols^2 pair rows for small alphabets
+    uint32_t        occ_stride;   // words per row: ceil((max_len + 1) / 32) + kOccPad
     uint32_t        n_seqs;
     uint32_t        max_len;
 };
@@ -59,23 +69,28 @@ struct Plan {
     uint32_t W;            // match-mask words per component, ceil((max_len + 1) / 32)
     uint32_t WS;           // summary words per component, ceil(W / 32)
     uint32_t list_cap;     // rank-space walk: match-list entries per item (0 = depth-first walk only)
-    uint32_t smem_bytes;
+    uint32_t smem_bytes;        // dynamic shared memory of the count kernel
+    uint32_t smem_bytes_emit;   // ... of the emit kernel (adds the record staging)
 };
 
 struct Work {
     uint32_t* counts;        // [n_seqs * n_units] sites per item
     uint64_t* chunk_sites;   // [n_chunks]
     uint64_t* chunk_words;   // [n_chunks] ; after the scan: exclusive prefix, [n_chunks] = total
-    uint64_t* totals;        // [0] words, [1] sites, [2] error flags
+    uint64_t* totals;        // [0] words, [1] sites, [2] error flags, [3] items with sites (length of `alive`)
+    uint32_t* alive;         // [n_seqs * n_units] items with sites, in completion order
+    uint32_t* lane_counts;   // [lane_cap][32] sites of every lane's run of ranks (rank-space walk)
+    uint32_t  lane_cap;      // alive-list slots that have a lane_counts row
     uint64_t* seq_word_begin;   // [n_seqs + 1]
 };
 
 Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_count);
 
 cudaError_t launch_band(const DevQuery& q, int32_t* band, cudaStream_t s);
+cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, cudaStream_t s);
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s);
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s);
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                        cudaStream_t s);
+                        uint32_t n_alive, cudaStream_t s);
 
 }   // namespace bss

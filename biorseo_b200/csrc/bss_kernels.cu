@@ -28,7 +28,26 @@
 // Not a contraction: integer/bit work only, no tensor cores.
 #include "bss_device.cuh"
 
+#include <cstdlib>
+
 namespace bss {
+
+// Optional per-phase cycle accounting (debug builds only: -DBSS_PHASE_TIMING). Sums, over all
+// groups, the cycles between phase boundaries; read back with bss_debug_phase_cycles().
+#ifdef BSS_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define BSS_PHASE(id)                                                                  \
+    do {                                                                               \
+        const long long now_ = clock64();                                              \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[id], (unsigned long long)(now_ - phase_t0_)); \
+        phase_t0_ = now_;                                                              \
+    } while (0)
+#define BSS_PHASE_BEGIN() long long phase_t0_ = clock64()
+#else
+#define BSS_PHASE(id) do { } while (0)
+#define BSS_PHASE_BEGIN() do { } while (0)
+#endif
+
 namespace {
 
 __device__ __forceinline__ int unpack_anchor(uint32_t w) { return (int)(int8_t)(w & 0xFFu); }
@@ -87,8 +106,12 @@ __device__ __forceinline__ bool checks_pass(const ItemCtx& cx, int level)
         const int      aa = unpack_anchor(ea), ba = unpack_anchor(eb);
         const int      u  = (aa < 0 ? 0 : placed(cx, aa)) + unpack_off(ea);
         const int      v  = (ba < 0 ? 0 : placed(cx, ba)) + unpack_off(eb);
-        const int      a = min(u, v), b = max(u, v);
-        if (a < 0 || b >= cx.n || a == b) return false;
+        int            a = u, b = v;
+        if (!(ea & kCheckOrdered)) {   // ordered checks have 0 <= u < v < n by construction
+            a = min(u, v);
+            b = max(u, v);
+            if (a < 0 || b >= cx.n || a == b) return false;
+        }
         if (!((__ldg(cx.mask + (size_t)a * cx.mstride + (b >> 5)) >> (b & 31)) & 1u)) return false;
     }
     return true;
@@ -243,32 +266,36 @@ struct Group {
 };
 
 // Match masks of the components of one unit: M[c][w] bit b = pattern c matches at 32w + b.
+// Every component carries a match program (row of the query's occurrence table, shift): the
+// mask is the AND of the shifted rows. Rows are single symbols or, for small alphabets, pairs
+// of adjacent symbols (half the steps). The table lives in global memory (a few KB per
+// sequence, built once per query) and is read through L1.
 // Returns false as soon as one component has no match at all (the unit cannot be placed).
 template <int G>
-__device__ __forceinline__ bool match_components(const uint32_t* blob, const uint32_t* occ, int WP, uint32_t* M, uint32_t* S,
-                                                 int W, int WS, int n)
+__device__ __forceinline__ bool match_components(const uint32_t* blob, const uint32_t* __restrict__ occ, int WP, uint32_t* M,
+                                                 uint32_t* S, int W, int WS, int n)
 {
     using Gr       = Group<G>;
     const int  C   = (int)(blob[1] & 0xFFu);
     const int  Wq  = (n + 32) >> 5;   // ceil((n + 1) / 32): positions 0..n
-    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(blob);
+    const uint16_t* halves = reinterpret_cast<const uint16_t*>(blob);
     for (int c = 0; c < C; c++) {
-        const uint32_t desc = blob[4 + 2 * c];
-        const int      k    = (int)(desc & 0xFFu);
-        const uint8_t* pat  = bytes + ((desc >> 8) & 0xFFFFu);
-        const int      last = n - k;   // last position where the pattern still fits (k = 0: position n)
-        bool           any  = false;
+        const uint32_t  desc  = blob[4 + 2 * c];
+        const int       k     = (int)(desc & 0xFFu);
+        const int       steps = (int)((blob[5 + 2 * c] >> 16) & 0xFFu);
+        const uint16_t* prog  = halves + ((desc >> 8) & 0xFFFFu);
+        const int       last  = n - k;   // last position where the pattern still fits (k = 0: position n)
+        bool            any   = false;
         for (int w0 = 0; w0 < W; w0 += G) {
             const int w = w0 + (int)Gr::lane();
             uint32_t  m = 0;
             if (w < Wq && last >= (w << 5)) {
                 const int hi = last - (w << 5);
                 m            = hi >= 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u);
-                for (int j = 0; j < k && m; j++) {
-                    const uint32_t sym = pat[j];
-                    if (sym == kWildcard) continue;
-                    const uint32_t* row = occ + sym * WP + w + (j >> 5);
-                    m &= __funnelshift_r(row[0], row[1], j & 31);
+                for (int i = 0; i < steps; i++) {
+                    const uint32_t  st  = prog[i];
+                    const uint32_t* row = occ + (st & 0x7Fu) * WP + w + (st >> 12);
+                    m &= __funnelshift_r(__ldg(row), __ldg(row + 1), (st >> 7) & 31u);
                 }
             }
             if (w < W) M[c * W + w] = m;
@@ -377,10 +404,14 @@ __device__ __forceinline__ bool gate_open(const uint32_t* gblob, const uint32_t*
 struct RankCtx {
     ItemCtx   cx;
     uint16_t* mpos;    // [cap] match positions, lists of the components back to back
-    uint32_t* N;       // [cap] placements below each match (components c+1.. only)
+    uint32_t* N;       // [cap] placements below each match (components c+1.. only); kHasGreedy: some of its
+                       //       children are greedy matches (rare: re-derived with kids_of)
+    uint32_t* KID;     // [cap] list range [ja, jb) of the children of each match: ja | jb << 16
     uint32_t* PS;      // [cap + C] per component a_c + 1 prefix sums of N over the thinned matches
     uint16_t* MWP;     // [C][W] matches before each mask word
     uint16_t* lbeg;    // [C + 1] first list entry of each component
+    uint32_t* idx;     // this thread's odometer column (stride kThreads): list index | end of the sibling range << 16
+    uint32_t* aux;     // this thread's column: start of the sibling range | greedy siblings left (this one included) << 16
 };
 
 __device__ __forceinline__ int list_len(const RankCtx& rc, int c) { return (int)rc.lbeg[c + 1] - (int)rc.lbeg[c]; }
@@ -405,6 +436,12 @@ __device__ __forceinline__ bool is_thinned(const RankCtx& rc, int c, int pos)
 struct Kids {
     int efirst, nex, ja, jb;
 };
+constexpr uint32_t kHasGreedy  = 0x80000000u;   // N flag: some children of this match are greedy matches
+constexpr uint32_t kGreedyOnly = 0x40000000u;   // N flag: not in the thinned set, only ever reached as a greedy match
+constexpr uint32_t kCountMask  = 0x3FFFFFFFu;
+
+// A list entry that a parent's range [ja, jb) really contains: thinned, with placements below it.
+__device__ __forceinline__ bool in_range_live(uint32_t n) { return ((n & ~kHasGreedy) - 1u) < kCountMask; }
 
 __device__ __forceinline__ Kids kids_of(const RankCtx& rc, int c, int p)
 {
@@ -497,7 +534,7 @@ __device__ __forceinline__ bool rank_build_lists(const RankCtx& rc, int cap)
 }
 
 // Backward dynamic programme. Returns the number of placements before the checks, or
-// UINT64_MAX when a count does not fit 31 bits (the caller falls back to the depth-first walk).
+// UINT64_MAX when a count does not fit 30 bits (the caller falls back to the depth-first walk).
 __device__ __forceinline__ uint64_t rank_count(const RankCtx& rc)
 {
     const ItemCtx& cx   = rc.cx;
@@ -513,6 +550,7 @@ __device__ __forceinline__ uint64_t rank_count(const RankCtx& rc)
         for (int j0 = 0; j0 < a; j0 += 32) {
             const int j = j0 + lane;
             uint64_t  n = 0;
+            uint32_t  greedy = 0;
             int       p = 0;
             if (j < a) {
                 p = rc.mpos[b + j];
@@ -523,14 +561,17 @@ __device__ __forceinline__ uint64_t rank_count(const RankCtx& rc)
                     const int  ke = max(1, (int)(cx.blob[4 + 2 * (c + 1)] & 0xFFu));
                     int        e  = kd.efirst;
                     for (int x = 0; x < kd.nex; x++) {
-                        n += rc.N[rc.lbeg[c + 1] + match_rank(rc, c + 1, e)];
+                        n += rc.N[rc.lbeg[c + 1] + match_rank(rc, c + 1, e)] & kCountMask;
                         e = next_bit(cx.M + (c + 1) * cx.W, cx.SM + (c + 1) * cx.WS, cx.W, cx.WS, e + ke);
                     }
                     n += PSn[kd.jb] - PSn[kd.ja];
+                    rc.KID[b + j] = (uint32_t)kd.ja | ((uint32_t)kd.jb << 16);
+                    if (kd.nex) greedy = kHasGreedy;
                 }
-                if (n >= 0x80000000ull) overflow = true;
-                rc.N[b + j] = (uint32_t)n;
-                if (!is_thinned(rc, c, p)) n = 0;   // only ever reached as a greedy match, never through a range
+                if (n > kCountMask) overflow = true;
+                const bool thinned = is_thinned(rc, c, p);
+                rc.N[b + j] = (uint32_t)n | greedy | (thinned ? 0u : kGreedyOnly);
+                if (!thinned) n = 0;   // only ever reached as a greedy match, never through a range
             }
             uint64_t inc = n;
 #pragma unroll
@@ -540,7 +581,7 @@ __device__ __forceinline__ uint64_t rank_count(const RankCtx& rc)
             }
             if (j < a) PS[j + 1] = (uint32_t)(running + inc);
             running += __shfl_sync(0xFFFFFFFFu, inc, 31);
-            if (running >= 0x80000000ull) overflow = true;
+            if (running > kCountMask) overflow = true;
         }
         total = running;
         __syncwarp();
@@ -549,223 +590,411 @@ __device__ __forceinline__ uint64_t rank_count(const RankCtx& rc)
     return total;
 }
 
-// Positions of the placement of depth-first rank r into this lane's stack column.
+// First child of list entry gj (component c-1) that has placements below it: sets the odometer of level c.
+__device__ __forceinline__ void rank_first_child(const RankCtx& rc, int c, int gj)
+{
+    const ItemCtx& cx  = rc.cx;
+    const int      b   = rc.lbeg[c];
+    const uint32_t kid = rc.KID[gj];
+    const int      ja = (int)(kid & 0xFFFFu), jb = (int)(kid >> 16);
+    if (rc.N[gj] & kHasGreedy) {   // greedy matches come first, in position order
+        const Kids kd = kids_of(rc, c, (int)rc.mpos[gj]);
+        const int  ke = max(1, (int)(cx.blob[4 + 2 * c] & 0xFFu));
+        int        e  = kd.efirst;
+        for (int x = kd.nex; x > 0; x--) {
+            const int je = match_rank(rc, c, e);
+            if (rc.N[b + je] & kCountMask) {
+                rc.idx[c * kThreads]   = (uint32_t)je | ((uint32_t)jb << 16);
+                rc.aux[c * kThreads]   = (uint32_t)ja | ((uint32_t)x << 16);
+                cx.stack[c * kThreads] = (uint32_t)e;
+                return;
+            }
+            e = next_bit(cx.M + c * cx.W, cx.SM + c * cx.WS, cx.W, cx.WS, e + ke);
+        }
+    }
+    int j = ja;
+    while (j < jb && !in_range_live(rc.N[b + j])) j++;
+    rc.idx[c * kThreads]   = (uint32_t)j | ((uint32_t)jb << 16);
+    rc.aux[c * kThreads]   = (uint32_t)ja;
+    cx.stack[c * kThreads] = rc.mpos[b + j];
+}
+
+// Odometer state (list indices + positions of every component) of the placement of depth-first rank r.
 __device__ __forceinline__ void rank_unrank(const RankCtx& rc, uint32_t r)
 {
     const ItemCtx& cx = rc.cx;
-    int            p;
+    int            gj;   // list entry (all components back to back) of the component placed last
     {
-        const uint32_t* PS = rc.PS;
-        const int       j  = rank_search(PS, 0, list_len(rc, 0), r);
-        r -= PS[j];
-        p = rc.mpos[j];
-        cx.stack[0] = (uint32_t)p;
+        const int a0 = list_len(rc, 0);
+        const int j  = rank_search(rc.PS, 0, a0, r);
+        r -= rc.PS[j];
+        gj          = j;
+        rc.idx[0]   = (uint32_t)j | ((uint32_t)a0 << 16);
+        rc.aux[0]   = 0;
+        cx.stack[0] = rc.mpos[j];
     }
     for (int c = 1; c < cx.C; c++) {
-        const Kids      kd = kids_of(rc, c, p);
-        const int       b  = rc.lbeg[c];
-        const uint32_t* PS = rc.PS + b + c;
-        bool            done = false;
-        if (kd.nex) {
-            const int ke = max(1, (int)(cx.blob[4 + 2 * c] & 0xFFu));
-            int       e  = kd.efirst;
-            for (int x = 0; x < kd.nex; x++) {
-                const uint32_t n = rc.N[b + match_rank(rc, c, e)];
-                if (r < n) { p = e; done = true; break; }
+        const int       b   = rc.lbeg[c];
+        const uint32_t* PS  = rc.PS + b + c;
+        const uint32_t  kid = rc.KID[gj];
+        const int       ja = (int)(kid & 0xFFFFu), jb = (int)(kid >> 16);
+        int             j = -1;
+        uint32_t        aux = (uint32_t)ja;
+        if (rc.N[gj] & kHasGreedy) {
+            const Kids kd = kids_of(rc, c, (int)rc.mpos[gj]);
+            const int  ke = max(1, (int)(cx.blob[4 + 2 * c] & 0xFFu));
+            int        e  = kd.efirst;
+            for (int x = kd.nex; x > 0; x--) {
+                const int      je = match_rank(rc, c, e);
+                const uint32_t n  = rc.N[b + je] & kCountMask;
+                if (r < n) { j = je; aux |= (uint32_t)x << 16; break; }
                 r -= n;
                 e = next_bit(cx.M + c * cx.W, cx.SM + c * cx.WS, cx.W, cx.WS, e + ke);
             }
         }
-        if (!done) {
-            const int j = rank_search(PS, kd.ja, kd.jb, PS[kd.ja] + r);
-            r -= PS[j] - PS[kd.ja];
-            p = rc.mpos[b + j];
+        if (j < 0) {
+            const uint32_t base = PS[ja];
+            j = rank_search(PS, ja, jb, base + r);
+            r -= PS[j] - base;
         }
-        cx.stack[c * kThreads] = (uint32_t)p;
+        gj                     = b + j;
+        rc.idx[c * kThreads]   = (uint32_t)j | ((uint32_t)jb << 16);
+        rc.aux[c * kThreads]   = aux;
+        cx.stack[c * kThreads] = rc.mpos[gj];
     }
 }
 
-__device__ __forceinline__ bool all_checks_pass(const ItemCtx& cx)
+// Steps the odometer to the next placement in depth-first order that differs at level `from` or
+// above (the caller knows there is one). Returns the first level whose component moved.
+__device__ __forceinline__ int rank_advance(const RankCtx& rc, int from)
 {
-    const int       nk  = (int)((cx.blob[1] >> 8) & 0xFFu);
-    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
-    for (int i = 0; i < nk; i++) {
-        const uint32_t ea = chk[2 * i], eb = chk[2 * i + 1];
-        const int      aa = unpack_anchor(ea), ba = unpack_anchor(eb);
-        const int      u  = (aa < 0 ? 0 : placed(cx, aa)) + unpack_off(ea);
-        const int      v  = (ba < 0 ? 0 : placed(cx, ba)) + unpack_off(eb);
-        const int      a = min(u, v), b = max(u, v);
-        if (a < 0 || b >= cx.n || a == b) return false;
-        if (!((__ldg(cx.mask + (size_t)a * cx.mstride + (b >> 5)) >> (b & 31)) & 1u)) return false;
+    const ItemCtx& cx = rc.cx;
+    int            c  = from, j = 0;
+    for (;; c--) {
+        const int      b   = rc.lbeg[c];
+        const uint32_t idx = rc.idx[c * kThreads], aux = rc.aux[c * kThreads];
+        const int      jb  = (int)(idx >> 16);
+        int            xs  = (int)(aux >> 16);
+        j                  = (int)(idx & 0xFFFFu);
+        if (xs > 1) {   // further greedy siblings
+            const int ke = max(1, (int)(cx.blob[4 + 2 * c] & 0xFFu));
+            int       e  = (int)cx.stack[c * kThreads];
+            bool      hit = false;
+            while (xs > 1) {
+                e = next_bit(cx.M + c * cx.W, cx.SM + c * cx.WS, cx.W, cx.WS, e + ke);
+                xs--;
+                j = match_rank(rc, c, e);
+                if (rc.N[b + j] & kCountMask) { hit = true; break; }
+            }
+            if (hit) {
+                rc.idx[c * kThreads]   = (uint32_t)j | ((uint32_t)jb << 16);
+                rc.aux[c * kThreads]   = (aux & 0xFFFFu) | ((uint32_t)xs << 16);
+                cx.stack[c * kThreads] = (uint32_t)e;
+                break;
+            }
+        }
+        if (xs >= 1) {   // the greedy siblings are used up: on to the range
+            j = (int)(aux & 0xFFFFu);
+            rc.aux[c * kThreads] = aux & 0xFFFFu;
+        } else {
+            j++;
+        }
+        while (j < jb && !in_range_live(rc.N[b + j])) j++;
+        if (j < jb) {
+            rc.idx[c * kThreads]   = (uint32_t)j | ((uint32_t)jb << 16);
+            cx.stack[c * kThreads] = rc.mpos[b + j];
+            break;
+        }
     }
-    return true;
+    for (int d = c + 1; d < cx.C; d++) {
+        rank_first_child(rc, d, (int)rc.lbeg[d - 1] + j);
+        j = (int)(rc.idx[d * kThreads] & 0xFFFFu);
+    }
+    return c;
 }
 
-// Enumerates ranks [0, total) 32 at a time. Returns the number of sites; when EMIT, writes
-// their records from `out` on, staged through `stage` (32 * (C + 1) words) so that every
-// batch leaves as one contiguous block.
+constexpr int kHoist = 4;   // leaf-level checks kept in registers by the fast leaf loop
+
+// Leaves (placements of the last component) below the current upper placement: list entries
+// [j, jb), at most `quota` of them. Every leaf check is an ordered pair (u fixed by the upper
+// placement, v = leaf position + offset): the word index of row u is hoisted, the test is one
+// load and one funnel shift. Returns the number of leaves visited; `fill` counts the sites.
+template <int NL, bool EMIT>
+__device__ __forceinline__ uint32_t leaf_run(const RankCtx& rc, int& j, int jb, uint32_t quota, uint32_t module, uint32_t* slot_base,
+                                             uint32_t& fill)
+{
+    const ItemCtx&  cx = rc.cx;
+    const int       C = cx.C, L = C - 1, R = C + 1;
+    const int       bL = rc.lbeg[L];
+    const uint32_t  range = cx.blob[5 + 2 * L];
+    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16) + 2 * (range & 0xFFu);
+    uint32_t        row[NL > 0 ? NL : 1], off[NL > 0 ? NL : 1];
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+        const uint32_t ea = chk[2 * i];
+        row[i] = (uint32_t)(placed(cx, unpack_anchor(ea)) + unpack_off(ea)) * (uint32_t)cx.mstride;
+        off[i] = (uint32_t)unpack_off(chk[2 * i + 1]);
+    }
+    const bool sparse = (cx.ovl >> L) & 1u;   // some list entries are not in the thinned set
+    uint32_t   done   = 0;
+    for (; j < jb && done < quota; j++) {
+        if (sparse && !in_range_live(rc.N[bL + j])) continue;
+        const uint32_t p  = rc.mpos[bL + j];
+        uint32_t       ok = 1u;
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+            const uint32_t v = p + off[i];
+            ok &= __funnelshift_r(__ldg(cx.mask + row[i] + (v >> 5)), 0u, v);
+        }
+        done++;
+        if (ok) {
+            if (EMIT) {
+                uint32_t* rec = slot_base + fill * R;
+                rec[0]        = module;
+                for (int c = 0; c < L; c++) rec[1 + c] = cx.stack[c * kThreads];
+                rec[C] = p;
+            }
+            fill++;
+        }
+    }
+    if (sparse)
+        while (j < jb && !in_range_live(rc.N[bL + j])) j++;
+    return done;
+}
+
+// Walks `cnt` consecutive ranks from `first` with this lane's odometer and returns how many
+// placements pass their checks. The odometer only steps the upper components; under each of
+// their placements the leaves are a run of consecutive list entries (leaf_run). When EMIT, the
+// records go straight to `dst`, this lane's part of the output: every lane streams through its
+// own contiguous range, and L2 merges the partial sectors before they reach HBM.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t rank_chunk(const RankCtx& rc, uint32_t first, uint32_t cnt, int leaf_checks, uint32_t module,
+                                               uint32_t* __restrict__ dst)
+{
+    const ItemCtx& cx = rc.cx;
+    const int      C = cx.C, L = C - 1, R = C + 1;
+    const int      bL = rc.lbeg[L];
+    uint32_t       npass = 0, remaining = cnt;
+    int            ok_upper = 0;   // checks of levels [0, ok_upper) hold for the current upper placement
+    if (cnt) rank_unrank(rc, first);
+    while (remaining > 0) {
+        while (ok_upper < L && checks_pass(cx, ok_upper)) ok_upper++;
+        const uint32_t idx = rc.idx[L * kThreads];
+        int            j = (int)(idx & 0xFFFFu);
+        const int      jb = (int)(idx >> 16);
+        const bool     in_greedy = (rc.aux[L * kThreads] >> 16) != 0;
+        if (leaf_checks < 0 || in_greedy) {
+            // one placement at a time, every check through the generic test
+            if (ok_upper == L && checks_pass(cx, L)) {
+                if (EMIT) {
+                    uint32_t* rec = dst + (size_t)npass * R;
+                    rec[0]        = module;
+                    for (int c = 0; c < C; c++) rec[1 + c] = cx.stack[c * kThreads];
+                }
+                npass++;
+            }
+            if (--remaining) ok_upper = min(ok_upper, rank_advance(rc, L));
+            continue;
+        }
+        if (ok_upper < L) {   // an upper check fails: none of the leaves below is a site
+            const uint32_t* PSL = rc.PS + bL + L;
+            remaining -= min(remaining, PSL[jb] - PSL[j]);
+            j = jb;
+        } else {
+            uint32_t* base = EMIT ? dst + (size_t)npass * R : nullptr;
+            uint32_t  done, fill = 0;
+            switch (leaf_checks) {
+            case 0: done = leaf_run<0, EMIT>(rc, j, jb, remaining, module, base, fill); break;
+            case 1: done = leaf_run<1, EMIT>(rc, j, jb, remaining, module, base, fill); break;
+            case 2: done = leaf_run<2, EMIT>(rc, j, jb, remaining, module, base, fill); break;
+            case 3: done = leaf_run<3, EMIT>(rc, j, jb, remaining, module, base, fill); break;
+            default: done = leaf_run<4, EMIT>(rc, j, jb, remaining, module, base, fill); break;
+            }
+            remaining -= done;
+            npass += fill;
+        }
+        if (remaining) {
+            if (j >= jb) {
+                ok_upper = min(ok_upper, rank_advance(rc, L - 1));
+            } else {
+                rc.idx[L * kThreads]   = (uint32_t)j | ((uint32_t)jb << 16);
+                cx.stack[L * kThreads] = rc.mpos[bL + j];
+            }
+        }
+    }
+    return npass;
+}
+
+// Enumerates ranks [0, total): lane l takes the l-th of 32 equal runs of consecutive ranks, so
+// the lanes of a warp carry the same load whatever the shape of the placement tree. Returns the
+// number of sites and, in `lane_sites`, those of this lane's run. The count pass records the
+// latter; their prefix gives every lane its place in the output, so the emit pass is a single
+// walk that writes the records where they belong (when `known` is missing it counts first):
+// canonical order, contiguous block per item.
 template <bool EMIT>
 __device__ __forceinline__ uint64_t rank_walk(const RankCtx& rc, uint32_t total, uint32_t module, uint32_t* __restrict__ out,
-                                              uint32_t* stage)
+                                              const uint32_t* __restrict__ known, uint32_t& lane_sites)
 {
     const ItemCtx& cx   = rc.cx;
     const uint32_t lane = threadIdx.x & 31;
     const int      R    = cx.C + 1;
-    uint64_t       found = 0;
-    for (uint32_t f0 = 0; f0 < total; f0 += 32) {
-        const uint32_t f  = f0 + lane;
-        bool           ok = f < total;
-        if (ok) {
-            rank_unrank(rc, f);
-            ok = all_checks_pass(cx);
-        }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
-        if (EMIT && bal) {
-            if (ok) {
-                uint32_t* rec = stage + __popc(bal & ((1u << lane) - 1u)) * R;
-                rec[0]        = module;
-                for (int c = 0; c < cx.C; c++) rec[1 + c] = (uint32_t)placed(cx, c);
-            }
-            __syncwarp();
-            const uint32_t words = (uint32_t)__popc(bal) * R;
-            uint32_t*      dst   = out + found * (uint64_t)R;
-            for (uint32_t i = lane; i < words; i += 32) dst[i] = stage[i];
-            __syncwarp();
-        }
-        found += __popc(bal);
+    const uint32_t per  = (total + 31u) / 32u;
+    const uint32_t mine = lane * per;
+    const uint32_t cnt  = mine < total ? min(per, total - mine) : 0u;
+    // the fast leaf loop needs every leaf-level check to be an ordered pair with an earlier component
+    int leaf_checks = -1;
+    if (cx.C >= 2) {
+        const uint32_t  range = cx.blob[5 + 2 * (cx.C - 1)];
+        const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
+        const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
+        leaf_checks = ce - cb <= kHoist ? ce - cb : -1;
+        for (int i = cb; i < ce; i++)
+            if (!(chk[2 * i] & kCheckOrdered)) leaf_checks = -1;
     }
-    return found;
+    BSS_PHASE_BEGIN();
+    // sites of this lane's run: recorded by the count pass, or counted now
+    lane_sites    = (EMIT && known) ? known[lane] : rank_chunk<false>(rc, mine, cnt, leaf_checks, module, nullptr);
+    uint32_t incl = lane_sites;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += up;
+    }
+    const uint32_t sites = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    BSS_PHASE(9);
+    if (EMIT && sites) {
+        rank_chunk<true>(rc, mine, cnt, leaf_checks, module, out + (size_t)(incl - lane_sites) * R);
+        __syncwarp();
+        BSS_PHASE(10);
+    }
+    return sites;
 }
 
 struct Smem {
-    uint32_t* occ;       // [n_symbols][WP]
     uint32_t* blob;      // [groups][kBlobStage]
     uint32_t* M;         // [groups][cmax][W]
     uint32_t* T;         // [groups][cmax][W]
     uint32_t* SM;        // [groups][cmax][WS]
     uint32_t* ST;        // [groups][cmax][WS]
     uint32_t* stack;     // [cmax][kThreads]
+    uint32_t* idx;       // [2][cmax][kThreads] odometer columns of the rank-space walk
     uint32_t* rank;      // [groups][rank_words] rank-space scratch (32-lane groups only)
-    uint64_t* item_off;  // [units_per_chunk] (emit only)
 };
 
 // Rank-space scratch of one group, in words: N, PS, staging, then the u16 arrays.
-__host__ __device__ inline uint32_t rank_words(uint32_t cmax, uint32_t W, uint32_t cap)
+__host__ __device__ inline uint32_t rank_words(uint32_t cmax, uint32_t W, uint32_t cap, bool emit)
 {
     if (cap == 0) return 0;
-    return cap + (cap + cmax + 1) + 32 * (cmax + 1) + (cap + 1) / 2 + (cmax * W + 1) / 2 + (cmax + 2) / 2;
+    (void)emit;
+    return 2 * cap + (cap + cmax + 1) + (cap + 1) / 2 + (cmax * W + 1) / 2 + (cmax + 2) / 2;
 }
 
-__host__ __device__ inline uint32_t smem_words(uint32_t n_symbols, uint32_t cmax, uint32_t W, uint32_t WS, uint32_t groups,
-                                               uint32_t units_per_chunk, uint32_t cap)
+__host__ __device__ inline uint32_t smem_words(uint32_t cmax, uint32_t W, uint32_t WS, uint32_t groups,
+                                               uint32_t units_per_chunk, uint32_t cap, bool emit)
 {
-    uint32_t words = n_symbols * (W + kOccPad);
-    words += groups * (kBlobStage + 2 * cmax * (W + WS) + rank_words(cmax, W, cap));
-    words += cmax * kThreads;
-    words = (words + 1) & ~1u;
-    words += 2 * units_per_chunk;
+    uint32_t words = groups * (kBlobStage + 2 * cmax * (W + WS) + rank_words(cmax, W, cap, emit));
+    words += (cap ? 3 : 1) * cmax * kThreads;
+    (void)units_per_chunk;
     return words;
 }
 
-template <int G>
+template <int G, bool EMIT>
 __device__ __forceinline__ Smem carve(uint32_t* base, const DevLibrary& lib, const Plan& plan)
 {
-    const uint32_t groups = kThreads / G, WP = plan.W + kOccPad;
+    const uint32_t groups = kThreads / G;
     Smem           s;
-    s.occ   = base;               base += lib.n_symbols * WP;
     s.blob  = base;               base += groups * kBlobStage;
     s.M     = base;               base += groups * lib.cmax * plan.W;
     s.T     = base;               base += groups * lib.cmax * plan.W;
     s.SM    = base;               base += groups * lib.cmax * plan.WS;
     s.ST    = base;               base += groups * lib.cmax * plan.WS;
     s.stack = base;               base += lib.cmax * kThreads;
-    s.rank  = base;               base += groups * rank_words(lib.cmax, plan.W, plan.list_cap);
-    uintptr_t p = reinterpret_cast<uintptr_t>(base);
-    p           = (p + 7) & ~(uintptr_t)7;
-    s.item_off  = reinterpret_cast<uint64_t*>(p);
+    s.idx   = base;               base += (plan.list_cap ? 2 : 0) * lib.cmax * kThreads;
+    s.rank  = base;               base += groups * rank_words(lib.cmax, plan.W, plan.list_cap, EMIT);
     return s;
 }
 
-// Occurrence rows of the sequence: occ[a][w] bit b = (seq[32w + b] == alphabet[a]).
-__device__ __forceinline__ void build_occurrence(uint32_t* occ, const DevLibrary& lib, const uint8_t* __restrict__ seq, int n, int W)
+// The sequence-dependent inputs of an item.
+struct SeqCtx {
+    const uint32_t* pair_mask;
+    const uint32_t* occ;
+    uint64_t        item0;   // index of (this sequence, unit 0)
+    int             n, band, Wq;
+};
+
+__device__ __forceinline__ SeqCtx load_seq(const DevLibrary& lib, const DevQuery& query, uint32_t qi)
 {
-    const int WP = W + kOccPad;
-    for (uint32_t i = threadIdx.x; i < lib.n_symbols * (uint32_t)WP; i += kThreads) occ[i] = 0;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int w = warp; w < ((n + 31) >> 5); w += kThreads / 32) {
-        const int     q    = (w << 5) + lane;
-        const int     byte = q < n ? (int)__ldg(seq + q) : -1;
-        for (uint32_t a = 0; a < lib.n_symbols; a++) {
-            const uint32_t bits = __ballot_sync(0xFFFFFFFFu, byte == (int)lib.alphabet[a]);
-            if (lane == 0) occ[a * WP + w] = bits;
-        }
-    }
-    __syncthreads();
+    SeqCtx sq;
+    sq.n         = (int)(query.seq_begin[qi + 1] - query.seq_begin[qi]);
+    sq.pair_mask = query.masks + query.mask_begin[qi];
+    sq.band      = query.band[qi];
+    sq.occ       = query.occ + (size_t)qi * query.occ_rows * query.occ_stride;
+    sq.item0     = (uint64_t)qi * lib.n_units;
+    sq.Wq        = (sq.n + 32) >> 5;
+    return sq;
 }
 
+// Count pass (EMIT = false): one CTA per chunk = (sequence, contiguous unit range); the groups
+// of the CTA draw units from the chunk's counter, write the site count of every item, add the
+// items that have sites to the alive list, and the CTA leaves the chunk's totals behind.
+// Emit pass (EMIT = true): the groups walk the alive list (any order: every item knows its own
+// place in the output from the scanned chunk totals and the counts of the chunk's earlier items).
 template <int G, bool EMIT>
-__global__ void __launch_bounds__(kThreads) search_kernel(const DevLibrary lib, const DevQuery query, const Plan plan,
-                                                          const Work work, uint32_t* __restrict__ records)
+__global__ void __launch_bounds__(kThreads, 6) search_kernel(const DevLibrary lib, const DevQuery query, const Plan plan,
+                                                             const Work work, uint32_t* __restrict__ records, uint32_t n_alive)
 {
     using Gr = Group<G>;
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ uint32_t next_unit;
-    const uint32_t chunk = blockIdx.x;
-    if (EMIT && work.chunk_sites[chunk] == 0) return;   // nothing to write for this chunk
+    constexpr uint32_t groups = kThreads / G;
+    const int          W = (int)plan.W, WS = (int)plan.WS, WP = (int)query.occ_stride;
 
-    const uint32_t qi = chunk / plan.chunks_per_seq;
-    const uint32_t u0 = (chunk % plan.chunks_per_seq) * plan.units_per_chunk;
-    const uint32_t u1 = min(lib.n_units, u0 + plan.units_per_chunk);
-    const uint64_t sb = query.seq_begin[qi];
-    const int      n  = (int)(query.seq_begin[qi + 1] - sb);
-    const uint8_t* seq = query.seqs + sb;
-    const uint32_t* pair_mask = query.masks + query.mask_begin[qi];
-    const int      band = query.band[qi];
-    const int      W = (int)plan.W, WS = (int)plan.WS, WP = W + kOccPad;
-    const int      Wq = (n + 32) >> 5;
-
-    Smem sm = carve<G>(smem_raw, lib, plan);
-    if (threadIdx.x == 0) next_unit = u0;
-    build_occurrence(sm.occ, lib, seq, n, W);
-
+    Smem           sm     = carve<G, EMIT>(smem_raw, lib, plan);
     const uint32_t gid    = threadIdx.x / G;
     uint32_t*      g_blob = sm.blob + gid * kBlobStage;
     uint32_t*      g_M    = sm.M + gid * lib.cmax * W;
     uint32_t*      g_T    = sm.T + gid * lib.cmax * W;
     uint32_t*      g_SM   = sm.SM + gid * lib.cmax * WS;
     uint32_t*      g_ST   = sm.ST + gid * lib.cmax * WS;
-    const uint64_t item0  = (uint64_t)qi * lib.n_units;
 
-    if (EMIT) {
-        // Word offset of every item of the chunk: exclusive scan of count * record length.
-        // One warp does it; chunks hold at most kMaxChunkUnits items.
-        if (threadIdx.x < 32) {
-            uint64_t carry = work.chunk_words[chunk];
-            for (uint32_t b = u0; b < u1; b += 32) {
-                const uint32_t u = b + threadIdx.x;
-                uint64_t       v = 0;
-                if (u < u1) {
-                    const uint32_t c = work.counts[item0 + u];
-                    if (c) v = (uint64_t)c * (1u + (__ldg(lib.blob + __ldg(lib.unit_off + u) + 1) & 0xFFu));
-                }
-                uint64_t total;
-                const uint64_t ex = Group<32>::exclusive(v, total);
-                if (u < u1) sm.item_off[u - u0] = carry + ex;
-                carry += total;
-            }
-        }
+    // count pass: this CTA's chunk
+    const uint32_t chunk = blockIdx.x;
+    uint32_t       u1 = 0;
+    SeqCtx         sq{};
+    if (!EMIT) {
+        const uint32_t u0 = (chunk % plan.chunks_per_seq) * plan.units_per_chunk;
+        u1                = min(lib.n_units, u0 + plan.units_per_chunk);
+        sq                = load_seq(lib, query, chunk / plan.chunks_per_seq);
+        if (threadIdx.x == 0) next_unit = u0;
         __syncthreads();
     }
-
     uint64_t my_sites = 0, my_words = 0;   // accumulated by lane 0 of each group (count pass)
+    uint32_t slot = blockIdx.x * groups + gid;   // emit pass: position in the alive list
 
-    for (;;) {
+    BSS_PHASE_BEGIN();
+    for (;; slot += gridDim.x * groups) {
+        BSS_PHASE(7);
         uint32_t u = 0;
-        if (Gr::lane() == 0) u = atomicAdd(&next_unit, 1u);
-        u = Gr::first(u);
-        if (u >= u1) break;
-        if (EMIT && work.counts[item0 + u] == 0) continue;
+        uint64_t out_words = 0;   // emit pass: where the item's records start
+        if (!EMIT) {
+            if (Gr::lane() == 0) u = atomicAdd(&next_unit, 1u);
+            u = Gr::first(u);
+            if (u >= u1) break;
+        } else {
+            if (slot >= n_alive) break;
+            const uint32_t item = work.alive[slot];
+            const uint32_t qi   = item / lib.n_units;
+            u                   = item - qi * lib.n_units;
+            sq                  = load_seq(lib, query, qi);
+            // records of the chunk's earlier items
+            const uint32_t c0 = u / plan.units_per_chunk, v0 = c0 * plan.units_per_chunk;
+            uint64_t       before = 0;
+            for (uint32_t v = v0 + Gr::lane(); v < u; v += G)
+                before += (uint64_t)work.counts[sq.item0 + v] * __ldg(lib.unit_rlen + v);
+            out_words = work.chunk_words[qi * plan.chunks_per_seq + c0] + Gr::sum(before);
+        }
+        const int       n = sq.n;
+        const uint32_t* occ = sq.occ;
 
         // stage the unit descriptor
         const uint32_t  boff  = __ldg(lib.unit_off + u);
@@ -782,91 +1011,113 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const DevLibrary lib, 
         const int      delay  = (int)(blob[1] >> 16);
         const uint32_t gate   = blob[2];
 
+        BSS_PHASE(0);
         bool alive = true;
         if (!EMIT && gate != kNoGate) {   // an emitted item has already passed its gate
             const uint32_t* gb = lib.blob + __ldg(lib.unit_off + gate);
-            alive              = gate_open<G>(gb, sm.occ, WP, g_M, g_SM, W, WS, n);
+            alive              = gate_open<G>(gb, occ, WP, g_M, g_SM, W, WS, n);
             Gr::sync();
         }
         // An empty first pattern at position 0 with delay 0 leaves "no room" (unsigned wrap in
         // the reference, cppsrc/Motif.cpp:461) and ends the enumeration before it starts.
         if (C > 1 && (blob[4] & 0xFFu) == 0 && delay == 0) alive = false;
-        if (alive) alive = match_components<G>(blob, sm.occ, WP, g_M, g_SM, W, WS, n);
+        if (alive) alive = match_components<G>(blob, occ, WP, g_M, g_SM, W, WS, n);
 
+        BSS_PHASE(1);
         uint64_t item_sites = 0;
+        uint32_t lane_sites = 0;
+        bool     ranked     = false;
         if (alive) {
             ItemCtx cx;
-            cx.blob = blob; cx.M = g_M; cx.T = g_T; cx.SM = g_SM; cx.ST = g_ST; cx.mask = pair_mask;
+            cx.blob = blob; cx.M = g_M; cx.T = g_T; cx.SM = g_SM; cx.ST = g_ST; cx.mask = sq.pair_mask;
             cx.stack = sm.stack + threadIdx.x;
             cx.ovl   = thin_components<G>(blob, g_M, g_SM, g_T, g_ST, W, WS);
-            cx.W = W; cx.WS = WS; cx.n = n; cx.mstride = (n + 31) >> 5; cx.C = C; cx.delay = delay; cx.band = band;
+            cx.W = W; cx.WS = WS; cx.n = n; cx.mstride = (n + 31) >> 5; cx.C = C; cx.delay = delay; cx.band = sq.band;
 
-            bool ranked = false;
+            BSS_PHASE(2);
             if constexpr (G == 32) {
                 if (plan.list_cap) {
                     const uint32_t cap = plan.list_cap;
-                    uint32_t*      rw  = sm.rank + gid * rank_words(lib.cmax, plan.W, cap);
+                    uint32_t*      rw  = sm.rank + gid * rank_words(lib.cmax, plan.W, cap, EMIT);
                     RankCtx        rc;
                     rc.cx   = cx;
                     rc.N    = rw;                        rw += cap;
+                    rc.KID  = rw;                        rw += cap;
                     rc.PS   = rw;                        rw += cap + lib.cmax + 1;
-                    uint32_t* stage = rw;                rw += 32 * (lib.cmax + 1);
                     rc.mpos = reinterpret_cast<uint16_t*>(rw);   rw += (cap + 1) / 2;
                     rc.MWP  = reinterpret_cast<uint16_t*>(rw);   rw += (lib.cmax * plan.W + 1) / 2;
                     rc.lbeg = reinterpret_cast<uint16_t*>(rw);
-                    if (rank_build_lists(rc, (int)cap)) {
+                    rc.idx  = sm.idx + threadIdx.x;
+                    rc.aux  = sm.idx + lib.cmax * kThreads + threadIdx.x;
+                    const bool listed = rank_build_lists(rc, (int)cap);
+                    BSS_PHASE(3);
+                    if (listed) {
                         const uint64_t total = rank_count(rc);
+                        BSS_PHASE(4);
                         if (total != ~0ull) {
                             ranked = true;
                             if (total) {
-                                uint32_t* out = EMIT ? records + sm.item_off[u - u0] : nullptr;
-                                item_sites    = rank_walk<EMIT>(rc, (uint32_t)total, module, out, stage);
+                                const uint32_t* known = (EMIT && slot < work.lane_cap) ? work.lane_counts + (size_t)slot * 32 : nullptr;
+                                item_sites = rank_walk<EMIT>(rc, (uint32_t)total, module, EMIT ? records + out_words : nullptr, known, lane_sites);
+                                BSS_PHASE(5);
                             }
                         }
                     }
                 }
             }
             if (!ranked) {
-            // Component 0: its chain from position 0 starts on a run start, i.e. it is the thinned set.
-            const uint32_t* first = (cx.ovl & 1u) ? g_T : g_M;
-
-            if (!EMIT) {
-                uint64_t mine = 0;
-                for (int w = Gr::lane(); w < Wq; w += G)
-                    for (uint32_t x = first[w]; x; x &= x - 1) mine += walk_subtree<false>(cx, (w << 5) + __ffs(x) - 1, module, nullptr);
-                item_sites = Gr::sum(mine);
-            } else {
-                // sites below each word of component 0, then their exclusive prefix
-                uint64_t carry = 0;
-                for (int w0 = 0; w0 < Wq; w0 += G) {
-                    const int w    = w0 + (int)Gr::lane();
-                    uint64_t  mine = 0;
-                    uint32_t  x    = 0;
-                    if (w < Wq) {
-                        x = first[w];
-                        for (uint32_t y = x; y; y &= y - 1) mine += walk_subtree<false>(cx, (w << 5) + __ffs(y) - 1, module, nullptr);
-                    }
-                    uint64_t       total;
-                    const uint64_t ex = Gr::exclusive(mine, total);
-                    if (w < Wq && mine) {
-                        uint32_t* out = records + sm.item_off[u - u0] + (carry + ex) * (uint64_t)(C + 1);
-                        for (uint32_t y = x; y; y &= y - 1) {
-                            const uint64_t wrote = walk_subtree<true>(cx, (w << 5) + __ffs(y) - 1, module, out);
-                            out += wrote * (uint64_t)(C + 1);
+                BSS_PHASE(7);
+                // Component 0: its chain from position 0 starts on a run start, i.e. it is the thinned set.
+                const uint32_t* first = (cx.ovl & 1u) ? g_T : g_M;
+                if (!EMIT) {
+                    uint64_t mine = 0;
+                    for (int w = Gr::lane(); w < sq.Wq; w += G)
+                        for (uint32_t x = first[w]; x; x &= x - 1) mine += walk_subtree<false>(cx, (w << 5) + __ffs(x) - 1, module, nullptr);
+                    item_sites = Gr::sum(mine);
+                } else {
+                    // sites below each word of component 0, then their exclusive prefix
+                    uint64_t carry = 0;
+                    for (int w0 = 0; w0 < sq.Wq; w0 += G) {
+                        const int w    = w0 + (int)Gr::lane();
+                        uint64_t  mine = 0;
+                        uint32_t  x    = 0;
+                        if (w < sq.Wq) {
+                            x = first[w];
+                            for (uint32_t y = x; y; y &= y - 1) mine += walk_subtree<false>(cx, (w << 5) + __ffs(y) - 1, module, nullptr);
                         }
+                        uint64_t       total;
+                        const uint64_t ex = Gr::exclusive(mine, total);
+                        if (w < sq.Wq && mine) {
+                            uint32_t* out = records + out_words + (carry + ex) * (uint64_t)(C + 1);
+                            for (uint32_t y = x; y; y &= y - 1) {
+                                const uint64_t wrote = walk_subtree<true>(cx, (w << 5) + __ffs(y) - 1, module, out);
+                                out += wrote * (uint64_t)(C + 1);
+                            }
+                        }
+                        carry += total;
                     }
-                    carry += total;
+                    item_sites = carry;
                 }
-                item_sites = carry;
-            }
+                BSS_PHASE(6);
             }
         }
         Gr::sync();   // the group's scratch is reused by its next item
-        if (!EMIT && Gr::lane() == 0) {
-            if (item_sites > 0xFFFFFFFFull) atomicOr((unsigned long long*)(work.totals + 2), 1ull);
-            work.counts[item0 + u] = (uint32_t)item_sites;
-            my_sites += item_sites;
-            my_words += item_sites * (uint64_t)(C + 1);
+        if (!EMIT) {
+            uint32_t where = 0;
+            if (Gr::lane() == 0) {
+                if (item_sites > 0xFFFFFFFFull) atomicOr((unsigned long long*)(work.totals + 2), 1ull);
+                work.counts[sq.item0 + u] = (uint32_t)item_sites;
+                my_sites += item_sites;
+                my_words += item_sites * (uint64_t)(C + 1);
+                if (item_sites) {
+                    where             = (uint32_t)atomicAdd((unsigned long long*)(work.totals + 3), 1ull);
+                    work.alive[where] = (uint32_t)(sq.item0 + u);
+                }
+            }
+            if (G == 32 && ranked && item_sites) {   // sites of every lane's run of ranks, for the emit pass
+                where = Gr::first(where);
+                if (where < work.lane_cap) work.lane_counts[(size_t)where * 32 + Gr::lane()] = lane_sites;
+            }
         }
     }
 
@@ -959,17 +1210,51 @@ __global__ void __launch_bounds__(256) band_kernel(const DevQuery query, int32_t
     if (lane == 0 && best >= 0) atomicMax(band + qi, best);
 }
 
+// Occurrence table of every sequence: row a (a < n_symbols) bit q = (seq[q] == alphabet[a]);
+// with `pairs`, row n_symbols + a * n_symbols + b bit q = (seq[q] == alphabet[a] && seq[q+1] == alphabet[b]).
+// Rows are `stride` words long and zero beyond the sequence. One CTA per sequence.
+__global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const DevLibrary lib, uint32_t* __restrict__ occ)
+{
+    const uint32_t qi = blockIdx.x;
+    const uint64_t sb = query.seq_begin[qi];
+    const int      n  = (int)(query.seq_begin[qi + 1] - sb);
+    const uint8_t* seq = query.seqs + sb;
+    const int      WP = (int)query.occ_stride, ns = (int)lib.n_symbols;
+    uint32_t*      mine = occ + (size_t)qi * query.occ_rows * WP;
+    const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31, Wn = (n + 31) >> 5;
+    for (int i = threadIdx.x; i < ns * WP; i += 128)
+        if (i % WP >= Wn) mine[i] = 0;
+    for (int w = warp; w < Wn; w += 4) {
+        const int q    = (w << 5) + lane;
+        const int byte = q < n ? (int)__ldg(seq + q) : -1;
+        for (int a = 0; a < ns; a++) {
+            const uint32_t bits = __ballot_sync(0xFFFFFFFFu, byte == (int)lib.alphabet[a]);
+            if (lane == 0) mine[a * WP + w] = bits;
+        }
+    }
+    if ((int)query.occ_rows == ns) return;
+    __syncthreads();
+    for (int i = threadIdx.x; i < ns * ns * WP; i += 128) {
+        const int      r = i / WP, w = i % WP, a = r / ns, b = r % ns;
+        const uint32_t lo = mine[b * WP + w], hi = w + 1 < WP ? mine[b * WP + w + 1] : 0u;
+        mine[(ns + r) * WP + w] = mine[a * WP + w] & __funnelshift_r(lo, hi, 1);
+    }
+}
+
 template <bool EMIT>
 cudaError_t launch_search(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                          cudaStream_t s)
+                          uint32_t n_alive, cudaStream_t s)
 {
-    if (plan.n_chunks == 0) return cudaSuccess;
+    const uint32_t groups = kThreads / plan.group;
+    const uint32_t grid   = EMIT ? (n_alive + groups - 1) / groups : plan.n_chunks;
+    if (grid == 0) return cudaSuccess;
 #define BSS_LAUNCH(GG)                                                                                                    \
     do {                                                                                                                  \
         auto kernel = search_kernel<GG, EMIT>;                                                                            \
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);  \
+        const uint32_t smem = EMIT ? plan.smem_bytes_emit : plan.smem_bytes;                                               \
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
         if (e != cudaSuccess) return e;                                                                                   \
-        kernel<<<plan.n_chunks, kThreads, plan.smem_bytes, s>>>(lib, q, plan, work, records);                            \
+        kernel<<<grid < (1u << 20) ? grid : (1u << 20), kThreads, smem, s>>>(lib, q, plan, work, records, n_alive);      \
     } while (0)
     switch (plan.group) {
     case 4: BSS_LAUNCH(4); break;
@@ -997,12 +1282,15 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
     uint32_t       upc     = (lib.n_units + per_seq - 1) / (per_seq ? per_seq : 1);
     upc                    = ((upc + groups - 1) / groups) * groups;
     if (upc < 4 * groups) upc = 4 * groups;
+    if (const char* dbg = getenv("BSS_DEBUG_UPC")) upc = (uint32_t)atoi(dbg);
     if (upc > kMaxChunkUnits) upc = kMaxChunkUnits;
     p.units_per_chunk = upc;
     p.chunks_per_seq  = lib.n_units ? (lib.n_units + upc - 1) / upc : 0;
     p.n_chunks        = p.chunks_per_seq * n_seqs;
-    p.list_cap        = p.group == 32 ? 384u : 0u;
-    p.smem_bytes      = 4u * smem_words(lib.n_symbols, lib.cmax, p.W, p.WS, groups, upc, p.list_cap);
+    p.list_cap        = p.group == 32 ? 192u : 0u;
+    if (const char* dbg = getenv("BSS_DEBUG_CAP")) p.list_cap = p.group == 32 ? (uint32_t)atoi(dbg) : 0u;
+    p.smem_bytes      = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, false);
+    p.smem_bytes_emit = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, true);
     return p;
 }
 
@@ -1019,9 +1307,16 @@ cudaError_t launch_band(const DevQuery& q, int32_t* band, cudaStream_t s)
     return cudaGetLastError();
 }
 
+cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, cudaStream_t s)
+{
+    if (q.n_seqs == 0) return cudaSuccess;
+    occ_kernel<<<q.n_seqs, 128, 0, s>>>(q, lib, occ);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s)
 {
-    return launch_search<false>(lib, q, plan, work, nullptr, s);
+    return launch_search<false>(lib, q, plan, work, nullptr, 0, s);
 }
 
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s)
@@ -1031,9 +1326,22 @@ cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, c
 }
 
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                        cudaStream_t s)
+                        uint32_t n_alive, cudaStream_t s)
 {
-    return launch_search<true>(lib, q, plan, work, records, s);
+    return launch_search<true>(lib, q, plan, work, records, n_alive, s);
 }
 
 }   // namespace bss
+
+#ifdef BSS_PHASE_TIMING
+extern "C" int bss_debug_phase_cycles(unsigned long long* out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpyFromSymbol(out, bss::g_phase_cycles, sizeof(unsigned long long) * 16);
+    if (e == cudaSuccess && reset) {
+        unsigned long long zero[16] = {};
+        e = cudaMemcpyToSymbol(bss::g_phase_cycles, zero, sizeof zero);
+    }
+    return (int)e;
+}
+#endif

@@ -1,0 +1,22 @@
+import csv, sys, subprocess, io
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units = rows[0], rows[1]
+keys = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__thread_inst_executed_per_inst_executed.ratio',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'launch__registers_per_thread', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers', 'launch__grid_size',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed_op_shared_ld.sum', 'smsp__inst_executed_op_global_ld.sum',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__cycles_active.avg', 'sm__cycles_elapsed.max',
+        'smsp__cycles_active.avg', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct']
+stall = [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('_per_issue_active.ratio')]
+for r in rows[2:]:
+    print('==', r[hdr.index('Kernel Name')][:90], 'grid', r[hdr.index('Grid Size')] if 'Grid Size' in hdr else '')
+    for k in keys:
+        if k in hdr:
+            i = hdr.index(k); print(f'  {k} = {r[i]} {units[i]}')
+    st = sorted(((float(r[hdr.index(h)] or 0), h) for h in stall), reverse=True)[:7]
+    for v, h in st:
+        print(f'  stall {h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]}: {v:.2f}')
