@@ -293,6 +293,8 @@ class DeviceLibrary:
         return Sites(h, 1)
 
     def search_batch(self, seqs, masks):
+        if len(seqs) == 1:   # no concatenation of the (possibly large) mask
+            return self.search(seqs[0], masks[0])
         seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
         seq_begin = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.uint64)
         blob = np.frombuffer(b"".join(seqs) + b"\0", dtype=np.uint8)

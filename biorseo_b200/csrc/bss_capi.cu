@@ -94,6 +94,17 @@ bool can_self_overlap(const uint8_t* p, uint32_t k)
 
 }   // namespace
 
+struct bss_query {
+    int           device = 0;
+    bss::DevQuery dev{};
+    DeviceBuffer  storage;
+    // the occurrence table is built for one alphabet: the creating library's
+    uint32_t      n_symbols = 0, pair_rows = 0;
+    uint8_t       alphabet[32] = {};
+    uint64_t      total_len = 0;
+    uint64_t      h2d_bytes = 0;
+};
+
 struct bss_library {
     int          device     = 0;
     int          sm_count   = 148;
@@ -106,22 +117,12 @@ struct bss_library {
     // work buffers, reused across searches
     DeviceBuffer d_counts, d_chunk_sites, d_chunk_words, d_totals, d_seq_word_begin, d_alive, d_lane_counts;
     uint32_t     n_alive = 0;   // items with sites of the last count pass
+    bss_query    oneshot;       // storage of the host-buffer entry points (bss_search, bss_search_batch), reused across calls
     PinnedBuffer h_totals;
     // one spare set of result buffers, recycled by bss_sites_free
     DeviceBuffer spare_records;
     PinnedBuffer spare_host;
     bss_stats    stats{};
-};
-
-struct bss_query {
-    int           device = 0;
-    bss::DevQuery dev{};
-    DeviceBuffer  storage;
-    // the occurrence table is built for one alphabet: the creating library's
-    uint32_t      n_symbols = 0, pair_rows = 0;
-    uint8_t       alphabet[32] = {};
-    uint64_t      total_len = 0;
-    uint64_t      h2d_bytes = 0;
 };
 
 struct bss_sites {
@@ -178,6 +179,7 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     // unit descriptors
     std::vector<uint32_t> blob, unit_off(n_all + 1, 0);
     std::vector<uint32_t> module_components(t->n_modules, 0);
+    std::vector<float>    density;   // per searched unit: expected matches per nucleotide, all components
     uint32_t              cmax = 1;
     for (uint32_t u = 0; u < n_all; u++) {
         unit_off[u] = (uint32_t)blob.size();
@@ -234,6 +236,17 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
                 program.push_back((uint16_t)(row | ((shift & 31u) << 7) | ((shift >> 5) << 12)));
             }
             prog_range[c - c0] = {first_step, (uint32_t)program.size() - first_step};
+        }
+        if (u < t->n_units) {   // uniform symbols: a pattern with l literal symbols matches one position in |alphabet|^l
+            double d = 0.0;
+            for (uint32_t c = c0; c < c1; c++) {
+                const uint32_t pb = t->comp_pat_begin[c], k = t->comp_pat_begin[c + 1] - pb;
+                double         f  = 1.0;
+                for (uint32_t j = 0; j < k; j++)
+                    if (t->pattern[pb + j] != '.') f /= std::max<double>(2.0, (double)alphabet.size());
+                d += f;
+            }
+            density.push_back((float)d);
         }
         const uint32_t pat_words = ((uint32_t)program.size() + 1) / 2;
         const uint32_t head      = 4 + 2 * C;
@@ -323,6 +336,12 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     lib->dev.n_symbols = (uint32_t)alphabet.size();
     lib->dev.cmax      = cmax;
     lib->dev.pair_rows = alphabet.size() <= bss::kPairAlphabet ? 1u : 0u;
+    lib->dev.list_density = 0.f;
+    if (!density.empty()) {
+        const size_t at = (density.size() - 1) * 98 / 100;
+        std::nth_element(density.begin(), density.begin() + at, density.end());
+        lib->dev.list_density = density[at];
+    }
     std::memset(lib->dev.alphabet, 0, sizeof lib->dev.alphabet);
     std::copy(alphabet.begin(), alphabet.end(), lib->dev.alphabet);
     *out = lib;
@@ -336,7 +355,7 @@ void bss_library_destroy(bss_library* lib)
     if (lib->own_stream) cudaStreamSynchronize(lib->own_stream);
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
-    lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
+    lib->oneshot.storage.release(); lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
     lib->d_chunk_words.release(); lib->d_totals.release(); lib->d_seq_word_begin.release(); lib->h_totals.release();
     lib->spare_records.release(); lib->spare_host.release();
     if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
@@ -364,11 +383,16 @@ uint32_t bss_library_module_components(const bss_library* lib, uint32_t module)
     return (lib && module < lib->module_components.size()) ? lib->module_components[module] : 0;
 }
 
-int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
-                     const uint64_t* mask_begin, bss_query** out)
+}   // extern "C"
+
+namespace {
+
+// Validates the host buffers, (re)uses q's device storage and queues upload + occurrence
+// table + band on the library's stream. With `wait` the call returns once the query is resident.
+int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
+               const uint64_t* mask_begin, bool wait)
 {
-    if (!lib || !out || !seq_begin || !mask_begin || (n_seqs && (!seqs || !masks))) return fail(BSS_ERR_INVALID, "null argument");
-    *out = nullptr;
+    if (!lib || !seq_begin || !mask_begin || (n_seqs && (!seqs || !masks))) return fail(BSS_ERR_INVALID, "null argument");
     uint32_t max_len = 0;
     for (uint32_t q = 0; q < n_seqs; q++) {
         if (seq_begin[q + 1] < seq_begin[q] || mask_begin[q + 1] < mask_begin[q]) return fail(BSS_ERR_INVALID, "non-monotonic offsets");
@@ -383,7 +407,6 @@ int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
         return fail(BSS_ERR_BAD_SEQUENCE, "query contains a line terminator");
 
     BSS_CUDA(cudaSetDevice(lib->device));
-    bss_query* q = new bss_query();
     q->device    = lib->device;
     // one allocation: [seq_begin | mask_begin | band | occurrence table | masks | seqs]
     const uint32_t ns = lib->dev.n_symbols, occ_rows = ns + (lib->dev.pair_rows ? ns * ns : 0u);
@@ -393,7 +416,7 @@ int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
                  off_occ = off_band + 4 * (((size_t)n_seqs + 3) & ~(size_t)3), off_mask = off_occ + 4 * ((occ_words + 3) & ~(size_t)3),
                  off_seq = off_mask + 4 * total_mask, bytes = off_seq + total_len + 16;
     cudaError_t e = q->storage.reserve(bytes);
-    if (e != cudaSuccess) { delete q; return cuda_fail(e, "cudaMalloc(query)"); }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(query)");
     char* d = static_cast<char*>(q->storage.ptr);
     std::vector<uint64_t> sb(n_seqs + 1), mb(n_seqs + 1);
     for (uint32_t i = 0; i <= n_seqs; i++) { sb[i] = seq_begin[i] - seq_begin[0]; mb[i] = mask_begin[i] - mask_begin[0]; }
@@ -419,10 +442,30 @@ int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
     if (e == cudaSuccess) e = bss::launch_occ(lib->dev, q->dev, reinterpret_cast<uint32_t*>(d + off_occ), st);
     // widest pair the mask allows, per sequence: bounds the window a tied component is searched in
     if (e == cudaSuccess) e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // sb / mb are stack-owned staging
-    if (e != cudaSuccess) { q->storage.release(); delete q; return cuda_fail(e, "query upload"); }
+    // (copies from pageable host memory are staged before cudaMemcpyAsync returns: sb / mb may go out of scope)
+    if (e == cudaSuccess && wait) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "query upload");
     q->total_len      = total_len;
     q->h2d_bytes      = 16 * (uint64_t)(n_seqs + 1) + 4 * total_mask + total_len;
+    return BSS_OK;
+}
+
+}   // namespace
+
+extern "C" {
+
+int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
+                     const uint64_t* mask_begin, bss_query** out)
+{
+    if (!out) return fail(BSS_ERR_INVALID, "null argument");
+    *out         = nullptr;
+    bss_query* q = new bss_query();
+    const int  rc = query_fill(lib, q, n_seqs, seqs, seq_begin, masks, mask_begin, true);
+    if (rc != BSS_OK) {
+        q->storage.release();
+        delete q;
+        return rc;
+    }
     *out = q;
     return BSS_OK;
 }
@@ -582,13 +625,13 @@ int bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
                      const uint64_t* mask_begin, bss_sites** out)
 {
     if (!out) return fail(BSS_ERR_INVALID, "null argument");
-    *out         = nullptr;
-    bss_query* q = nullptr;
-    int        rc = bss_query_create(lib, n_seqs, seqs, seq_begin, masks, mask_begin, &q);
+    *out = nullptr;
+    if (!lib) return fail(BSS_ERR_INVALID, "null argument");
+    bss_query* q  = &lib->oneshot;   // device storage kept between calls: no allocation once it has grown
+    int        rc = query_fill(lib, q, n_seqs, seqs, seq_begin, masks, mask_begin, false);
     if (rc != BSS_OK) return rc;
     rc = bss_search_query(lib, q, 1, out);
     if (rc == BSS_OK) lib->stats.h2d_bytes = q->h2d_bytes;
-    bss_query_destroy(q);
     return rc;
 }
 

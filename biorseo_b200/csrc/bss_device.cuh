@@ -42,6 +42,7 @@ struct DevLibrary {
     uint32_t        n_symbols;   // alphabet size
     uint32_t        cmax;        // max components per unit (gates included)
     uint32_t        module_base; // added to every module index written into a record (library shards)
+    float           list_density; // expected matches per nucleotide of a unit (all components), 98th percentile over units
     uint32_t        pair_rows;   // 1: the match programs use pair rows (alphabet of at most kPairAlphabet symbols)
     uint8_t         alphabet[32];
 };

@@ -30,6 +30,10 @@
 
 #include <cstdlib>
 
+#ifndef BSS_MIN_CTAS
+#define BSS_MIN_CTAS 8   // resident CTAs per SM the register allocation is held to
+#endif
+
 namespace bss {
 
 // Optional per-phase cycle accounting (debug builds only: -DBSS_PHASE_TIMING). Sums, over all
@@ -940,7 +944,7 @@ __device__ __forceinline__ SeqCtx load_seq(const DevLibrary& lib, const DevQuery
 // Emit pass (EMIT = true): the groups walk the alive list (any order: every item knows its own
 // place in the output from the scanned chunk totals and the counts of the chunk's earlier items).
 template <int G, bool EMIT>
-__global__ void __launch_bounds__(kThreads, 6) search_kernel(const DevLibrary lib, const DevQuery query, const Plan plan,
+__global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const DevLibrary lib, const DevQuery query, const Plan plan,
                                                              const Work work, uint32_t* __restrict__ records, uint32_t n_alive)
 {
     using Gr = Group<G>;
@@ -1287,7 +1291,14 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
     p.units_per_chunk = upc;
     p.chunks_per_seq  = lib.n_units ? (lib.n_units + upc - 1) / upc : 0;
     p.n_chunks        = p.chunks_per_seq * n_seqs;
-    p.list_cap        = p.group == 32 ? 192u : 0u;
+    // Rank-space walk (32-lane groups): room for the match lists of all but the densest few units
+    // (lib.list_density = 98th percentile over the units of the expected matches per nucleotide,
+    // all components together); denser items take the depth-first walk.
+    p.list_cap = 0;
+    if (p.group == 32) {
+        const double want = 1.4 * lib.list_density * max_len + 16.0;
+        p.list_cap        = want > 1024.0 ? 1024u : want < 64.0 ? 64u : (((uint32_t)want + 31u) & ~31u);
+    }
     if (const char* dbg = getenv("BSS_DEBUG_CAP")) p.list_cap = p.group == 32 ? (uint32_t)atoi(dbg) : 0u;
     p.smem_bytes      = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, false);
     p.smem_bytes_emit = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, true);
