@@ -188,6 +188,36 @@ class Query:
             pass
 
 
+class HostBatch:
+    """Query batch packed once into the flat host buffers the C ABI takes (bss_search_batch):
+    concatenated sequences + offsets, concatenated pair masks + offsets. With pinned=True the two
+    large buffers live in page-locked memory (torch), so every search uploads them by DMA."""
+
+    def __init__(self, seqs, masks, pinned=False):
+        seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+        self.n_seqs = len(seqs)
+        self.seq_begin = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.uint64)
+        blob = np.frombuffer(b"".join(seqs) + b"\0", dtype=np.uint8)
+        flat = [np.ascontiguousarray(m, dtype=np.uint32).reshape(-1) for m in masks]
+        self.mask_begin = np.concatenate([[0], np.cumsum([m.size for m in flat])]).astype(np.uint64)
+        words = int(self.mask_begin[-1])
+        if pinned:
+            import torch
+            self._keep = (torch.empty(blob.size, dtype=torch.uint8, pin_memory=True),
+                          torch.empty(words + 1, dtype=torch.int32, pin_memory=True))
+            self.seqs = self._keep[0].numpy()
+            self.masks = self._keep[1].numpy().view(np.uint32)
+        else:
+            self.seqs, self.masks = np.empty(blob.size, np.uint8), np.empty(words + 1, np.uint32)
+        self.seqs[:] = blob
+        at = 0
+        for m in flat:
+            self.masks[at:at + m.size] = m
+            at += m.size
+        self.masks[words] = 0
+        self.h2d_bytes = int(blob.size - 1 + 4 * words + 16 * (self.n_seqs + 1))
+
+
 class Sites:
     def __init__(self, handle, n_seqs):
         self._lib = capi.load()
@@ -305,6 +335,13 @@ class DeviceLibrary:
         _check(self._lib.bss_search_batch(self._h, len(seqs), blob.ctypes.data_as(C.c_void_p), seq_begin.ctypes.data_as(capi.u64p),
                                           allm.ctypes.data_as(C.c_void_p), mask_begin.ctypes.data_as(capi.u64p), C.byref(h)))
         return Sites(h, len(seqs))
+
+    def search_host(self, batch):
+        """One-shot on a HostBatch: upload, search, download (bss_search_batch)."""
+        h = C.c_void_p()
+        _check(self._lib.bss_search_batch(self._h, batch.n_seqs, batch.seqs.ctypes.data_as(C.c_void_p), batch.seq_begin.ctypes.data_as(capi.u64p),
+                                          batch.masks.ctypes.data_as(C.c_void_p), batch.mask_begin.ctypes.data_as(capi.u64p), C.byref(h)))
+        return Sites(h, batch.n_seqs)
 
     def stats(self):
         s = capi.BssStats()

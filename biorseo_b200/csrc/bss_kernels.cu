@@ -1277,15 +1277,20 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
     Plan p{};
     p.W  = (max_len + 32) / 32;
     p.WS = (p.W + 31) / 32;
-    p.group = p.W <= 4 ? 4 : p.W <= 8 ? 8 : p.W <= 16 ? 16 : 32;
+    // Lanes per item. Short sequences in large batches: narrow groups, several items per warp (most
+    // items end in the match phase). Otherwise a whole warp per item, which also enables the
+    // rank-space walk.
+    const uint64_t n_items = (uint64_t)n_seqs * lib.n_units;
+    p.group = (p.W > 16 || n_items <= (1u << 17)) ? 32 : p.W <= 4 ? 4 : p.W <= 8 ? 8 : 16;
+    if (const char* dbg = getenv("BSS_DEBUG_GROUP")) p.group = (uint32_t)atoi(dbg);
     const uint32_t groups = kThreads / p.group;
     // Several waves of CTAs, so that the hardware scheduler evens out chunks of unequal cost;
-    // a chunk holds at least a few items per group to amortise its occurrence rows.
+    // a chunk holds at least one item per group.
     const uint32_t target = (uint32_t)sm_count * 24u;
     uint32_t       per_seq = n_seqs >= target ? 1u : (target + n_seqs - 1) / (n_seqs ? n_seqs : 1);
     uint32_t       upc     = (lib.n_units + per_seq - 1) / (per_seq ? per_seq : 1);
     upc                    = ((upc + groups - 1) / groups) * groups;
-    if (upc < 4 * groups) upc = 4 * groups;
+    if (upc < groups) upc = groups;
     if (const char* dbg = getenv("BSS_DEBUG_UPC")) upc = (uint32_t)atoi(dbg);
     if (upc > kMaxChunkUnits) upc = kMaxChunkUnits;
     p.units_per_chunk = upc;

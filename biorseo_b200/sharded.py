@@ -55,3 +55,68 @@ def allgatherv(local, group=None, counts_out=None):
     if counts_out is not None:
         counts_out[:] = counts
     return out, counts
+
+
+class PaddedGatherer:
+    """All-gather-v for record streams whose sizes are stable from call to call (the search of a
+    query stream against a sharded library): ONE collective, no size exchange ahead of it.
+
+    Every rank contributes a block of `capacity` int32 words: a header of `header_words`
+    (the search's own (n_seqs + 1) u64 word offsets, written by bss_search_query_into next to
+    the records; its last entry is the number of words that follow), the records, padding.
+    The search writes straight into the block (`block()`), one all_gather_into_tensor moves
+    the blocks, the counts arrive inside them, and the ranks cut the blocks down to the
+    canonical concatenation. When a rank's stream does not fit, every rank sees the same
+    counts, grows to the same capacity and the caller searches again into the new block.
+    The point-to-point `allgatherv` above is the exact-size path for very large or very
+    uneven shards.
+    """
+
+    def __init__(self, device, n_seqs=1, capacity_words=1 << 14, slack=1.25, group=None):
+        self.group = group
+        self.header_words = 2 * (n_seqs + 1)          # (n_seqs + 1) u64 offsets
+        self.slack = slack
+        cap = torch.tensor([int(capacity_words) + self.header_words], dtype=torch.int64, device=device)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)   # blocks must have one size on every rank
+        self._allocate(device, int(cap.item()))
+
+    def _allocate(self, device, capacity):
+        world = dist.get_world_size(self.group)
+        self.capacity = (capacity + 3) & ~3
+        self._send = torch.zeros(self.capacity, dtype=torch.int32, device=device)
+        self._recv = torch.empty(world * self.capacity, dtype=torch.int32, device=device)
+
+    def block(self):
+        """(header tensor, records tensor): views of this rank's block for the search to fill."""
+        return self._send[:self.header_words], self._send[self.header_words:]
+
+    def set_count(self, n_words):
+        """Only needed when the search did not fill the header itself (its stream did not fit)."""
+        self._send[:self.header_words].view(torch.int64)[-1] = int(n_words)
+
+    def exchange(self):
+        """Returns (gathered, counts), or (None, counts) after growing: search again and call again."""
+        world = dist.get_world_size(self.group)
+        dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+        blocks = self._recv.view(world, self.capacity)
+        counts = blocks[:, :self.header_words].view(torch.int64)[:, -1].tolist()   # the one host sync of the exchange
+        room = self.capacity - self.header_words
+        if max(counts) > room:
+            self._allocate(self._send.device, int(max(counts) * self.slack) + 16 + self.header_words)
+            return None, counts
+        h = self.header_words
+        out = torch.cat([blocks[r, h:h + c] for r, c in enumerate(counts)]) if sum(counts) else self._send[:0].clone()
+        return out, counts
+
+    def gather(self, local):
+        """Convenience for a stream that already exists elsewhere: copies it into the block first."""
+        while True:
+            n = local.numel()
+            self.set_count(n)
+            _, rec = self.block()
+            m = min(n, rec.numel())
+            if m:
+                rec[:m].copy_(local[:m])
+            out, counts = self.exchange()
+            if out is not None:
+                return out, counts

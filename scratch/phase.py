@@ -16,7 +16,9 @@ import bench
 names = ["fetch+blob", "gate+match", "thin", "lists", "DP", "walk(all)", "dfs", "tail/other", "tables", "walkA", "walkB"]
 for wname in sys.argv[1:]:
     w = bench.make_workload(wname, 0)
-    host = b.HostLibrary.from_json_modules(w["modules"])
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        host, _ = bench.host_library(w, tmp)
     dev = host.to_device(0)
     q = dev.query(w["seqs"], w["masks"])
     lib = capi.load()

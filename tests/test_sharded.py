@@ -42,6 +42,11 @@ def _worker(rank, world, port, seq, mask, modules, out_dir):
             rec = rec[:0] if os.environ.get("BSS_TEST_EMPTY_RANK") else rec
         gathered, counts = sharded.allgatherv(torch.from_numpy(rec.astype(np.int32)))
         assert sum(counts) == gathered.numel()
+        # the padded single-collective exchange must agree, from proposals that differ per rank and are too small (it grows)
+        padded = sharded.PaddedGatherer("cpu", n_seqs=1, capacity_words=8 + 3 * rank)
+        for _ in range(2):
+            again, counts2 = padded.gather(torch.from_numpy(rec.astype(np.int32)))
+            assert counts2 == counts and torch.equal(again, gathered)
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), gathered.numpy())
     finally:
         dist.destroy_process_group()
