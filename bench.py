@@ -343,16 +343,20 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
+    traffic_path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    traffic_table = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+
     def roofline(res):
         km = res["kernel_ms"]
         name = max(km, key=km.get)
+        traffic = traffic_table.get(res["workload"]["name"], {}).get(name)   # DRAM bytes per launch, from the committed ncu capture
         b_in, b_out = algorithmic_bytes(res["table"], res["seq_lens"], res["words"])
         # the count kernel reads the inputs, the emit kernel reads them again and writes the sites
         algo = {"count_ms": b_in, "scan_ms": 0, "emit_ms": b_in + b_out}[name]
         achieved = algo / (km[name] * 1e-3) / 1e9 if km[name] > 0 else 0.0
         return {"bound": "hbm", "kernel": {"count_ms": "search_kernel<G,false> (match+count)", "scan_ms": "scan_kernel",
                                            "emit_ms": "search_kernel<G,true> (emit)"}[name],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": algo, "kernel_ms": km[name], "peak_source": peak_src,
                 "all_kernels_ms": km}
 

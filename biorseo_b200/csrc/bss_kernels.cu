@@ -52,6 +52,16 @@ __device__ unsigned long long g_phase_cycles[16];
 #define BSS_PHASE_BEGIN() do { } while (0)
 #endif
 
+// Optional index checks (debug builds only: -DBSS_DEBUG_ASSERT; compute-sanitizer is not
+// available on the GPU pool). Violations are counted per site and read back with
+// bss_debug_assert_counts(); the fuzz tests are run against such a build.
+#ifdef BSS_DEBUG_ASSERT
+__device__ unsigned int g_assert_fail[32];
+#define BSS_ASSERT(cond, id) do { if (!(cond)) atomicAdd(&g_assert_fail[id], 1u); } while (0)
+#else
+#define BSS_ASSERT(cond, id) do { } while (0)
+#endif
+
 namespace {
 
 __device__ __forceinline__ int unpack_anchor(uint32_t w) { return (int)(int8_t)(w & 0xFFu); }
@@ -60,6 +70,7 @@ __device__ __forceinline__ int unpack_off(uint32_t w) { return (int)(int16_t)((w
 // First set bit at or after position t (t >= 0) of a bitset with a one-bit-per-word summary, or -1.
 __device__ __forceinline__ int next_bit(const uint32_t* __restrict__ B, const uint32_t* __restrict__ S, int W, int WS, int t)
 {
+    BSS_ASSERT(t >= 0, 0);
     int w = t >> 5;
     if (w >= W) return -1;
     uint32_t x = B[w] & (0xFFFFFFFFu << (t & 31));
@@ -75,7 +86,11 @@ __device__ __forceinline__ int next_bit(const uint32_t* __restrict__ B, const ui
     return (w << 5) + __ffs(B[w]) - 1;
 }
 
-__device__ __forceinline__ bool test_bit(const uint32_t* __restrict__ B, int q) { return (B[q >> 5] >> (q & 31)) & 1u; }
+__device__ __forceinline__ bool test_bit(const uint32_t* __restrict__ B, int q)
+{
+    BSS_ASSERT(q >= 0, 1);
+    return (B[q >> 5] >> (q & 31)) & 1u;
+}
 
 // Word w of (B << s): bit q of the result is bit q - s of B.
 __device__ __forceinline__ uint32_t shifted_up(const uint32_t* __restrict__ B, int w, int s)
@@ -97,7 +112,11 @@ struct ItemCtx {
     int             W, WS, n, mstride, C, delay, band;
 };
 
-__device__ __forceinline__ int placed(const ItemCtx& cx, int level) { return (int)(cx.stack[level * kThreads] & 0xFFFFu); }
+__device__ __forceinline__ int placed(const ItemCtx& cx, int level)
+{
+    BSS_ASSERT(level >= 0 && level < cx.C, 2);
+    return (int)(cx.stack[level * kThreads] & 0xFFFFu);
+}
 
 // All checks that become decidable once component `level` is placed.
 __device__ __forceinline__ bool checks_pass(const ItemCtx& cx, int level)
@@ -116,6 +135,7 @@ __device__ __forceinline__ bool checks_pass(const ItemCtx& cx, int level)
             b = max(u, v);
             if (a < 0 || b >= cx.n || a == b) return false;
         }
+        BSS_ASSERT(a >= 0 && a < b && b < cx.n, 3);
         if (!((__ldg(cx.mask + (size_t)a * cx.mstride + (b >> 5)) >> (b & 31)) & 1u)) return false;
     }
     return true;
@@ -426,6 +446,7 @@ __device__ __forceinline__ int match_rank(const RankCtx& rc, int c, int x)
     if (x <= 0) return 0;
     const int w = x >> 5;
     if (w >= rc.cx.W) return list_len(rc, c);
+    BSS_ASSERT(c >= 0 && c < rc.cx.C, 4);
     return (int)rc.MWP[c * rc.cx.W + w] + __popc(rc.cx.M[c * rc.cx.W + w] & ((1u << (x & 31)) - 1u));
 }
 
@@ -496,6 +517,7 @@ __device__ __forceinline__ Kids kids_of(const RankCtx& rc, int c, int p)
 // because target < PS[jb]).
 __device__ __forceinline__ int rank_search(const uint32_t* __restrict__ PS, int ja, int jb, uint32_t target)
 {
+    BSS_ASSERT(ja < jb && PS[ja] <= target && target < PS[jb], 5);
     int lo = ja, hi = jb;   // invariant: PS[lo] <= target < PS[hi]
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -618,6 +640,7 @@ __device__ __forceinline__ void rank_first_child(const RankCtx& rc, int c, int g
     }
     int j = ja;
     while (j < jb && !in_range_live(rc.N[b + j])) j++;
+    BSS_ASSERT(j < jb && b + j < (int)rc.lbeg[c + 1], 6);
     rc.idx[c * kThreads]   = (uint32_t)j | ((uint32_t)jb << 16);
     rc.aux[c * kThreads]   = (uint32_t)ja;
     cx.stack[c * kThreads] = rc.mpos[b + j];
@@ -662,10 +685,12 @@ __device__ __forceinline__ void rank_unrank(const RankCtx& rc, uint32_t r)
             r -= PS[j] - base;
         }
         gj                     = b + j;
+        BSS_ASSERT(j >= 0 && gj < (int)rc.lbeg[c + 1], 9);
         rc.idx[c * kThreads]   = (uint32_t)j | ((uint32_t)jb << 16);
         rc.aux[c * kThreads]   = aux;
         cx.stack[c * kThreads] = rc.mpos[gj];
     }
+    BSS_ASSERT(r == 0, 10);
 }
 
 // Steps the odometer to the next placement in depth-first order that differs at level `from` or
@@ -675,6 +700,7 @@ __device__ __forceinline__ int rank_advance(const RankCtx& rc, int from)
     const ItemCtx& cx = rc.cx;
     int            c  = from, j = 0;
     for (;; c--) {
+        BSS_ASSERT(c >= 0, 7);
         const int      b   = rc.lbeg[c];
         const uint32_t idx = rc.idx[c * kThreads], aux = rc.aux[c * kThreads];
         const int      jb  = (int)(idx >> 16);
@@ -748,6 +774,7 @@ __device__ __forceinline__ uint32_t leaf_run(const RankCtx& rc, int& j, int jb, 
 #pragma unroll
         for (int i = 0; i < NL; i++) {
             const uint32_t v = p + off[i];
+            BSS_ASSERT(v < (uint32_t)cx.n && row[i] / (uint32_t)cx.mstride < v, 8);
             ok &= __funnelshift_r(__ldg(cx.mask + row[i] + (v >> 5)), 0u, v);
         }
         done++;
@@ -1359,5 +1386,13 @@ extern "C" int bss_debug_phase_cycles(unsigned long long* out, int reset)
         e = cudaMemcpyToSymbol(bss::g_phase_cycles, zero, sizeof zero);
     }
     return (int)e;
+}
+#endif
+
+#ifdef BSS_DEBUG_ASSERT
+extern "C" int bss_debug_assert_counts(unsigned int* out)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, bss::g_assert_fail, sizeof(unsigned int) * 32);
 }
 #endif
