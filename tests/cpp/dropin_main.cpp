@@ -1,0 +1,63 @@
+// Test driver of the C++ drop-in (bsh::InsertionSiteSearch, biorseo_b200/host/site_search.h):
+// does what the patched MOIP constructor of INTEGRATION.md does — open the library, run the
+// search with an allowed_basepair predicate, walk the resulting vector<Motif> — and dumps the
+// sites in the oracle's text format (identifier \t first-second ... \t a-b ...).
+//
+//   dropin <jsonfolder|rinfolder|descfolder> <library path> <seq.txt> <mask.bin>
+//
+// Exit codes: 0 ok, 3 search failed (e.g. no GPU: there is no CPU fallback), 2 usage / input.
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+#include <string>
+#include <vector>
+
+#include "site_search.h"
+
+int main(int argc, char** argv)
+{
+    if (argc != 5) {
+        std::cerr << "usage: dropin <source> <library> <seq.txt> <mask.bin>\n";
+        return 2;
+    }
+    std::ifstream sf(argv[3]);
+    std::string   seq;
+    std::getline(sf, seq);
+    const size_t n = seq.size(), W = (n + 31) / 32;
+    std::ifstream mf(argv[4], std::ios::binary);
+    std::vector<uint32_t> mask(n * W, 0u);
+    mf.read(reinterpret_cast<char*>(mask.data()), (std::streamsize)(mask.size() * 4));
+    if (!sf || (size_t)mf.gcount() != mask.size() * 4) {
+        std::cerr << "cannot read the query\n";
+        return 2;
+    }
+    // the caller's predicate (MOIP::allowed_basepair, cppsrc/MOIP.cpp:896-910) — here backed by the mask file
+    auto allowed = [&](size_t u, size_t v) {
+        const size_t a = u < v ? u : v, b = u < v ? v : u;
+        return a != b && b < n && ((mask[a * W + (b >> 5)] >> (b & 31)) & 1u) != 0;
+    };
+
+    bsh::InsertionSiteSearch search;
+    std::string              err;
+    if (!search.open(argv[1], argv[2], -1, err)) {
+        std::cerr << "ERR: " << err << "\n";
+        return 3;
+    }
+    std::vector<Motif> insertion_sites_;
+    if (!search.run(seq, allowed, insertion_sites_, err)) {
+        std::cerr << "ERR: " << err << "\n";
+        return 3;
+    }
+    for (const Motif& m : insertion_sites_) {
+        std::cout << m.get_identifier() << '\t';
+        for (size_t j = 0; j < m.comp.size(); j++) std::cout << (j ? " " : "") << m.comp[j].pos.first << '-' << m.comp[j].pos.second;
+        std::cout << '\t';
+        for (size_t j = 0; j < m.links_.size(); j++) std::cout << (j ? " " : "") << m.links_[j].nts.first << '-' << m.links_[j].nts.second;
+        std::cout << '\n';
+    }
+    std::cerr << insertion_sites_.size() << " candidate motifs on " << search.library().n_seen() << " (" << search.library().rejected().size()
+              << " ignored motifs), Motif::delay = " << Motif::delay << "\n";
+    return 0;
+}
