@@ -115,8 +115,8 @@ struct bss_library {
     uint32_t              n_modules = 0, n_units = 0;
     std::vector<uint32_t> module_components;
     // work buffers, reused across searches
-    DeviceBuffer d_counts, d_chunk_sites, d_chunk_words, d_totals, d_seq_word_begin, d_alive, d_lane_counts;
-    uint32_t     n_alive = 0;   // items with sites of the last count pass
+    DeviceBuffer d_counts, d_chunk_sites, d_chunk_words, d_totals, d_seq_word_begin, d_alive, d_lane_counts, d_heavy;
+    uint32_t     n_alive = 0, n_heavy = 0;   // items with sites / parked heavy items of the last count pass
     bss_query    oneshot;       // storage of the host-buffer entry points (bss_search, bss_search_batch), reused across calls
     PinnedBuffer h_totals;
     // one spare set of result buffers, recycled by bss_sites_free
@@ -355,7 +355,7 @@ void bss_library_destroy(bss_library* lib)
     if (lib->own_stream) cudaStreamSynchronize(lib->own_stream);
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
-    lib->oneshot.storage.release(); lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
+    lib->oneshot.storage.release(); lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_heavy.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
     lib->d_chunk_words.release(); lib->d_totals.release(); lib->d_seq_word_begin.release(); lib->h_totals.release();
     lib->spare_records.release(); lib->spare_host.release();
     if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
@@ -501,6 +501,13 @@ int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& 
     work.alive       = static_cast<uint32_t*>(lib->d_alive.ptr);
     work.lane_counts = static_cast<uint32_t*>(lib->d_lane_counts.ptr);
     work.lane_cap    = (uint32_t)lane_cap;
+    // heavy items: 1024 items x 256 blocks; [items | ranks | task sites | task lane counts]
+    const size_t heavy_words = plan.list_cap ? 2 * 1024 + 1024 * 256 * (size_t)33 : 4;
+    BSS_CUDA(lib->d_heavy.reserve(heavy_words * 4));
+    work.heavy_items      = static_cast<uint32_t*>(lib->d_heavy.ptr);
+    work.heavy_ranks      = work.heavy_items + 1024;
+    work.task_sites       = work.heavy_ranks + 1024;
+    work.task_lane_counts = work.task_sites + 1024 * 256;
     BSS_CUDA(lib->d_chunk_sites.reserve(8 * (size_t)(plan.n_chunks + 1)));
     BSS_CUDA(lib->d_chunk_words.reserve(8 * (size_t)(plan.n_chunks + 1)));
     BSS_CUDA(lib->d_seq_word_begin.reserve(8 * (size_t)(q->dev.n_seqs + 1)));
@@ -511,24 +518,25 @@ int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& 
     work.seq_word_begin = static_cast<uint64_t*>(lib->d_seq_word_begin.ptr);
     cudaStream_t st = lib->stream;
     lib->stats      = bss_stats{};
-    BSS_CUDA(cudaMemsetAsync(work.totals, 0, 32, st));
+    BSS_CUDA(cudaMemsetAsync(work.totals, 0, 48, st));
     BSS_CUDA(cudaMemsetAsync(work.seq_word_begin, 0, 8 * (size_t)(q->dev.n_seqs + 1), st));
     BSS_CUDA(cudaEventRecord(lib->ev[0], st));
-    BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, st));
+    BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, lib->sm_count, st));
     BSS_CUDA(cudaEventRecord(lib->ev[1], st));
     BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));
     BSS_CUDA(cudaEventRecord(lib->ev[2], st));
-    BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 32, cudaMemcpyDeviceToHost, st));
+    BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 40, cudaMemcpyDeviceToHost, st));
     BSS_CUDA(cudaStreamSynchronize(st));
     const uint64_t* tot = static_cast<const uint64_t*>(lib->h_totals.ptr);
     n_words             = tot[0];
     n_sites             = tot[1];
     lib->n_alive        = (uint32_t)tot[3];
-    lib->stats.kernel_launches   = (plan.n_chunks ? 1u : 0u) + 1u;
+    lib->n_heavy        = (uint32_t)std::min<uint64_t>(tot[4], 1024);
+    lib->stats.kernel_launches   = (plan.n_chunks ? 1u : 0u) + 1u + (plan.group == 32 && plan.list_cap && plan.n_chunks ? 1u : 0u);
     lib->stats.placements_tested = q->total_len * lib->n_units;
     lib->stats.n_sites           = n_sites;
     lib->stats.n_words           = n_words;
-    lib->stats.d2h_bytes         = 32;
+    lib->stats.d2h_bytes         = 40;
     if (tot[2] & 1) return fail(BSS_ERR_COUNT, "a unit has 2^32 or more sites on one sequence");
     return BSS_OK;
 }
@@ -537,7 +545,8 @@ int run_emit(bss_library* lib, const bss_query* q, const bss::Plan& plan, const 
 {
     cudaStream_t st = lib->stream;
     if (n_words && plan.n_chunks) {
-        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, lib->n_alive, st));
+        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, lib->n_alive, lib->n_heavy, lib->sm_count, st));
+        if (lib->n_heavy) lib->stats.kernel_launches++;
         lib->stats.kernel_launches++;
     }
     BSS_CUDA(cudaEventRecord(lib->ev[3], st));

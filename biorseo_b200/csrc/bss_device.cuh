@@ -69,6 +69,8 @@ struct Plan {
     uint32_t group;        // lanes cooperating on one (sequence, unit) item: 4, 8, 16 or 32
     uint32_t W;            // match-mask words per component, ceil((max_len + 1) / 32)
     uint32_t WS;           // summary words per component, ceil(W / 32)
+    uint32_t heavy_ranks;  // items with this many placements before the checks are walked block by block
+    uint32_t heavy_block;  // ranks per block of a heavy item (at most 256 blocks per item)
     uint32_t list_cap;     // rank-space walk: match-list entries per item (0 = depth-first walk only)
     uint32_t smem_bytes;        // dynamic shared memory of the count kernel
     uint32_t smem_bytes_emit;   // ... of the emit kernel (adds the record staging)
@@ -78,10 +80,14 @@ struct Work {
     uint32_t* counts;        // [n_seqs * n_units] sites per item
     uint64_t* chunk_sites;   // [n_chunks]
     uint64_t* chunk_words;   // [n_chunks] ; after the scan: exclusive prefix, [n_chunks] = total
-    uint64_t* totals;        // [0] words, [1] sites, [2] error flags, [3] items with sites (length of `alive`)
+    uint64_t* totals;        // [0] words, [1] sites, [2] error flags, [3] items with sites (length of `alive`), [4] heavy items
     uint32_t* alive;         // [n_seqs * n_units] items with sites, in completion order
     uint32_t* lane_counts;   // [lane_cap][32] sites of every lane's run of ranks (rank-space walk)
     uint32_t  lane_cap;      // alive-list slots that have a lane_counts row
+    uint32_t* heavy_items;   // [1024] items parked by the count pass (rank-space walk, too many placements for one warp)
+    uint32_t* heavy_ranks;   // [1024] their placements before the checks
+    uint32_t* task_sites;    // [1024 * 256] sites of every (heavy item, block) task
+    uint32_t* task_lane_counts;   // [1024 * 256][32] sites of every lane's run inside a task
     uint64_t* seq_word_begin;   // [n_seqs + 1]
 };
 
@@ -89,9 +95,9 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
 
 cudaError_t launch_band(const DevQuery& q, int32_t* band, cudaStream_t s);
 cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, cudaStream_t s);
-cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s);
+cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, int sm_count, cudaStream_t s);
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s);
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                        uint32_t n_alive, cudaStream_t s);
+                        uint32_t n_alive, uint32_t n_heavy, int sm_count, cudaStream_t s);
 
 }   // namespace bss

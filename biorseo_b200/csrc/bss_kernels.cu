@@ -856,22 +856,23 @@ __device__ __forceinline__ uint32_t rank_chunk(const RankCtx& rc, uint32_t first
     return npass;
 }
 
-// Enumerates ranks [0, total): lane l takes the l-th of 32 equal runs of consecutive ranks, so
+// Enumerates ranks [first, first + total): lane l takes the l-th of 32 equal runs of consecutive ranks, so
 // the lanes of a warp carry the same load whatever the shape of the placement tree. Returns the
 // number of sites and, in `lane_sites`, those of this lane's run. The count pass records the
 // latter; their prefix gives every lane its place in the output, so the emit pass is a single
 // walk that writes the records where they belong (when `known` is missing it counts first):
 // canonical order, contiguous block per item.
 template <bool EMIT>
-__device__ __forceinline__ uint64_t rank_walk(const RankCtx& rc, uint32_t total, uint32_t module, uint32_t* __restrict__ out,
+__device__ __forceinline__ uint64_t rank_walk(const RankCtx& rc, uint32_t first, uint32_t total, uint32_t module, uint32_t* __restrict__ out,
                                               const uint32_t* __restrict__ known, uint32_t& lane_sites)
 {
     const ItemCtx& cx   = rc.cx;
     const uint32_t lane = threadIdx.x & 31;
     const int      R    = cx.C + 1;
     const uint32_t per  = (total + 31u) / 32u;
-    const uint32_t mine = lane * per;
-    const uint32_t cnt  = mine < total ? min(per, total - mine) : 0u;
+    const uint32_t skip = lane * per;
+    const uint32_t mine = first + skip;
+    const uint32_t cnt  = skip < total ? min(per, total - skip) : 0u;
     // the fast leaf loop needs every leaf-level check to be an ordered pair with an earlier component
     int leaf_checks = -1;
     if (cx.C >= 2) {
@@ -970,10 +971,26 @@ __device__ __forceinline__ SeqCtx load_seq(const DevLibrary& lib, const DevQuery
 // items that have sites to the alive list, and the CTA leaves the chunk's totals behind.
 // Emit pass (EMIT = true): the groups walk the alive list (any order: every item knows its own
 // place in the output from the scanned chunk totals and the counts of the chunk's earlier items).
-template <int G, bool EMIT>
+// Heavy items (MODE 2, 3; 32-lane groups): an item whose placements before the checks number
+// plan.heavy_ranks or more is not walked by the warp that finds it in the count pass but
+// parked on the heavy list; its rank space is cut into blocks and every (item, block) task is
+// taken by a warp of these passes, which re-derives the item's lists and counts and walks its
+// block only. One monster unit is thereby spread over the whole GPU instead of one warp.
+constexpr int kModeCount = 0, kModeEmit = 1, kModeHeavyCount = 2, kModeHeavyEmit = 3;
+constexpr uint32_t kHeavyCap = 1024, kHeavyMaxBlocks = 256;
+
+__device__ __forceinline__ uint32_t heavy_blocks(uint32_t ranks, uint32_t block)
+{
+    const uint32_t b = (ranks + block - 1) / block;
+    return b > kHeavyMaxBlocks ? kHeavyMaxBlocks : b;
+}
+
+template <int G, int MODE>
 __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const DevLibrary lib, const DevQuery query, const Plan plan,
                                                              const Work work, uint32_t* __restrict__ records, uint32_t n_alive)
 {
+    constexpr bool EMIT = (MODE & 1) != 0, HEAVY = MODE >= 2;
+    static_assert(!HEAVY || G == 32, "heavy items are a 32-lane-group matter");
     using Gr = Group<G>;
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ uint32_t next_unit;
@@ -992,7 +1009,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
     const uint32_t chunk = blockIdx.x;
     uint32_t       u1 = 0;
     SeqCtx         sq{};
-    if (!EMIT) {
+    if (MODE == kModeCount) {
         const uint32_t u0 = (chunk % plan.chunks_per_seq) * plan.units_per_chunk;
         u1                = min(lib.n_units, u0 + plan.units_per_chunk);
         sq                = load_seq(lib, query, chunk / plan.chunks_per_seq);
@@ -1000,14 +1017,60 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
         __syncthreads();
     }
     uint64_t my_sites = 0, my_words = 0;   // accumulated by lane 0 of each group (count pass)
-    uint32_t slot = blockIdx.x * groups + gid;   // emit pass: position in the alive list
+    uint32_t slot = blockIdx.x * groups + gid;   // emit pass: position in the alive list; heavy passes: task
+
+    // heavy passes: tasks = blocks of the heavy items' rank spaces, numbered item after item
+    __shared__ uint32_t task_begin[HEAVY ? kHeavyCap + 1 : 1];
+    uint32_t            n_heavy = 0, n_tasks = 0;
+    if (HEAVY) {
+        n_heavy = (uint32_t)min((unsigned long long)work.totals[4], (unsigned long long)kHeavyCap);
+        if (threadIdx.x < 32) {
+            uint32_t carry = 0;
+            for (uint32_t b = 0; b < n_heavy; b += 32) {
+                const uint32_t h = b + threadIdx.x;
+                uint64_t       total;
+                const uint64_t ex = Group<32>::exclusive(h < n_heavy ? heavy_blocks(work.heavy_ranks[h], plan.heavy_block) : 0u, total);
+                if (h < n_heavy) task_begin[h] = carry + (uint32_t)ex;
+                carry += (uint32_t)total;
+            }
+            if (threadIdx.x == 0) task_begin[n_heavy] = carry;
+        }
+        __syncthreads();
+        n_tasks = task_begin[n_heavy];
+    }
 
     BSS_PHASE_BEGIN();
     for (;; slot += gridDim.x * groups) {
         BSS_PHASE(7);
         uint32_t u = 0;
         uint64_t out_words = 0;   // emit pass: where the item's records start
-        if (!EMIT) {
+        uint32_t rank0 = 0, rank_n = 0, chunk_of_item = 0, heavy_r = 0;   // heavy passes: this task's block of ranks
+        if (HEAVY) {
+            if (slot >= n_tasks) break;
+            int lo = 0, hi = (int)n_heavy;   // item whose tasks contain task `slot`
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (task_begin[mid] <= slot) lo = mid; else hi = mid;
+            }
+            const uint32_t item = work.heavy_items[lo], ranks = work.heavy_ranks[lo];
+            const uint32_t nb = heavy_blocks(ranks, plan.heavy_block), blk = slot - task_begin[lo], per = (ranks + nb - 1) / nb;
+            const uint32_t qi = item / lib.n_units;
+            u                 = item - qi * lib.n_units;
+            sq                = load_seq(lib, query, qi);
+            heavy_r           = ranks;
+            rank0             = blk * per;
+            rank_n            = rank0 < ranks ? min(per, ranks - rank0) : 0u;
+            chunk_of_item     = qi * plan.chunks_per_seq + u / plan.units_per_chunk;
+            if (EMIT) {
+                const uint32_t v0 = (u / plan.units_per_chunk) * plan.units_per_chunk;
+                uint64_t       before = 0;
+                for (uint32_t v = v0 + Gr::lane(); v < u; v += G)
+                    before += (uint64_t)work.counts[sq.item0 + v] * __ldg(lib.unit_rlen + v);
+                for (uint32_t t = Gr::lane(); t < blk; t += G)   // sites of the item's earlier blocks
+                    before += (uint64_t)work.task_sites[task_begin[lo] + t] * __ldg(lib.unit_rlen + u);
+                out_words = work.chunk_words[chunk_of_item] + Gr::sum(before);
+            }
+        } else if (!EMIT) {
             if (Gr::lane() == 0) u = atomicAdd(&next_unit, 1u);
             u = Gr::first(u);
             if (u >= u1) break;
@@ -1044,7 +1107,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
 
         BSS_PHASE(0);
         bool alive = true;
-        if (!EMIT && gate != kNoGate) {   // an emitted item has already passed its gate
+        if (MODE == kModeCount && gate != kNoGate) {   // items of the later passes have already passed their gate
             const uint32_t* gb = lib.blob + __ldg(lib.unit_off + gate);
             alive              = gate_open<G>(gb, occ, WP, g_M, g_SM, W, WS, n);
             Gr::sync();
@@ -1057,7 +1120,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
         BSS_PHASE(1);
         uint64_t item_sites = 0;
         uint32_t lane_sites = 0;
-        bool     ranked     = false;
+        bool     ranked = false, parked = false;
         if (alive) {
             ItemCtx cx;
             cx.blob = blob; cx.M = g_M; cx.T = g_T; cx.SM = g_SM; cx.ST = g_ST; cx.mask = sq.pair_mask;
@@ -1087,9 +1150,22 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
                         BSS_PHASE(4);
                         if (total != ~0ull) {
                             ranked = true;
-                            if (total) {
+                            if (HEAVY) {
+                                BSS_ASSERT(total == heavy_r, 11);
+                                const uint32_t* known = EMIT ? work.task_lane_counts + (size_t)slot * 32 : nullptr;
+                                if (rank_n) item_sites = rank_walk<EMIT>(rc, rank0, rank_n, module, EMIT ? records + out_words : nullptr, known, lane_sites);
+                            } else if (MODE == kModeCount && total >= plan.heavy_ranks) {
+                                uint32_t h = 0;   // park it: the heavy passes walk it block by block
+                                if (Gr::lane() == 0) h = (uint32_t)atomicAdd((unsigned long long*)(work.totals + 4), 1ull);
+                                h = Gr::first(h);
+                                if (h < kHeavyCap) {
+                                    if (Gr::lane() == 0) { work.heavy_items[h] = (uint32_t)(sq.item0 + u); work.heavy_ranks[h] = (uint32_t)total; }
+                                    parked = true;
+                                }
+                            }
+                            if (!HEAVY && !parked && total) {
                                 const uint32_t* known = (EMIT && slot < work.lane_cap) ? work.lane_counts + (size_t)slot * 32 : nullptr;
-                                item_sites = rank_walk<EMIT>(rc, (uint32_t)total, module, EMIT ? records + out_words : nullptr, known, lane_sites);
+                                item_sites = rank_walk<EMIT>(rc, 0u, (uint32_t)total, module, EMIT ? records + out_words : nullptr, known, lane_sites);
                                 BSS_PHASE(5);
                             }
                         }
@@ -1133,7 +1209,19 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
             }
         }
         Gr::sync();   // the group's scratch is reused by its next item
-        if (!EMIT) {
+        if (MODE == kModeHeavyCount) {
+            work.task_lane_counts[(size_t)slot * 32 + Gr::lane()] = lane_sites;
+            if (Gr::lane() == 0) {
+                work.task_sites[slot] = (uint32_t)item_sites;
+                if (item_sites) {
+                    const uint32_t old = atomicAdd(&work.counts[sq.item0 + u], (uint32_t)item_sites);
+                    if (old + (uint32_t)item_sites < old) atomicOr((unsigned long long*)(work.totals + 2), 1ull);
+                    atomicAdd((unsigned long long*)&work.chunk_sites[chunk_of_item], (unsigned long long)item_sites);
+                    atomicAdd((unsigned long long*)&work.chunk_words[chunk_of_item], (unsigned long long)(item_sites * (uint64_t)(C + 1)));
+                }
+            }
+        }
+        if (MODE == kModeCount) {
             uint32_t where = 0;
             if (Gr::lane() == 0) {
                 if (item_sites > 0xFFFFFFFFull) atomicOr((unsigned long long*)(work.totals + 2), 1ull);
@@ -1152,7 +1240,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
         }
     }
 
-    if (!EMIT) {
+    if (MODE == kModeCount) {
         __shared__ unsigned long long cta_sites, cta_words;
         if (threadIdx.x == 0) { cta_sites = 0; cta_words = 0; }
         __syncthreads();
@@ -1272,26 +1360,32 @@ __global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const De
     }
 }
 
-template <bool EMIT>
+template <int MODE>
 cudaError_t launch_search(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                          uint32_t n_alive, cudaStream_t s)
+                          uint32_t n_alive, uint32_t heavy_grid, cudaStream_t s)
 {
+    constexpr bool EMIT = (MODE & 1) != 0, HEAVY = MODE >= 2;
     const uint32_t groups = kThreads / plan.group;
-    const uint32_t grid   = EMIT ? (n_alive + groups - 1) / groups : plan.n_chunks;
+    uint32_t       grid   = HEAVY ? heavy_grid : EMIT ? (n_alive + groups - 1) / groups : plan.n_chunks;
     if (grid == 0) return cudaSuccess;
+    if (grid > (1u << 20)) grid = 1u << 20;
+    const uint32_t smem = EMIT ? plan.smem_bytes_emit : plan.smem_bytes;
 #define BSS_LAUNCH(GG)                                                                                                    \
     do {                                                                                                                  \
-        auto kernel = search_kernel<GG, EMIT>;                                                                            \
-        const uint32_t smem = EMIT ? plan.smem_bytes_emit : plan.smem_bytes;                                               \
+        auto kernel = search_kernel<GG, MODE>;                                                                            \
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
         if (e != cudaSuccess) return e;                                                                                   \
-        kernel<<<grid < (1u << 20) ? grid : (1u << 20), kThreads, smem, s>>>(lib, q, plan, work, records, n_alive);      \
+        kernel<<<grid, kThreads, smem, s>>>(lib, q, plan, work, records, n_alive);                                        \
     } while (0)
-    switch (plan.group) {
-    case 4: BSS_LAUNCH(4); break;
-    case 8: BSS_LAUNCH(8); break;
-    case 16: BSS_LAUNCH(16); break;
-    default: BSS_LAUNCH(32); break;
+    if constexpr (HEAVY) {
+        BSS_LAUNCH(32);
+    } else {
+        switch (plan.group) {
+        case 4: BSS_LAUNCH(4); break;
+        case 8: BSS_LAUNCH(8); break;
+        case 16: BSS_LAUNCH(16); break;
+        default: BSS_LAUNCH(32); break;
+        }
     }
 #undef BSS_LAUNCH
     return cudaGetLastError();
@@ -1331,6 +1425,9 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
         const double want = 1.4 * lib.list_density * max_len + 16.0;
         p.list_cap        = want > 1024.0 ? 1024u : want < 64.0 ? 64u : (((uint32_t)want + 31u) & ~31u);
     }
+    p.heavy_ranks = 1u << 17;
+    if (const char* dbg = getenv("BSS_DEBUG_HEAVY")) p.heavy_ranks = (uint32_t)atoll(dbg);
+    p.heavy_block = p.heavy_ranks / 4 ? p.heavy_ranks / 4 : 1;
     if (const char* dbg = getenv("BSS_DEBUG_CAP")) p.list_cap = p.group == 32 ? (uint32_t)atoi(dbg) : 0u;
     p.smem_bytes      = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, false);
     p.smem_bytes_emit = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, true);
@@ -1357,9 +1454,12 @@ cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s)
+cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, int sm_count, cudaStream_t s)
 {
-    return launch_search<false>(lib, q, plan, work, nullptr, 0, s);
+    cudaError_t e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, s);
+    // the blocks of the items the count pass parked on the heavy list (returns at once when there are none)
+    if (e == cudaSuccess && plan.group == 32 && plan.list_cap) e = launch_search<kModeHeavyCount>(lib, q, plan, work, nullptr, 0, (uint32_t)sm_count * 8u, s);
+    return e;
 }
 
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s)
@@ -1369,12 +1469,15 @@ cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, c
 }
 
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                        uint32_t n_alive, cudaStream_t s)
+                        uint32_t n_alive, uint32_t n_heavy, int sm_count, cudaStream_t s)
 {
-    return launch_search<true>(lib, q, plan, work, records, n_alive, s);
+    cudaError_t e = launch_search<kModeEmit>(lib, q, plan, work, records, n_alive, 0, s);
+    if (e == cudaSuccess && n_heavy) e = launch_search<kModeHeavyEmit>(lib, q, plan, work, records, 0, (uint32_t)sm_count * 8u, s);
+    return e;
 }
 
 }   // namespace bss
+
 
 #ifdef BSS_PHASE_TIMING
 extern "C" int bss_debug_phase_cycles(unsigned long long* out, int reset)

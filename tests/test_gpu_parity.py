@@ -292,3 +292,25 @@ def test_random_tables_long_sequences(seed):
     assert np.array_equal(got.records(), expect)
     got.close()
     dev.close()
+
+
+@pytest.mark.parametrize("seed,threshold", [(0, 64), (3, 200), (8, 1000), (9, 5000)])
+def test_heavy_items_are_walked_block_by_block(seed, threshold, monkeypatch):
+    """Items with many placements are parked by the count pass and walked as (item, block-of-ranks)
+    tasks by separate passes; with the threshold lowered, ordinary items take that route."""
+    monkeypatch.setenv("BSS_DEBUG_HEAVY", str(threshold))
+    test_random_tables_long_sequences(seed)
+    test_full_size_like_small(seed)
+
+
+def test_full_size_like_small(seed=0):
+    """c4b-like units on a 700-nt query, all-allowed mask: thousands of sites per unit."""
+    seq = synth.sequence(700, 40 + seed)
+    modules = synth.json_modules(120, 300 + seed, "c4b")
+    host = b.HostLibrary.from_json_modules(modules)
+    dev = host.to_device()
+    mask = synth.mask_all(700)
+    got = dev.search(seq, mask)
+    assert np.array_equal(got.records(), flat_interp.search_table(host.table(), seq, mask))
+    got.close()
+    dev.close()
