@@ -228,6 +228,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    bench_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(bench_stream)
+
     def run_workload(name, steps, warmup, with_e2e=True, with_collective=True):
         w = make_workload(name, rank)
         with tempfile.TemporaryDirectory() as tmp:
@@ -235,7 +238,7 @@ def main():
         table = host.table()
         dev = host.to_device(local_rank)
         dev.set_module_base(rank * host.n_modules)
-        stream = torch.cuda.current_stream()
+        stream = bench_stream                # a real (non-default) stream: kernels, collectives and the timing events all go there
         dev.set_stream(stream.cuda_stream)
         query = dev.query(w["seqs"], w["masks"])
         seq_lens = [len(s) for s in w["seqs"]]
@@ -382,6 +385,36 @@ def main():
             except Exception as exc:   # a secondary workload must never take the headline down
                 also[name] = {"error": str(exc)[:200]}
         line["also"] = also
+
+    if rank == 0 and world == 1 and not args.no_extra:
+        # Pair-mask producer (row "next" of the path, cppsrc/MOIP.cpp:77-90): n^2 floats in, n^2/8 bytes out,
+        # device pointers, CUDA events; 16000 nt (BSS_MAX_SEQ_LEN): the 1 GB matrix is far larger than L2.
+        try:
+            host = b.HostLibrary.from_json_modules(make_workload("c1", 0)["modules"][:8])
+            dev = host.to_device(local_rank)
+            n = 16000
+            pij = torch.rand((n, n), dtype=torch.float32, device="cuda") * 0.004
+            out = torch.empty((n, (n + 31) // 32), dtype=torch.int32, device="cuda")
+            stream = bench_stream
+            res = {}
+            for layout, (rs, cs) in (("row_major", (n, 1)), ("column_major", (1, n))):
+                for _ in range(3):
+                    dev.pair_mask_device(pij.data_ptr(), n, rs, cs, 1e-3, out.data_ptr(), stream.cuda_stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(10):
+                    dev.pair_mask_device(pij.data_ptr(), n, rs, cs, 1e-3, out.data_ptr(), stream.cuda_stream)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 10
+                nbytes = (n * (n - 1) // 2) * 4 + n * ((n + 31) // 32) * 4      # the floats above the diagonal + the whole bit matrix
+                res[layout] = {"ms": ms, "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+                               "algorithmic_bytes_per_launch": nbytes}
+            line["also"]["pair_mask_from_pij_16000"] = {"describe": "allowed_basepair bit matrix from a 16000 x 16000 float32 probability matrix (HBM-bound: the floats above the diagonal in, the bit matrix out)",
+                                                        "bound": "hbm", "peak": peak, **res}
+            dev.close()
+        except Exception as exc:
+            line.setdefault("also", {})["pair_mask_from_pij_16000"] = {"error": str(exc)[:200]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_search(w, sample_size(args.workload), repeat=1)

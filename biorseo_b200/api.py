@@ -299,6 +299,35 @@ class DeviceLibrary:
     def query(self, seqs, masks):
         return Query(self, seqs, masks)
 
+    def pair_mask(self, pij, theta):
+        """Packed allowed_basepair mask from an n x n float matrix (any strides), built on the device."""
+        pij = np.asarray(pij, dtype=np.float32)
+        n = pij.shape[0]
+        assert pij.ndim == 2 and pij.shape[1] == n
+        rs, cs = (st // 4 for st in pij.strides) if n > 1 else (max(n, 1), 1)
+        mask = np.zeros((n, (n + 31) // 32), dtype=np.uint32)
+        _check(self._lib.bss_pair_mask(self._h, pij.ctypes.data_as(C.c_void_p), n, rs, cs, float(theta), mask.ctypes.data_as(C.c_void_p)))
+        return mask
+
+    def pair_mask_device(self, pij_ptr, n, row_stride, col_stride, theta, mask_ptr, cuda_stream=None):
+        _check(self._lib.bss_pair_mask_device(self._h, C.c_void_p(pij_ptr), n, row_stride, col_stride, float(theta), C.c_void_p(mask_ptr),
+                                              C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def query_pij(self, seq, pij, theta):
+        """One-sequence resident query whose mask is produced on the device from the probability matrix."""
+        seq = seq.encode() if isinstance(seq, str) else bytes(seq)
+        pij = np.asarray(pij, dtype=np.float32)
+        n = len(seq)
+        assert pij.shape == (n, n)
+        rs, cs = (st // 4 for st in pij.strides) if n > 1 else (max(n, 1), 1)
+        q = Query.__new__(Query)
+        q._lib, q._h, q.n_seqs = self._lib, C.c_void_p(), 1
+        q.lengths = np.array([n], dtype=np.uint64)
+        buf = np.frombuffer(seq + b"\0", dtype=np.uint8)
+        _check(self._lib.bss_query_create_pij(self._h, buf.ctypes.data_as(C.c_void_p), n, pij.ctypes.data_as(C.c_void_p), rs, cs, float(theta), C.byref(q._h)))
+        q.h2d_bytes = int(pij.size * 4 + n + 32)
+        return q
+
     def search_query(self, query, fetch=True):
         h = C.c_void_p()
         _check(self._lib.bss_search_query(self._h, query._h, 1 if fetch else 0, C.byref(h)))

@@ -46,6 +46,9 @@ SIGNATURES = {
     "bss_library_module_components": (C.c_uint32, [C.c_void_p, C.c_uint32]),
     "bss_query_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, u64p, C.c_void_p, u64p, C.POINTER(C.c_void_p)]),
     "bss_query_destroy": (None, [C.c_void_p]),
+    "bss_pair_mask_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p]),
+    "bss_pair_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p]),
+    "bss_query_create_pij": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.POINTER(C.c_void_p)]),
     "bss_search_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "bss_search_query_into": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, u64p, u64p]),
     "bss_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -390,9 +390,9 @@ namespace {
 // Validates the host buffers, (re)uses q's device storage and queues upload + occurrence
 // table + band on the library's stream. With `wait` the call returns once the query is resident.
 int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
-               const uint64_t* mask_begin, bool wait)
+               const uint64_t* mask_begin, bool wait, bool device_mask = false)
 {
-    if (!lib || !seq_begin || !mask_begin || (n_seqs && (!seqs || !masks))) return fail(BSS_ERR_INVALID, "null argument");
+    if (!lib || !seq_begin || !mask_begin || (n_seqs && (!seqs || (!masks && !device_mask)))) return fail(BSS_ERR_INVALID, "null argument");
     uint32_t max_len = 0;
     for (uint32_t q = 0; q < n_seqs; q++) {
         if (seq_begin[q + 1] < seq_begin[q] || mask_begin[q + 1] < mask_begin[q]) return fail(BSS_ERR_INVALID, "non-monotonic offsets");
@@ -423,7 +423,7 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     cudaStream_t st = lib->stream;
     e = cudaMemcpyAsync(d + off_sb, sb.data(), 8 * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_mb, mb.data(), 8 * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && total_mask) e = cudaMemcpyAsync(d + off_mask, masks + mask_begin[0], 4 * total_mask, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && total_mask && !device_mask) e = cudaMemcpyAsync(d + off_mask, masks + mask_begin[0], 4 * total_mask, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && total_len) e = cudaMemcpyAsync(d + off_seq, s0, total_len, cudaMemcpyHostToDevice, st);
     q->dev.seq_begin  = reinterpret_cast<const uint64_t*>(d + off_sb);
     q->dev.mask_begin = reinterpret_cast<const uint64_t*>(d + off_mb);
@@ -441,7 +441,7 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     // per-symbol (and per-symbol-pair) occurrence bit rows of every sequence, matched against by every unit
     if (e == cudaSuccess) e = bss::launch_occ(lib->dev, q->dev, reinterpret_cast<uint32_t*>(d + off_occ), st);
     // widest pair the mask allows, per sequence: bounds the window a tied component is searched in
-    if (e == cudaSuccess) e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), st);
+    if (e == cudaSuccess && !device_mask) e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), st);   // (a device-built mask gets its band afterwards)
     // (copies from pageable host memory are staged before cudaMemcpyAsync returns: sb / mb may go out of scope)
     if (e == cudaSuccess && wait) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "query upload");
@@ -453,6 +453,89 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
 }   // namespace
 
 extern "C" {
+
+namespace {
+
+int check_pij_args(const bss_library* lib, const void* pij, uint32_t n, uint64_t row_stride, uint64_t col_stride)
+{
+    if (!lib || (n && !pij)) return fail(BSS_ERR_INVALID, "null argument");
+    if (n > BSS_MAX_SEQ_LEN) return fail(BSS_ERR_LIMIT, "sequence longer than BSS_MAX_SEQ_LEN");
+    if (n > 1 && (row_stride == 0 || col_stride == 0)) return fail(BSS_ERR_INVALID, "zero stride");
+    return BSS_OK;
+}
+
+// elements spanned by an n x n matrix with these strides
+uint64_t pij_extent(uint32_t n, uint64_t row_stride, uint64_t col_stride) { return n ? (uint64_t)(n - 1) * (row_stride + col_stride) + 1 : 0; }
+
+}   // namespace
+
+int bss_pair_mask_device(bss_library* lib, const float* d_pij, uint32_t n, uint64_t row_stride, uint64_t col_stride, float theta,
+                         uint32_t* d_mask, void* cuda_stream)
+{
+    int rc = check_pij_args(lib, d_pij, n, row_stride, col_stride);
+    if (rc != BSS_OK) return rc;
+    if (n && !d_mask) return fail(BSS_ERR_INVALID, "null argument");
+    BSS_CUDA(cudaSetDevice(lib->device));
+    BSS_CUDA(bss::launch_pair_mask(d_pij, n, row_stride, col_stride, theta, d_mask, lib->sm_count,
+                                   cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : lib->stream));
+    return BSS_OK;
+}
+
+int bss_pair_mask(bss_library* lib, const float* pij, uint32_t n, uint64_t row_stride, uint64_t col_stride, float theta, uint32_t* mask)
+{
+    int rc = check_pij_args(lib, pij, n, row_stride, col_stride);
+    if (rc != BSS_OK) return rc;
+    if (n == 0) return BSS_OK;
+    if (!mask) return fail(BSS_ERR_INVALID, "null argument");
+    BSS_CUDA(cudaSetDevice(lib->device));
+    const uint64_t extent = pij_extent(n, row_stride, col_stride), words = (uint64_t)n * ((n + 31) / 32);
+    DeviceBuffer   d_pij, d_mask;
+    cudaError_t    e = d_pij.reserve(extent * 4);
+    if (e == cudaSuccess) e = d_mask.reserve(words * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pij.ptr, pij, extent * 4, cudaMemcpyHostToDevice, lib->stream);
+    if (e == cudaSuccess) e = bss::launch_pair_mask(static_cast<const float*>(d_pij.ptr), n, row_stride, col_stride, theta, static_cast<uint32_t*>(d_mask.ptr), lib->sm_count, lib->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mask, d_mask.ptr, words * 4, cudaMemcpyDeviceToHost, lib->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(lib->stream);
+    d_pij.release();
+    d_mask.release();
+    if (e != cudaSuccess) return cuda_fail(e, "bss_pair_mask");
+    return BSS_OK;
+}
+
+int bss_query_create_pij(bss_library* lib, const char* seq, uint32_t n, const float* pij, uint64_t row_stride, uint64_t col_stride, float theta,
+                         bss_query** out)
+{
+    if (!out) return fail(BSS_ERR_INVALID, "null argument");
+    *out   = nullptr;
+    int rc = check_pij_args(lib, pij, n, row_stride, col_stride);
+    if (rc != BSS_OK) return rc;
+    if (n && !seq) return fail(BSS_ERR_INVALID, "null argument");
+    // the query is laid out as for a host mask (zeroes uploaded in its place), then the mask region is produced on the device
+    const uint64_t        seq_begin[2]  = {0, n};
+    const uint64_t        words         = (uint64_t)n * ((n + 31) / 32);
+    const uint64_t        mask_begin[2] = {0, words};
+    bss_query*            q             = new bss_query();
+    rc = query_fill(lib, q, 1, seq, seq_begin, nullptr, mask_begin, true, /*device_mask=*/true);
+    if (rc == BSS_OK && n) {
+        const uint64_t extent = pij_extent(n, row_stride, col_stride);
+        DeviceBuffer   d_pij;
+        cudaError_t    e = d_pij.reserve(extent * 4);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pij.ptr, pij, extent * 4, cudaMemcpyHostToDevice, lib->stream);
+        if (e == cudaSuccess) e = bss::launch_pair_mask(static_cast<const float*>(d_pij.ptr), n, row_stride, col_stride, theta, const_cast<uint32_t*>(q->dev.masks), lib->sm_count, lib->stream);
+        if (e == cudaSuccess) e = bss::launch_band(q->dev, const_cast<int32_t*>(q->dev.band), lib->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(lib->stream);
+        d_pij.release();
+        if (e != cudaSuccess) rc = cuda_fail(e, "bss_query_create_pij");
+        q->h2d_bytes = 16 * 2 + extent * 4 + n;
+    }
+    if (rc != BSS_OK) {
+        q->storage.release();
+        delete q;
+        return rc;
+    }
+    *out = q;
+    return BSS_OK;
+}
 
 int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
                      const uint64_t* mask_begin, bss_query** out)

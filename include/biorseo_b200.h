@@ -137,6 +137,22 @@ int  bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const
                       const uint32_t* masks, const uint64_t* mask_begin, bss_query** out);
 void bss_query_destroy(bss_query* q);
 
+/* ---- pair mask from the base-pair probability matrix (row "next" of the path: the caller's loop
+ * cppsrc/MOIP.cpp:77-90 that defines MOIP::allowed_basepair, cppsrc/MOIP.cpp:896-910) ---- */
+/* bit v of row u (u < v) is set iff v >= u + 4, u + 6 < n and pij[u * row_stride + v * col_stride] > theta
+ * (float comparison, NaN is "not allowed"). Strides are in elements: (n, 1) for a row-major matrix,
+ * (1, n) for Eigen's column-major MatrixXf. For n <= 6 the mask is empty (the reference's unsigned
+ * n - 6 makes its own behaviour undefined there). */
+/* Device pointers in and out, asynchronous on `cuda_stream` (NULL: the library's stream). */
+int  bss_pair_mask_device(bss_library* lib, const float* d_pij, uint32_t n, uint64_t row_stride, uint64_t col_stride, float theta,
+                          uint32_t* d_mask, void* cuda_stream);
+/* Host matrix in, host mask out (n * ceil(n/32) words): upload, kernel, download. */
+int  bss_pair_mask(bss_library* lib, const float* pij, uint32_t n, uint64_t row_stride, uint64_t col_stride, float theta, uint32_t* mask);
+/* One-sequence query whose pair mask is built on the device from the host probability matrix:
+ * the packed mask never exists on the host. */
+int  bss_query_create_pij(bss_library* lib, const char* seq, uint32_t n, const float* pij, uint64_t row_stride, uint64_t col_stride,
+                          float theta, bss_query** out);
+
 /* ---- search ---- */
 /* Replaces Pool + MOIP::allowed_motifs_from_{desc,rin,json} + find_next_ones_in for every
  * (sequence, unit). Sites come back in canonical order (sequence, unit, depth-first

@@ -162,9 +162,50 @@ static int run_fno(int argc, char** argv)
     return 0;
 }
 
+extern const float* g_oracle_pij;
+
+// pairmask <seqfile> <pijfile: n x n float32, row-major> <theta> <empty json library>
+// Runs the reference's own MOIP constructor (cppsrc/MOIP.cpp:74-90 builds index_of_yuv_ from
+// pij > theta) and prints MOIP::allowed_basepair(u, v) (cppsrc/MOIP.cpp:896-910) for every
+// u < v as n rows of ceil(n/32) hexadecimal words.
+static int run_pairmask(int argc, char** argv)
+{
+    if (argc < 6) return 2;
+    string seq = read_file(argv[2]);
+    if (!seq.empty() && seq.back() == '\n') seq.pop_back();
+    const string bytes = read_file(argv[3]);
+    const size_t n = seq.size(), W = (n + 31) / 32;
+    if (bytes.size() != n * n * 4) {
+        std::fprintf(stderr, "pij file holds %zu bytes, expected %zu\n", bytes.size(), n * n * 4);
+        return 2;
+    }
+    vector<float> pij(n * n);
+    std::memcpy(pij.data(), bytes.data(), bytes.size());
+    g_oracle_pij    = pij.data();
+    g_oracle_mask_n = n;
+    const float theta = (float)std::atof(argv[4]);
+    Motif::delay      = 1;
+    RNA  rna("query", seq, false);
+    MOIP moip(rna, "jsonfolder", argv[5], theta, false);
+    for (size_t u = 0; u < n; u++) {
+        vector<uint32_t> row(W, 0u);
+        for (size_t v = u + 1; v < n; v++)
+            if (moip.allowed_basepair(u, v)) row[v >> 5] |= 1u << (v & 31);
+        string line;
+        char   buf[16];
+        for (size_t w = 0; w < W; w++) {
+            std::snprintf(buf, sizeof buf, "%08x", row[w]);
+            line += buf;
+        }
+        std::puts(line.c_str());
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc >= 5 && string(argv[1]) == "fno") return run_fno(argc, argv);
+    if (argc >= 6 && string(argv[1]) == "pairmask") return run_pairmask(argc, argv);
     if (argc < 6) {
         std::fprintf(stderr, "usage: %s ctor|jobs|bench <source> <library> <seqfile> <maskfile> [threads] [repeat] [max_modules]\n", argv[0]);
         return 2;

@@ -11,12 +11,19 @@
 // Set by the harness before an RNA is constructed: row-major n x ceil(n/32) u32 words.
 const uint32_t* g_oracle_mask_words = nullptr;
 size_t          g_oracle_mask_n     = 0;
+// Or a full probability matrix (row-major n x n floats), for the pair-mask producer tests.
+const float*    g_oracle_pij        = nullptr;
 
 RNA::RNA(void) {}
 
 RNA::RNA(std::string name, std::string seq, bool verbose)
 : verbose_{verbose}, name_(name), seq_(seq), n_(seq.size()), pij_(Eigen::MatrixXf::Zero(seq.size(), seq.size()))
 {
+    if (g_oracle_pij != nullptr && g_oracle_mask_n == n_) {
+        for (size_t u = 0; u < n_; u++)
+            for (size_t v = 0; v < n_; v++) pij_(u, v) = g_oracle_pij[u * n_ + v];
+        return;
+    }
     if (g_oracle_mask_words == nullptr || g_oracle_mask_n != n_) return;
     const size_t W = (n_ + 31) / 32;
     for (size_t u = 0; u < n_; u++)

@@ -160,5 +160,23 @@ def materialise(case, tmp):
     return os.path.join(tmp, "lib")
 
 
+def make_pair_mask_golden():
+    """tests/golden/pair_mask.json: masks produced by the reference's own MOIP constructor
+    (oracle/_ref `pairmask` mode) for the seeded matrices of tests/test_pair_mask.py."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_pair_mask as t
+    cases = []
+    for n, seed, theta in t.CASES:
+        with tempfile.TemporaryDirectory() as tmp:
+            ref = t.reference_mask(synth.sequence(n, seed), t.matrix(n, seed, theta), theta, tmp)
+        cases.append({"n": n, "seed": seed, "theta": theta, "mask_hex": [f"{int(x):08x}" for x in ref.reshape(-1)]})
+    with open(os.path.join(ROOT, "tests", "golden", "pair_mask.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py::make_pair_mask_golden (reference MOIP constructor)", "cases": cases}, f)
+
+
 if __name__ == "__main__":
-    main()
+    if "--pair-mask" in sys.argv:
+        make_pair_mask_golden()
+    else:
+        main()
