@@ -62,6 +62,22 @@ class HostLibrary:
         return cls(h)
 
     @classmethod
+    def load_compiled(cls, path):
+        """Reads a library written by save_compiled(): no parsing, no validation."""
+        lib = capi.load()
+        h = C.c_void_p()
+        _check(lib.bsh_library_load_compiled(str(path).encode(), C.byref(h)), host=True)
+        return cls(h)
+
+    def save_compiled(self, path):
+        _check(self._lib.bsh_library_save_compiled(self._h, str(path).encode()), host=True)
+        return path
+
+    @property
+    def kind(self):
+        return self._lib.bsh_library_kind(self._h)
+
+    @classmethod
     def from_json_modules(cls, modules):
         """modules: iterable of (key, sequence, struct2d), in canonical (key-sorted) order."""
         lib = capi.load()

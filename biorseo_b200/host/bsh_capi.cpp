@@ -33,6 +33,30 @@ int bsh_library_load(int kind, const char* path, bsh_library** out)
     return 0;
 }
 
+int bsh_library_save_compiled(const bsh_library* lib, const char* path)
+{
+    if (!lib || !path) return host_fail("bad argument");
+    std::string err;
+    if (!lib->lib.save_compiled(path, err)) return host_fail(err);
+    return 0;
+}
+
+int bsh_library_load_compiled(const char* path, bsh_library** out)
+{
+    if (!path || !out) return host_fail("bad argument");
+    *out = nullptr;
+    bsh_library* h = new bsh_library();
+    std::string  err;
+    if (!h->lib.load_compiled(path, err)) {
+        delete h;
+        return host_fail(err);
+    }
+    *out = h;
+    return 0;
+}
+
+int bsh_library_kind(const bsh_library* lib) { return lib ? (int)lib->lib.kind() : -1; }
+
 int bsh_library_new(int kind, bsh_library** out)
 {
     if (!out || kind != BSH_KIND_JSON) return host_fail("only JSON-style libraries can be built in memory");

@@ -4,6 +4,7 @@
 #include <cctype>
 #include <climits>
 #include <filesystem>
+#include <cstring>
 #include <fstream>
 #include <sstream>
 
@@ -520,6 +521,122 @@ bool ModuleLibrary::load(LibraryKind kind, const std::string& path, std::string&
         }
         if (!err.empty()) return false;
     }
+    finish();
+    return true;
+}
+
+// ---- compiled library file -------------------------------------------------------------------
+// "BSHLIB1\0", u32 kind, u64 n_seen, modules, rejected, units, gates. Integers little-endian,
+// strings and vectors length-prefixed (u32). Every count is checked against the file size.
+namespace {
+
+struct Writer {
+    std::string out;
+    void u8(uint8_t v) { out.push_back((char)v); }
+    void u32(uint32_t v) { for (int i = 0; i < 4; i++) out.push_back((char)(v >> (8 * i))); }
+    void u64(uint64_t v) { for (int i = 0; i < 8; i++) out.push_back((char)(v >> (8 * i))); }
+    void i16(int16_t v) { out.push_back((char)(uint8_t)v); out.push_back((char)((uint16_t)v >> 8)); }
+    void str(const std::string& s) { u32((uint32_t)s.size()); out += s; }
+    void link(const LinkSpec& l) { i16(l.a.anchor); i16(l.a.off); i16(l.b.anchor); i16(l.b.off); u8(l.long_range ? 1 : 0); }
+};
+
+struct Reader {
+    const std::string& in;
+    size_t             at = 0;
+    bool               ok = true;
+    explicit Reader(const std::string& s) : in(s) {}
+    bool need(size_t n) { if (!ok || in.size() - at < n) ok = false; return ok; }
+    uint8_t u8() { if (!need(1)) return 0; return (uint8_t)in[at++]; }
+    uint32_t u32() { if (!need(4)) return 0; uint32_t v = 0; for (int i = 0; i < 4; i++) v |= (uint32_t)(uint8_t)in[at++] << (8 * i); return v; }
+    uint64_t u64() { if (!need(8)) return 0; uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)(uint8_t)in[at++] << (8 * i); return v; }
+    int16_t i16() { if (!need(2)) return 0; uint16_t v = (uint8_t)in[at] | ((uint16_t)(uint8_t)in[at + 1] << 8); at += 2; return (int16_t)v; }
+    // a count of items that take at least `each` bytes apiece
+    uint32_t count(size_t each) { const uint32_t n = u32(); if (ok && (uint64_t)n * each > in.size() - at) ok = false; return ok ? n : 0; }
+    std::string str() { const uint32_t n = count(1); std::string s; if (ok) { s.assign(in, at, n); at += n; } return s; }
+    LinkSpec link() { LinkSpec l; l.a.anchor = i16(); l.a.off = i16(); l.b.anchor = i16(); l.b.off = i16(); l.long_range = u8() != 0; return l; }
+};
+
+const char kMagic[8] = {'B', 'S', 'H', 'L', 'I', 'B', '1', 0};
+
+}   // namespace
+
+bool ModuleLibrary::save_compiled(const std::string& path, std::string& err) const
+{
+    Writer w;
+    w.out.assign(kMagic, kMagic + 8);
+    w.u32((uint32_t)kind_);
+    w.u64(n_seen_);
+    w.u32((uint32_t)modules_.size());
+    for (const ModuleInfo& m : modules_) {
+        w.str(m.id);
+        w.u32((uint32_t)m.source);
+        w.u32((uint32_t)m.k.size());
+        for (uint32_t k : m.k) w.u32(k);
+        w.u32((uint32_t)m.links.size());
+        for (const LinkSpec& l : m.links) w.link(l);
+        w.u32(m.first_unit);
+        w.u32(m.n_units);
+    }
+    w.u32((uint32_t)rejected_.size());
+    for (const Rejected& r : rejected_) { w.str(r.id); w.u8((uint8_t)r.code); }
+    for (const std::vector<Unit>* set : {&units_, &gates_}) {
+        w.u32((uint32_t)set->size());
+        for (const Unit& u : *set) {
+            w.u32(u.module); w.u32(u.delay); w.u32(u.gate);
+            w.u32((uint32_t)u.patterns.size());
+            for (const std::string& p : u.patterns) w.str(p);
+            w.u32((uint32_t)u.checks.size());
+            for (const LinkSpec& c : u.checks) w.link(c);
+        }
+    }
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    if (!f || !f.write(w.out.data(), (std::streamsize)w.out.size())) { err = "cannot write " + path; return false; }
+    return true;
+}
+
+bool ModuleLibrary::load_compiled(const std::string& path, std::string& err)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { err = "cannot open " + path; return false; }
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string bytes = ss.str();
+    if (bytes.size() < 8 || std::memcmp(bytes.data(), kMagic, 8) != 0) { err = path + " is not a compiled module library"; return false; }
+    Reader r(bytes);
+    r.at = 8;
+    const uint32_t kind = r.u32();
+    if (!r.ok || kind > 2) { err = path + ": bad header"; return false; }
+    clear((LibraryKind)kind);
+    n_seen_ = (size_t)r.u64();
+    const uint32_t n_modules = r.count(24);
+    modules_.resize(n_modules);
+    for (ModuleInfo& m : modules_) {
+        m.id     = r.str();
+        m.source = (source_type)r.u32();
+        m.k.resize(r.count(4));
+        for (uint32_t& k : m.k) k = r.u32();
+        m.links.resize(r.count(9));
+        for (LinkSpec& l : m.links) l = r.link();
+        m.first_unit = r.u32();
+        m.n_units    = r.u32();
+    }
+    rejected_.resize(r.count(5));
+    for (Rejected& x : rejected_) { x.id = r.str(); x.code = (char)r.u8(); }
+    for (std::vector<Unit>* set : {&units_, &gates_}) {
+        set->resize(r.count(20));
+        for (Unit& u : *set) {
+            u.module = r.u32(); u.delay = r.u32(); u.gate = r.u32();
+            u.patterns.resize(r.count(4));
+            for (std::string& p : u.patterns) p = r.str();
+            u.checks.resize(r.count(9));
+            for (LinkSpec& c : u.checks) c = r.link();
+        }
+    }
+    bool sane = r.ok && r.at == bytes.size();
+    for (const Unit& u : units_) sane = sane && u.module < modules_.size() && (u.gate == NO_GATE || u.gate < gates_.size()) && !u.patterns.empty();
+    for (const Unit& u : gates_) sane = sane && u.module < modules_.size() && !u.patterns.empty();
+    for (const ModuleInfo& m : modules_) sane = sane && (uint64_t)m.first_unit + m.n_units <= units_.size() && !m.k.empty();
+    if (!sane) { clear((LibraryKind)kind); err = path + ": truncated or corrupt compiled library"; return false; }
     finish();
     return true;
 }

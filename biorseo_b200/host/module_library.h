@@ -69,6 +69,13 @@ class ModuleLibrary
     // Record [module, p_0 .. p_{C-1}] -> the Motif the reference would have pushed.
     Motif rebuild(const uint32_t* record) const;
 
+    // Compiled form: everything load() produces (accepted modules with their link recipes, the
+    // searchable units, the reject log), in one little-endian binary file. Loading it replaces the
+    // per-run JSON parse / directory walk / per-module validation of cppsrc/MOIP.cpp:159-188,
+    // 211-234, 259-288 by one sequential read.
+    bool save_compiled(const std::string& path, std::string& err) const;
+    bool load_compiled(const std::string& path, std::string& err);
+
     // Direct construction (synthetic libraries in benchmarks and tests).
     void clear(LibraryKind kind);
     // Adds one JSON-style module; returns the reject code or 0.

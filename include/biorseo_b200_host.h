@@ -24,6 +24,12 @@ typedef struct bsh_library bsh_library;
 
 /* Parse + validate a library from disk. 0 on success. */
 int  bsh_library_load(int kind, const char* path, bsh_library** out);
+/* Compiled form of a loaded library (one binary file: accepted modules with their link recipes,
+ * searchable units, reject log). Loading it replaces the per-run JSON parse / directory walk /
+ * validation of cppsrc/MOIP.cpp:159-188, 211-234, 259-288 by one sequential read. */
+int  bsh_library_save_compiled(const bsh_library* lib, const char* path);
+int  bsh_library_load_compiled(const char* path, bsh_library** out);
+int  bsh_library_kind(const bsh_library* lib);                              /* BSH_KIND_* */
 /* Build a JSON-style library in memory (synthetic benchmarks): new, add..., seal. */
 int  bsh_library_new(int kind, bsh_library** out);
 int  bsh_library_add_json(bsh_library* lib, const char* key, const char* sequence, const char* struct2d); /* reject code or 0 */
