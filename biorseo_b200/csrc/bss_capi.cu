@@ -567,7 +567,9 @@ namespace {
 
 // count + scan, then the totals come back to the host. On success `plan` and `work` describe
 // the pending emit.
-int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work, uint64_t& n_words, uint64_t& n_sites)
+int read_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, uint64_t& n_words, uint64_t& n_sites);
+
+int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work, uint64_t& n_words, uint64_t& n_sites, bool wait = true)
 {
     if (q->n_symbols != lib->dev.n_symbols || q->pair_rows != lib->dev.pair_rows || std::memcmp(q->alphabet, lib->dev.alphabet, sizeof q->alphabet))
         return fail(BSS_ERR_INVALID, "the query was created for a library with a different pattern alphabet");
@@ -608,6 +610,14 @@ int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& 
     BSS_CUDA(cudaEventRecord(lib->ev[1], st));
     BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));
     BSS_CUDA(cudaEventRecord(lib->ev[2], st));
+    if (!wait) return BSS_OK;   // the caller queues the emit pass behind it and reads the totals at the end
+    return read_totals(lib, q, plan, work, n_words, n_sites);
+}
+
+// Totals of the count pass back to the host (one synchronisation).
+int read_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, uint64_t& n_words, uint64_t& n_sites)
+{
+    cudaStream_t st = lib->stream;
     BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 40, cudaMemcpyDeviceToHost, st));
     BSS_CUDA(cudaStreamSynchronize(st));
     const uint64_t* tot = static_cast<const uint64_t*>(lib->h_totals.ptr);
@@ -628,7 +638,7 @@ int run_emit(bss_library* lib, const bss_query* q, const bss::Plan& plan, const 
 {
     cudaStream_t st = lib->stream;
     if (n_words && plan.n_chunks) {
-        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, lib->n_alive, lib->n_heavy, lib->sm_count, st));
+        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, lib->n_alive, lib->n_heavy, ~0ull, lib->sm_count, st));
         if (lib->n_heavy) lib->stats.kernel_launches++;
         lib->stats.kernel_launches++;
     }
@@ -700,16 +710,26 @@ int bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_reco
     bss::Plan plan;
     bss::Work work;
     uint64_t  n_words = 0, n_sites = 0;
-    int       rc = run_count(lib, q, plan, work, n_words, n_sites);
+    // Everything is queued at once — count, scan, emit — and the host reads the totals only at the
+    // end: the emit passes take their sizes from device memory and write nothing when the records
+    // would not fit `capacity_words`.
+    int rc = run_count(lib, q, plan, work, n_words, n_sites, /*wait=*/false);
+    if (rc != BSS_OK) return rc;
+    cudaStream_t st = lib->stream;
+    if (plan.n_chunks && d_records && capacity_words) {
+        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, 0xFFFFFFFFu, 0, capacity_words, lib->sm_count, st));
+        if (d_seq_word_begin) BSS_CUDA(bss::launch_guarded_copy(work, capacity_words, d_seq_word_begin, q->dev.n_seqs + 1, st));
+    }
+    BSS_CUDA(cudaEventRecord(lib->ev[3], st));
+    rc           = read_totals(lib, q, plan, work, n_words, n_sites);
     *n_words_out = n_words;
     *n_sites_out = n_sites;
     if (rc != BSS_OK) return rc;
     if (n_words > capacity_words || (n_words && !d_records)) return fail(BSS_ERR_OVERFLOW, "output buffer too small");
-    rc = run_emit(lib, q, plan, work, d_records, n_words);
-    if (rc != BSS_OK) return rc;
-    if (d_seq_word_begin)
-        BSS_CUDA(cudaMemcpyAsync(d_seq_word_begin, work.seq_word_begin, 8 * (size_t)(q->dev.n_seqs + 1), cudaMemcpyDeviceToDevice, lib->stream));
-    BSS_CUDA(cudaStreamSynchronize(lib->stream));
+    if (n_words == 0 && d_seq_word_begin && !(plan.n_chunks && d_records && capacity_words))   // nothing was queued: offsets are all zero
+        BSS_CUDA(cudaMemsetAsync(d_seq_word_begin, 0, 8 * (size_t)(q->dev.n_seqs + 1), st));
+    if (plan.n_chunks) lib->stats.kernel_launches += 1 + (plan.group == 32 && plan.list_cap ? 1 : 0);
+    BSS_CUDA(cudaStreamSynchronize(st));
     return finish_stats(lib);
 }
 

@@ -101,6 +101,7 @@ cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, 
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, int sm_count, cudaStream_t s);
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s);
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                        uint32_t n_alive, uint32_t n_heavy, int sm_count, cudaStream_t s);
+                        uint32_t n_alive, uint32_t n_heavy, uint64_t capacity_words, int sm_count, cudaStream_t s);
+cudaError_t launch_guarded_copy(const Work& work, uint64_t capacity_words, uint64_t* dst, uint32_t n, cudaStream_t s);
 
 }   // namespace bss

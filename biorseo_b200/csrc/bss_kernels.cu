@@ -987,9 +987,16 @@ __device__ __forceinline__ uint32_t heavy_blocks(uint32_t ranks, uint32_t block)
 
 template <int G, int MODE>
 __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const DevLibrary lib, const DevQuery query, const Plan plan,
-                                                             const Work work, uint32_t* __restrict__ records, uint32_t n_alive)
+                                                             const Work work, uint32_t* __restrict__ records, uint32_t n_alive,
+                                                             uint64_t capacity_words)
 {
     constexpr bool EMIT = (MODE & 1) != 0, HEAVY = MODE >= 2;
+    if (EMIT) {
+        // Emit passes queued behind the count pass without a host round trip: the sizes come from
+        // device memory, and nothing is written when the records would not fit the caller's buffer.
+        if (work.totals[0] > capacity_words) return;
+        if (n_alive == 0xFFFFFFFFu) n_alive = (uint32_t)work.totals[3];
+    }
     static_assert(!HEAVY || G == 32, "heavy items are a 32-lane-group matter");
     using Gr = Group<G>;
     extern __shared__ __align__(16) uint32_t smem_raw[];
@@ -1362,11 +1369,12 @@ __global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const De
 
 template <int MODE>
 cudaError_t launch_search(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                          uint32_t n_alive, uint32_t heavy_grid, cudaStream_t s)
+                          uint32_t n_alive, uint32_t heavy_grid, uint64_t capacity_words, cudaStream_t s)
 {
     constexpr bool EMIT = (MODE & 1) != 0, HEAVY = MODE >= 2;
     const uint32_t groups = kThreads / plan.group;
-    uint32_t       grid   = HEAVY ? heavy_grid : EMIT ? (n_alive + groups - 1) / groups : plan.n_chunks;
+    // (n_alive == UINT32_MAX: read on the device; the grid is then a fixed number of CTAs that stride over the list)
+    uint32_t       grid   = HEAVY ? heavy_grid : EMIT ? (n_alive == 0xFFFFFFFFu ? heavy_grid * 4 : (n_alive + groups - 1) / groups) : plan.n_chunks;
     if (grid == 0) return cudaSuccess;
     if (grid > (1u << 20)) grid = 1u << 20;
     const uint32_t smem = EMIT ? plan.smem_bytes_emit : plan.smem_bytes;
@@ -1375,7 +1383,7 @@ cudaError_t launch_search(const DevLibrary& lib, const DevQuery& q, const Plan& 
         auto kernel = search_kernel<GG, MODE>;                                                                            \
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
         if (e != cudaSuccess) return e;                                                                                   \
-        kernel<<<grid, kThreads, smem, s>>>(lib, q, plan, work, records, n_alive);                                        \
+        kernel<<<grid, kThreads, smem, s>>>(lib, q, plan, work, records, n_alive, capacity_words);                        \
     } while (0)
     if constexpr (HEAVY) {
         BSS_LAUNCH(32);
@@ -1456,9 +1464,9 @@ cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, 
 
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, int sm_count, cudaStream_t s)
 {
-    cudaError_t e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, s);
+    cudaError_t e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, 0, s);
     // the blocks of the items the count pass parked on the heavy list (returns at once when there are none)
-    if (e == cudaSuccess && plan.group == 32 && plan.list_cap) e = launch_search<kModeHeavyCount>(lib, q, plan, work, nullptr, 0, (uint32_t)sm_count * 8u, s);
+    if (e == cudaSuccess && plan.group == 32 && plan.list_cap) e = launch_search<kModeHeavyCount>(lib, q, plan, work, nullptr, 0, (uint32_t)sm_count * 8u, 0, s);
     return e;
 }
 
@@ -1469,11 +1477,30 @@ cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, c
 }
 
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                        uint32_t n_alive, uint32_t n_heavy, int sm_count, cudaStream_t s)
+                        uint32_t n_alive, uint32_t n_heavy, uint64_t capacity_words, int sm_count, cudaStream_t s)
 {
-    cudaError_t e = launch_search<kModeEmit>(lib, q, plan, work, records, n_alive, 0, s);
-    if (e == cudaSuccess && n_heavy) e = launch_search<kModeHeavyEmit>(lib, q, plan, work, records, 0, (uint32_t)sm_count * 8u, s);
+    // n_alive == UINT32_MAX: sizes are read on the device (no host round trip after the count pass);
+    // the heavy emit is then launched unconditionally (it returns at once without heavy items).
+    const bool  blind = n_alive == 0xFFFFFFFFu;
+    cudaError_t e     = launch_search<kModeEmit>(lib, q, plan, work, records, n_alive, (uint32_t)sm_count * 8u, capacity_words, s);
+    if (e == cudaSuccess && (n_heavy || (blind && plan.group == 32 && plan.list_cap)))
+        e = launch_search<kModeHeavyEmit>(lib, q, plan, work, records, 0, (uint32_t)sm_count * 8u, capacity_words, s);
     return e;
+}
+
+// dst[0..n] = src[0..n] unless the records did not fit (then nothing may be written)
+__global__ void guarded_copy_kernel(const uint64_t* __restrict__ totals, uint64_t capacity_words, const uint64_t* __restrict__ src,
+                                    uint64_t* __restrict__ dst, uint32_t n)
+{
+    if (totals[0] > capacity_words) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+cudaError_t launch_guarded_copy(const Work& work, uint64_t capacity_words, uint64_t* dst, uint32_t n, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    guarded_copy_kernel<<<n > 4096 ? 16 : 1, 256, 0, s>>>(work.totals, capacity_words, work.seq_word_begin, dst, n);
+    return cudaGetLastError();
 }
 
 }   // namespace bss
