@@ -255,17 +255,16 @@ def main():
         padded = world > 1 and with_collective and n_words <= (4 << 20)
         gatherer = sharded.PaddedGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=int(1.25 * n_words) + 1024) if padded else None
 
+        gathered = []
+
         def step():
             if padded:
-                while True:
-                    head, rec = gatherer.block()
-                    rc, nw, ns = dev.search_query_into(query, rec.data_ptr(), rec.numel(), seq_begin_ptr=head.data_ptr())
-                    if rc != 0:
-                        gatherer.set_count(nw)
-                    out, _ = gatherer.exchange()
-                    if out is not None:
-                        break
-                assert nw == n_words
+                # search straight into this rank's block, all-gather, cut: nothing waits for the host
+                # (the block was sized from the first search; an overflow would show in the flag checked after the loop)
+                head, rec = gatherer.block()
+                rc, nw, ns = dev.search_query_into(query, rec.data_ptr(), rec.numel(), seq_begin_ptr=head.data_ptr())
+                assert rc == 0 and nw == n_words
+                gathered.append(gatherer.exchange_async(dev, stream.cuda_stream))
                 return
             rc, nw, ns = dev.search_query_into(query, records.data_ptr(), records.numel())
             assert rc == 0 and nw == n_words
@@ -298,6 +297,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         wall = time.perf_counter() - wall0
+        if gathered:   # the exchanges were complete and consistent: no overflow, every rank's count, canonical order
+            out, counts, overflow = gathered[-1]
+            assert int(overflow.item()) == 0
+            counts = counts.tolist()
+            assert counts[rank] == n_words
+            mine = out[sum(counts[:rank]):sum(counts[:rank + 1])]
+            assert torch.equal(mine, gatherer.block()[1][:n_words])
         clocks = sampler.summary()
 
         total_ms = float(sum(step_ms))

@@ -388,6 +388,10 @@ class DeviceLibrary:
                                           batch.masks.ctypes.data_as(C.c_void_p), batch.mask_begin.ctypes.data_as(capi.u64p), C.byref(h)))
         return Sites(h, batch.n_seqs)
 
+    def gather_cut(self, blocks_ptr, world, block_words, header_words, out_ptr, counts_ptr, overflow_ptr, cuda_stream=None):
+        _check(self._lib.bss_gather_cut(self._h, C.c_void_p(blocks_ptr), world, block_words, header_words, C.c_void_p(out_ptr), C.c_void_p(counts_ptr),
+                                        C.c_void_p(overflow_ptr), C.c_void_p(cuda_stream) if cuda_stream else None))
+
     def stats(self):
         s = capi.BssStats()
         _check(self._lib.bss_last_stats(self._h, C.byref(s)))

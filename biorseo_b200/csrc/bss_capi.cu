@@ -733,6 +733,17 @@ int bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_reco
     return finish_stats(lib);
 }
 
+int bss_gather_cut(bss_library* lib, const uint32_t* d_blocks, uint32_t world, uint64_t block_words, uint32_t header_words, uint32_t* d_out,
+                   uint64_t* d_counts, uint32_t* d_overflow, void* cuda_stream)
+{
+    if (!lib || !d_blocks || !d_out || !d_counts || !d_overflow) return fail(BSS_ERR_INVALID, "null argument");
+    if (header_words < 2 || (header_words & 1) || block_words < header_words) return fail(BSS_ERR_INVALID, "bad block layout");
+    BSS_CUDA(cudaSetDevice(lib->device));
+    BSS_CUDA(bss::launch_gather_cut(d_blocks, world, block_words, header_words, d_out, d_counts, d_overflow,
+                                    cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : lib->stream));
+    return BSS_OK;
+}
+
 int bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
                      const uint64_t* mask_begin, bss_sites** out)
 {

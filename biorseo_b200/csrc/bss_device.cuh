@@ -97,6 +97,8 @@ cudaError_t launch_band(const DevQuery& q, int32_t* band, cudaStream_t s);
 // bit v of row u (u < v) = v >= u + 4 && u + 6 < n && pij[u * row_stride + v * col_stride] > theta
 cudaError_t launch_pair_mask(const float* pij, uint32_t n, uint64_t row_stride, uint64_t col_stride, float theta, uint32_t* mask,
                              int sm_count, cudaStream_t s);
+cudaError_t launch_gather_cut(const uint32_t* blocks, uint32_t world, uint64_t block_words, uint32_t header_words, uint32_t* out,
+                              uint64_t* counts, uint32_t* overflow, cudaStream_t s);
 cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, cudaStream_t s);
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, int sm_count, cudaStream_t s);
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s);

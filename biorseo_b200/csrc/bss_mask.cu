@@ -106,4 +106,42 @@ cudaError_t launch_pair_mask(const float* pij, uint32_t n, uint64_t row_stride, 
     return cudaGetLastError();
 }
 
+// Cut of a padded all-gather (biorseo_b200/sharded.py: every rank's block is [header | records |
+// padding], the header's last u64 is the number of record words): writes the blocks' records back
+// to back in rank order = canonical (module, placement) order, and the per-rank counts, without the
+// host having to know any size. One CTA per rank. A count that does not fit a block raises *overflow.
+__global__ void __launch_bounds__(256) gather_cut_kernel(const uint32_t* __restrict__ blocks, uint32_t world, uint64_t block_words,
+                                                         uint32_t header_words, uint32_t* __restrict__ out, uint64_t* __restrict__ counts,
+                                                         uint32_t* __restrict__ overflow)
+{
+    const uint32_t r = blockIdx.x;
+    __shared__ uint64_t before, mine;
+    if (threadIdx.x == 0) {
+        uint64_t sum = 0, c = 0;
+        bool     bad = false;
+        for (uint32_t p = 0; p < world; p++) {
+            const uint64_t n = *reinterpret_cast<const uint64_t*>(blocks + p * block_words + header_words - 2);
+            if (n > block_words - header_words) bad = true;
+            if (p < r) sum += n;
+            if (p == r) c = n;
+        }
+        before = sum;
+        mine   = bad ? 0 : c;
+        if (bad) *overflow = 1u;
+        counts[r] = c;
+    }
+    __syncthreads();
+    const uint32_t* src = blocks + r * block_words + header_words;
+    uint32_t*       dst = out + before;
+    for (uint64_t i = threadIdx.x; i < mine; i += 256) dst[i] = src[i];
+}
+
+cudaError_t launch_gather_cut(const uint32_t* blocks, uint32_t world, uint64_t block_words, uint32_t header_words, uint32_t* out,
+                              uint64_t* counts, uint32_t* overflow, cudaStream_t s)
+{
+    if (world == 0) return cudaSuccess;
+    gather_cut_kernel<<<world, 256, 0, s>>>(blocks, world, block_words, header_words, out, counts, overflow);
+    return cudaGetLastError();
+}
+
 }   // namespace bss

@@ -85,6 +85,7 @@ class PaddedGatherer:
         self.capacity = (capacity + 3) & ~3
         self._send = torch.zeros(self.capacity, dtype=torch.int32, device=device)
         self._recv = torch.empty(world * self.capacity, dtype=torch.int32, device=device)
+        self._out = None
 
     def block(self):
         """(header tensor, records tensor): views of this rank's block for the search to fill."""
@@ -107,6 +108,27 @@ class PaddedGatherer:
         h = self.header_words
         out = torch.cat([blocks[r, h:h + c] for r, c in enumerate(counts)]) if sum(counts) else self._send[:0].clone()
         return out, counts
+
+    def exchange_async(self, dev_lib, cuda_stream=None):
+        """The exchange without any host round trip (CUDA only): all-gather of the blocks, then the
+        library's cut kernel writes the canonical concatenation. Returns (out, counts, overflow):
+        device tensors — `out` has room for the worst case, counts[r] words belong to rank r,
+        overflow != 0 means a block was too small (check it at the next point the host waits
+        anyway, then grow() and repeat that search)."""
+        world = dist.get_world_size(self.group)
+        dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+        room = self.capacity - self.header_words
+        if self._out is None or self._out.numel() != world * room:
+            self._out = torch.empty(world * room, dtype=torch.int32, device=self._send.device)
+            self._counts = torch.zeros(world, dtype=torch.int64, device=self._send.device)
+            self._overflow = torch.zeros(1, dtype=torch.int32, device=self._send.device)
+        dev_lib.gather_cut(self._recv.data_ptr(), world, self.capacity, self.header_words, self._out.data_ptr(), self._counts.data_ptr(),
+                           self._overflow.data_ptr(), cuda_stream)
+        return self._out, self._counts, self._overflow
+
+    def grow(self, need_words):
+        self._allocate(self._send.device, int(need_words * self.slack) + 16 + self.header_words)
+        self._out = None
 
     def gather(self, local):
         """Convenience for a stream that already exists elsewhere: copies it into the block first."""

@@ -173,6 +173,16 @@ int  bss_search(bss_library* lib, const char* seq, uint32_t n, const uint32_t* m
 int  bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin,
                       const uint32_t* masks, const uint64_t* mask_begin, bss_sites** out);
 
+/* ---- multi-GPU: cut of a padded all-gather (biorseo_b200/sharded.py) ---- */
+/* d_blocks holds `world` blocks of block_words u32 each: [header_words of header | records | padding];
+ * the last u64 of a header is the block's number of record words (what bss_search_query_into writes
+ * when the header is its d_seq_word_begin and the records follow it). Writes the records of all
+ * blocks back to back, in rank order, to d_out (room for world * (block_words - header_words) words),
+ * the per-rank counts to d_counts[world], and sets *d_overflow to 1 when a count exceeds a block
+ * (then nothing of that exchange may be used). Asynchronous on `cuda_stream`; no host round trip. */
+int  bss_gather_cut(bss_library* lib, const uint32_t* d_blocks, uint32_t world, uint64_t block_words, uint32_t header_words,
+                    uint32_t* d_out, uint64_t* d_counts, uint32_t* d_overflow, void* cuda_stream);
+
 /* ---- results ---- */
 uint64_t        bss_sites_count(const bss_sites* s);
 uint64_t        bss_sites_words(const bss_sites* s);

@@ -314,3 +314,30 @@ def test_full_size_like_small(seed=0):
     assert np.array_equal(got.records(), flat_interp.search_table(host.table(), seq, mask))
     got.close()
     dev.close()
+
+
+def test_gather_cut_concatenates_padded_blocks():
+    """The cut kernel of the padded all-gather-v: blocks [header | records | padding] -> records back to back."""
+    torch = pytest.importorskip("torch")
+    dev = b.HostLibrary.from_json_modules(synth.json_modules(5, 1, "c1")).to_device()
+    rng = np.random.default_rng(3)
+    for world, cap, header in ((1, 64, 4), (2, 1000, 4), (8, 4096, 4), (5, 257 * 4, 22)):
+        counts = [int(c) for c in rng.integers(0, cap - header + 1, world)]
+        counts[rng.integers(0, world)] = 0
+        blocks = rng.integers(0, 1 << 31, (world, cap), dtype=np.int64).astype(np.int32)
+        for r, c in enumerate(counts):
+            blocks[r, header - 2:header] = np.array([c], dtype=np.int64).view(np.int32)
+        d_blocks = torch.from_numpy(blocks).cuda()
+        out = torch.full((world * (cap - header),), -1, dtype=torch.int32, device="cuda")
+        d_counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        dev.gather_cut(d_blocks.data_ptr(), world, cap, header, out.data_ptr(), d_counts.data_ptr(), flag.data_ptr())
+        torch.cuda.synchronize()
+        expect = np.concatenate([blocks[r, header:header + c] for r, c in enumerate(counts)])
+        assert d_counts.tolist() == counts and int(flag.item()) == 0
+        assert np.array_equal(out.cpu().numpy()[:expect.size], expect)
+        blocks[0, header - 2:header] = np.array([cap], dtype=np.int64).view(np.int32)   # a count that cannot fit
+        dev.gather_cut(torch.from_numpy(blocks).cuda().data_ptr(), world, cap, header, out.data_ptr(), d_counts.data_ptr(), flag.data_ptr())
+        torch.cuda.synchronize()
+        assert int(flag.item()) == 1
+    dev.close()
