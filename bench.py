@@ -106,33 +106,57 @@ def algorithmic_bytes(table, seq_lens, n_words):
 # clocks
 # ----------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of this rank's GPU, sampled DURING the timed region. In-process NVML
+    (nvidia_ml_py) when available: a query costs microseconds, where spawning nvidia-smi several times
+    a second from every rank disturbs the very thing being timed; nvidia-smi is the fallback."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+                    try:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.samples.append([mhz, self.max_mhz] + ["Active" if mask & bit else "Not Active" for _, bit in self.REASONS])
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.002 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
         sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 6 and s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+        names = [n for n, _ in self.REASONS]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 6 and str(s[2 + i]).lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------
@@ -256,6 +280,7 @@ def main():
         gatherer = sharded.PaddedGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=int(1.25 * n_words) + 1024) if padded else None
 
         gathered = []
+        breakdown = [] if os.environ.get("BSS_BENCH_BREAKDOWN") else None   # debug: event after the search of every step
 
         def step():
             if padded:
@@ -264,6 +289,9 @@ def main():
                 head, rec = gatherer.block()
                 rc, nw, ns = dev.search_query_into(query, rec.data_ptr(), rec.numel(), seq_begin_ptr=head.data_ptr())
                 assert rc == 0 and nw == n_words
+                if breakdown is not None:
+                    breakdown.append(torch.cuda.Event(enable_timing=True))
+                    breakdown[-1].record(stream)
                 gathered.append(gatherer.exchange_async(dev, stream.cuda_stream))
                 return
             rc, nw, ns = dev.search_query_into(query, records.data_ptr(), records.numel())
@@ -290,6 +318,9 @@ def main():
             torch.cuda.synchronize()
             st = dev.stats()                    # per-kernel device times of that search (read outside the timed region)
             step_ms.append(e0.elapsed_time(e1))
+            if breakdown:
+                sys.stderr.write(f"rank {rank}: search {e0.elapsed_time(breakdown[-1]):.3f} ms, exchange {breakdown[-1].elapsed_time(e1):.3f} ms, "
+                                 f"kernels {st['count_ms'] + st['scan_ms'] + st['emit_ms']:.3f} ms\n")
             for k in kernel_ms:
                 kernel_ms[k].append(st[k])
             launches += st["kernel_launches"]
