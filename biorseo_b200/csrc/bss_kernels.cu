@@ -991,6 +991,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
                                                              uint64_t capacity_words)
 {
     constexpr bool EMIT = (MODE & 1) != 0, HEAVY = MODE >= 2;
+    if (HEAVY && work.totals[4] == 0) return;   // the usual case: nothing was parked
     if (EMIT) {
         // Emit passes queued behind the count pass without a host round trip: the sizes come from
         // device memory, and nothing is written when the records would not fit the caller's buffer.
@@ -1466,7 +1467,7 @@ cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& p
 {
     cudaError_t e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, 0, s);
     // the blocks of the items the count pass parked on the heavy list (returns at once when there are none)
-    if (e == cudaSuccess && plan.group == 32 && plan.list_cap) e = launch_search<kModeHeavyCount>(lib, q, plan, work, nullptr, 0, (uint32_t)sm_count * 8u, 0, s);
+    if (e == cudaSuccess && plan.group == 32 && plan.list_cap) e = launch_search<kModeHeavyCount>(lib, q, plan, work, nullptr, 0, (uint32_t)sm_count * 4u, 0, s);
     return e;
 }
 
@@ -1482,9 +1483,9 @@ cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& pl
     // n_alive == UINT32_MAX: sizes are read on the device (no host round trip after the count pass);
     // the heavy emit is then launched unconditionally (it returns at once without heavy items).
     const bool  blind = n_alive == 0xFFFFFFFFu;
-    cudaError_t e     = launch_search<kModeEmit>(lib, q, plan, work, records, n_alive, (uint32_t)sm_count * 8u, capacity_words, s);
+    cudaError_t e     = launch_search<kModeEmit>(lib, q, plan, work, records, n_alive, (uint32_t)sm_count * 8u, capacity_words, s);   // (blind: 32 CTAs per SM stride over the list)
     if (e == cudaSuccess && (n_heavy || (blind && plan.group == 32 && plan.list_cap)))
-        e = launch_search<kModeHeavyEmit>(lib, q, plan, work, records, 0, (uint32_t)sm_count * 8u, capacity_words, s);
+        e = launch_search<kModeHeavyEmit>(lib, q, plan, work, records, 0, (uint32_t)sm_count * 4u, capacity_words, s);
     return e;
 }
 
