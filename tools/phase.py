@@ -1,14 +1,15 @@
 """Per-phase cycle breakdown (debug build with -DBSS_PHASE_TIMING into scratch/libphase.so)."""
 import ctypes as C, os, subprocess, sys
-ROOT = "/root/repo"; sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from biorseo_b200 import build, capi
 if sys.argv[1] == "build":
     srcs = [os.path.join(build.HERE, s) for s in build.CUDA_SOURCES + build.HOST_SOURCES]
     cmd = [build._nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-DBSS_PHASE_TIMING",
            "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(build.HERE, "host"), "-I", os.path.join(build.HERE, "csrc"),
-           "-o", os.path.join(ROOT, "scratch", "libphase.so")] + srcs
+           "-o", os.path.join(ROOT, "tools", "_build", "libphase.so")] + srcs
+    os.makedirs(os.path.join(ROOT, "tools", "_build"), exist_ok=True)
     subprocess.run(cmd, check=True); sys.exit(0)
-capi.LIB_PATH = os.path.join(ROOT, "scratch", "libphase.so")
+capi.LIB_PATH = os.path.join(ROOT, "tools", "_build", "libphase.so")
 import numpy as np
 import biorseo_b200 as b
 from biorseo_b200 import synth
