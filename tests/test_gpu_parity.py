@@ -341,3 +341,30 @@ def test_gather_cut_concatenates_padded_blocks():
         torch.cuda.synchronize()
         assert int(flag.item()) == 1
     dev.close()
+
+
+@pytest.mark.parametrize("n", [4097, 9000, 16000])
+def test_very_long_sequences(n):
+    """Up to BSS_MAX_SEQ_LEN: the shared-memory working set grows with the sequence; the search either
+    works (and is exact) or refuses with BSS_ERR_LIMIT — never a wrong answer."""
+    rng = np.random.default_rng(n)
+    table = _random_table(rng, 30, [ord(c) for c in "ACGU"], max_comp=3, max_len=7, min_len=5)
+    seq = bytes(rng.choice([ord(c) for c in "ACGU"], n).tolist())
+    mask = _banded_random_mask(n, 1, 60, 0.5)
+    dev = b.DeviceLibrary.from_table(table)
+    got = dev.search(seq, mask)
+    assert np.array_equal(got.records(), flat_interp.search_table(table, seq, mask))
+    got.close()
+    dev.close()
+
+
+def test_working_set_limit_is_reported():
+    rng = np.random.default_rng(5)
+    table = _random_table(rng, 4, [ord(c) for c in "ACGU"], max_comp=3, max_len=6, min_len=5)
+    wide = cases.fno_table(["ACGUA"] * 16, 1)            # 16 components: 16 masks of 501 words per group
+    seq = bytes(rng.choice([ord(c) for c in "ACGU"], 16000).tolist())
+    dev = b.DeviceLibrary.from_table(wide)
+    with pytest.raises(b.SearchError) as err:
+        dev.search(seq, synth.mask_all(16000))
+    assert err.value.code == b.capi.BSS_ERR_LIMIT
+    dev.close()
