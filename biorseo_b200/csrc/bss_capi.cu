@@ -95,6 +95,7 @@ bool can_self_overlap(const uint8_t* p, uint32_t k)
 }   // namespace
 
 struct bss_query {
+    uint64_t      serial = 0;   // distinguishes queries that reuse an address (CUDA graph cache key)
     int           device = 0;
     bss::DevQuery dev{};
     DeviceBuffer  storage;
@@ -117,6 +118,16 @@ struct bss_library {
     // work buffers, reused across searches
     DeviceBuffer d_counts, d_chunk_sites, d_chunk_words, d_totals, d_seq_word_begin, d_alive, d_lane_counts, d_heavy;
     uint32_t     n_alive = 0, n_heavy = 0;   // items with sites / parked heavy items of the last count pass
+    // bss_search_query_into replays its launch sequence as a CUDA graph while its arguments stay the same
+    struct GraphKey {
+        uint64_t query_serial = 0, capacity = 0, dev_serial = 0;
+        const void *records = nullptr, *seq_out = nullptr, *stream = nullptr, *counts = nullptr, *alive = nullptr, *lanes = nullptr, *heavy = nullptr,
+                   *chunk_sites = nullptr, *chunk_words = nullptr, *seq_begin = nullptr;
+        bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof *this) == 0; }
+    } graph_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool            graphs_ok  = true;
+    uint64_t        dev_serial = 1;   // bumped when launch parameters held by value change (module base)
     bss_query    oneshot;       // storage of the host-buffer entry points (bss_search, bss_search_batch), reused across calls
     PinnedBuffer h_totals;
     // one spare set of result buffers, recycled by bss_sites_free
@@ -353,6 +364,7 @@ void bss_library_destroy(bss_library* lib)
     if (!lib) return;
     cudaSetDevice(lib->device);
     if (lib->own_stream) cudaStreamSynchronize(lib->own_stream);
+    if (lib->graph_exec) cudaGraphExecDestroy(lib->graph_exec);
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
     lib->oneshot.storage.release(); lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_heavy.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
@@ -373,6 +385,7 @@ int bss_library_set_module_base(bss_library* lib, uint32_t base)
 {
     if (!lib) return fail(BSS_ERR_INVALID, "null library");
     lib->dev.module_base = base;
+    lib->dev_serial++;
     return BSS_OK;
 }
 
@@ -407,6 +420,8 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
         return fail(BSS_ERR_BAD_SEQUENCE, "query contains a line terminator");
 
     BSS_CUDA(cudaSetDevice(lib->device));
+    static uint64_t next_serial = 0;
+    q->serial    = ++next_serial;
     q->device    = lib->device;
     // one allocation: [seq_begin | mask_begin | band | occurrence table | masks | seqs]
     const uint32_t ns = lib->dev.n_symbols, occ_rows = ns + (lib->dev.pair_rows ? ns * ns : 0u);
@@ -567,9 +582,8 @@ namespace {
 
 // count + scan, then the totals come back to the host. On success `plan` and `work` describe
 // the pending emit.
-int read_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, uint64_t& n_words, uint64_t& n_sites);
-
-int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work, uint64_t& n_words, uint64_t& n_sites, bool wait = true)
+// Validation, work decomposition and (grow-only) work buffers of a search: no stream operation.
+int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work)
 {
     if (q->n_symbols != lib->dev.n_symbols || q->pair_rows != lib->dev.pair_rows || std::memcmp(q->alphabet, lib->dev.alphabet, sizeof q->alphabet))
         return fail(BSS_ERR_INVALID, "the query was created for a library with a different pattern alphabet");
@@ -601,25 +615,33 @@ int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& 
     work.chunk_words    = static_cast<uint64_t*>(lib->d_chunk_words.ptr);
     work.totals         = static_cast<uint64_t*>(lib->d_totals.ptr);
     work.seq_word_begin = static_cast<uint64_t*>(lib->d_seq_word_begin.ptr);
-    cudaStream_t st = lib->stream;
-    lib->stats      = bss_stats{};
-    BSS_CUDA(cudaMemsetAsync(work.totals, 0, 48, st));
-    BSS_CUDA(cudaMemsetAsync(work.seq_word_begin, 0, 8 * (size_t)(q->dev.n_seqs + 1), st));
-    BSS_CUDA(cudaEventRecord(lib->ev[0], st));
-    BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, lib->sm_count, st));
-    BSS_CUDA(cudaEventRecord(lib->ev[1], st));
-    BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));
-    BSS_CUDA(cudaEventRecord(lib->ev[2], st));
-    if (!wait) return BSS_OK;   // the caller queues the emit pass behind it and reads the totals at the end
-    return read_totals(lib, q, plan, work, n_words, n_sites);
+    lib->stats          = bss_stats{};
+    return BSS_OK;
 }
 
-// Totals of the count pass back to the host (one synchronisation).
-int read_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, uint64_t& n_words, uint64_t& n_sites)
+// Timing events: inside a stream capture they must be recorded as external events to stay usable.
+cudaError_t record_event(bss_library* lib, int i, bool capturing)
+{
+    return capturing ? cudaEventRecordWithFlags(lib->ev[i], lib->stream, cudaEventRecordExternal) : cudaEventRecord(lib->ev[i], lib->stream);
+}
+
+// Queues the count pass (+ heavy count) and the scan.
+int enqueue_count(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, bool capturing = false)
 {
     cudaStream_t st = lib->stream;
-    BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 40, cudaMemcpyDeviceToHost, st));
-    BSS_CUDA(cudaStreamSynchronize(st));
+    BSS_CUDA(cudaMemsetAsync(work.totals, 0, 48, st));
+    BSS_CUDA(cudaMemsetAsync(work.seq_word_begin, 0, 8 * (size_t)(q->dev.n_seqs + 1), st));
+    BSS_CUDA(record_event(lib, 0, capturing));
+    BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, lib->sm_count, st));
+    BSS_CUDA(record_event(lib, 1, capturing));
+    BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));
+    BSS_CUDA(record_event(lib, 2, capturing));
+    return BSS_OK;
+}
+
+// What the count pass found, once the copy queued by enqueue_totals has landed.
+int parse_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, uint64_t& n_words, uint64_t& n_sites)
+{
     const uint64_t* tot = static_cast<const uint64_t*>(lib->h_totals.ptr);
     n_words             = tot[0];
     n_sites             = tot[1];
@@ -632,6 +654,18 @@ int read_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, con
     lib->stats.d2h_bytes         = 40;
     if (tot[2] & 1) return fail(BSS_ERR_COUNT, "a unit has 2^32 or more sites on one sequence");
     return BSS_OK;
+}
+
+// count + scan, then the totals come back to the host (one synchronisation). On success `plan`
+// and `work` describe the pending emit.
+int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work, uint64_t& n_words, uint64_t& n_sites)
+{
+    int rc = prepare_search(lib, q, plan, work);
+    if (rc == BSS_OK) rc = enqueue_count(lib, q, plan, work);
+    if (rc != BSS_OK) return rc;
+    BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 40, cudaMemcpyDeviceToHost, lib->stream));
+    BSS_CUDA(cudaStreamSynchronize(lib->stream));
+    return parse_totals(lib, q, plan, n_words, n_sites);
 }
 
 int run_emit(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, uint32_t* d_records, uint64_t n_words)
@@ -712,24 +746,70 @@ int bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_reco
     uint64_t  n_words = 0, n_sites = 0;
     // Everything is queued at once — count, scan, emit — and the host reads the totals only at the
     // end: the emit passes take their sizes from device memory and write nothing when the records
-    // would not fit `capacity_words`.
-    int rc = run_count(lib, q, plan, work, n_words, n_sites, /*wait=*/false);
+    // would not fit `capacity_words`. While the arguments stay the same (a query stream searched
+    // into the same buffer, as in a benchmark loop or a sharded exchange) the whole sequence is
+    // replayed as one CUDA graph: one launch call instead of a dozen.
+    int rc = prepare_search(lib, q, plan, work);
     if (rc != BSS_OK) return rc;
-    cudaStream_t st = lib->stream;
-    if (plan.n_chunks && d_records && capacity_words) {
-        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, 0xFFFFFFFFu, 0, capacity_words, lib->sm_count, st));
-        if (d_seq_word_begin) BSS_CUDA(bss::launch_guarded_copy(work, capacity_words, d_seq_word_begin, q->dev.n_seqs + 1, st));
+    cudaStream_t st      = lib->stream;
+    const bool   emitting = plan.n_chunks && d_records && capacity_words;
+    auto enqueue = [&](bool capturing) -> int {
+        int r = enqueue_count(lib, q, plan, work, capturing);
+        if (r != BSS_OK) return r;
+        if (emitting) {
+            BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, 0xFFFFFFFFu, 0, capacity_words, lib->sm_count, st));
+            if (d_seq_word_begin) BSS_CUDA(bss::launch_guarded_copy(work, capacity_words, d_seq_word_begin, q->dev.n_seqs + 1, st));
+        }
+        BSS_CUDA(record_event(lib, 3, capturing));
+        BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 40, cudaMemcpyDeviceToHost, st));
+        return BSS_OK;
+    };
+    bool launched = false;
+    if (lib->graphs_ok) {
+        bss_library::GraphKey key;
+        key.query_serial = q->serial; key.capacity = capacity_words; key.dev_serial = lib->dev_serial;
+        key.records = d_records; key.seq_out = d_seq_word_begin; key.stream = st; key.counts = work.counts; key.alive = work.alive;
+        key.lanes = work.lane_counts; key.heavy = work.heavy_items; key.chunk_sites = work.chunk_sites; key.chunk_words = work.chunk_words;
+        key.seq_begin = work.seq_word_begin;
+        if (!lib->graph_exec || !(key == lib->graph_key)) {
+            if (lib->graph_exec) { cudaGraphExecDestroy(lib->graph_exec); lib->graph_exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            cudaError_t e     = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                const int   r  = enqueue(true);
+                cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+                e              = r != BSS_OK ? cudaErrorUnknown : e2;
+            }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&lib->graph_exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e != cudaSuccess) {   // no graphs on this stream / driver: plain launches from now on
+                cudaGetLastError();
+                lib->graph_exec = nullptr;
+                lib->graphs_ok  = false;
+            } else {
+                lib->graph_key = key;
+            }
+        }
+        if (lib->graph_exec) {
+            BSS_CUDA(cudaGraphLaunch(lib->graph_exec, st));
+            launched = true;
+        }
     }
-    BSS_CUDA(cudaEventRecord(lib->ev[3], st));
-    rc           = read_totals(lib, q, plan, work, n_words, n_sites);
+    if (!launched) {
+        rc = enqueue(false);
+        if (rc != BSS_OK) return rc;
+    }
+    BSS_CUDA(cudaStreamSynchronize(st));
+    rc           = parse_totals(lib, q, plan, n_words, n_sites);
     *n_words_out = n_words;
     *n_sites_out = n_sites;
     if (rc != BSS_OK) return rc;
     if (n_words > capacity_words || (n_words && !d_records)) return fail(BSS_ERR_OVERFLOW, "output buffer too small");
-    if (n_words == 0 && d_seq_word_begin && !(plan.n_chunks && d_records && capacity_words))   // nothing was queued: offsets are all zero
+    if (d_seq_word_begin && !emitting) {   // nothing was queued for the output: the offsets are all zero
         BSS_CUDA(cudaMemsetAsync(d_seq_word_begin, 0, 8 * (size_t)(q->dev.n_seqs + 1), st));
+        BSS_CUDA(cudaStreamSynchronize(st));
+    }
     if (plan.n_chunks) lib->stats.kernel_launches += 1 + (plan.group == 32 && plan.list_cap ? 1 : 0);
-    BSS_CUDA(cudaStreamSynchronize(st));
     return finish_stats(lib);
 }
 
