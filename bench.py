@@ -5,8 +5,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of synthetic input: every unit of this
-rank's library shard searched on the query (count -> scan -> emit kernels) and, when N > 1,
-the all-gather-v of the site lists. One JSON line is printed by rank 0.
+rank's library shard searched on the query (count -> scan -> emit kernels, queued without a
+host round trip and replayed as a CUDA graph) and, when N > 1, the all-gather-v of the site
+lists (padded single collective + device cut). One JSON line is printed by rank 0.
 
 Workloads (BASELINE.json configs):
   c4        2000-nt query x 50 000 multi-strand JSON motifs per GPU (half 2-4 strands of 5-8 nt,
