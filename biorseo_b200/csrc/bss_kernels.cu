@@ -316,6 +316,7 @@ __device__ __forceinline__ bool match_components(const uint32_t* blob, const uin
             if (w < Wq && last >= (w << 5)) {
                 const int hi = last - (w << 5);
                 m            = hi >= 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u);
+#pragma unroll 4
                 for (int i = 0; i < steps; i++) {
                     const uint32_t  st  = prog[i];
                     const uint32_t* row = occ + (st & 0x7Fu) * WP + w + (st >> 12);
@@ -353,35 +354,49 @@ __device__ __forceinline__ uint32_t thin_components(const uint32_t* blob, const 
         const uint32_t* Sc = SM + c * WS;
         uint32_t*       Tc = T + c * W;
         bool            any = false;
-        for (int w0 = 0; w0 < W; w0 += G) {   // run starts: matches without a match in the k-1 positions before them
+        for (int w0 = 0; w0 < W; w0 += G) {   // followers: matches with another match in the k-1 positions before them
             const int w = w0 + (int)Gr::lane();
-            uint32_t  m = 0, starts = 0;
+            uint32_t  near = 0;
             if (w < W) {
-                m             = Mc[w];
-                uint32_t near = 0;
+                const uint32_t m = Mc[w];
                 if (m)
                     for (int s = 1; s < k; s++) near |= shifted_up(Mc, w, s);
-                starts = m & ~near;
-                Tc[w]  = starts;
+                near &= m;
+                Tc[w] = near;
             }
-            any |= Gr::ballot(m != starts) != 0;
+            any |= Gr::ballot(near != 0) != 0;
         }
-        if (!any) continue;
+        if (!any) continue;   // no two matches overlap on this sequence: the chain from any start is M itself
         ovl |= 1u << c;
         Gr::sync();
-        // Greedy picks inside every run. A lane that reads a word after another lane has
-        // added picks to it restarts from a pick, which reproduces the same chain.
-        for (int w = (int)Gr::lane(); w < W; w += G) {
-            for (uint32_t x = Tc[w]; x; x &= x - 1) {
-                int prev = (w << 5) + __ffs(x) - 1, last = prev;
-                for (;;) {
-                    const int m = next_bit(Mc, Sc, W, WS, prev + 1);
-                    if (m < 0 || m - prev >= k) break;
-                    if (m - last >= k) {
-                        atomicOr(&Tc[m >> 5], 1u << (m & 31));
-                        last = m;
+        // A run needs a greedy walk only if it holds a follower of a follower (three matches or
+        // more): with two, the thinned set is just the run starts.
+        bool deep = false;
+        for (int w0 = 0; w0 < W; w0 += G) {
+            const int w = w0 + (int)Gr::lane();
+            uint32_t  f2 = 0;
+            if (w < W && Tc[w])
+                for (int s = 1; s < k; s++) f2 |= shifted_up(Tc, w, s);
+            deep |= Gr::ballot(w < W && (f2 & Tc[w]) != 0) != 0;
+        }
+        Gr::sync();
+        for (int w = (int)Gr::lane(); w < W; w += G) Tc[w] = Mc[w] & ~Tc[w];   // run starts
+        if (deep) {
+            Gr::sync();
+            // Greedy picks inside every run. A lane that reads a word after another lane has
+            // added picks to it restarts from a pick, which reproduces the same chain.
+            for (int w = (int)Gr::lane(); w < W; w += G) {
+                for (uint32_t x = Tc[w]; x; x &= x - 1) {
+                    int prev = (w << 5) + __ffs(x) - 1, last = prev;
+                    for (;;) {
+                        const int m = next_bit(Mc, Sc, W, WS, prev + 1);
+                        if (m < 0 || m - prev >= k) break;
+                        if (m - last >= k) {
+                            atomicOr(&Tc[m >> 5], 1u << (m & 31));
+                            last = m;
+                        }
+                        prev = m;
                     }
-                    prev = m;
                 }
             }
         }
