@@ -808,12 +808,37 @@ __device__ __forceinline__ uint32_t leaf_run(const RankCtx& rc, int& j, int jb, 
     return done;
 }
 
+// Ranks left in the subtree of the current entry of level `bl` (the current placement included),
+// or 0 when greedy matches are involved on the way down (their counts are not in the prefix sums).
+// The subtree holds N ranks; those already behind are the placements below the earlier siblings
+// of every level below `bl`. Leaves the levels in between on their last sibling, so that an
+// advance from the level above the leaves carries up to `bl`.
+__device__ __forceinline__ uint32_t subtree_skip(uint32_t* idx, const uint32_t* aux, const uint32_t* N, const uint32_t* PS, const uint16_t* lbeg,
+                                              int bl, int L)
+{
+    uint32_t used = 0;
+    for (int c = bl + 1; c <= L; c++) {
+        const uint32_t a      = aux[c * kThreads];
+        const int      parent = (int)lbeg[c - 1] + (int)(idx[(c - 1) * kThreads] & 0xFFFFu);
+        if ((a >> 16) != 0 || (N[parent] & kHasGreedy)) return 0;
+        const uint32_t* PSc = PS + lbeg[c] + c;
+        used += PSc[idx[c * kThreads] & 0xFFFFu] - PSc[a & 0xFFFFu];
+    }
+    const uint32_t below = N[(int)lbeg[bl] + (int)(idx[bl * kThreads] & 0xFFFFu)] & kCountMask;
+    BSS_ASSERT(used < below, 12);
+    for (int c = bl + 1; c < L; c++) {   // last sibling of every level in between
+        const uint32_t end = idx[c * kThreads] >> 16;
+        idx[c * kThreads]  = (end - 1u) | (end << 16);
+    }
+    return below - used;
+}
+
 // Walks `cnt` consecutive ranks from `first` with this lane's odometer and returns how many
 // placements pass their checks. The odometer only steps the upper components; under each of
 // their placements the leaves are a run of consecutive list entries (leaf_run). When EMIT, the
 // records go straight to `dst`, this lane's part of the output: every lane streams through its
 // own contiguous range, and L2 merges the partial sectors before they reach HBM.
-template <bool EMIT>
+template <bool EMIT, bool PRUNE>
 __device__ __forceinline__ uint32_t rank_chunk(const RankCtx& rc, uint32_t first, uint32_t cnt, int leaf_checks, uint32_t module,
                                                uint32_t* __restrict__ dst)
 {
@@ -842,9 +867,17 @@ __device__ __forceinline__ uint32_t rank_chunk(const RankCtx& rc, uint32_t first
             if (--remaining) ok_upper = min(ok_upper, rank_advance(rc, L));
             continue;
         }
-        if (ok_upper < L) {   // an upper check fails: none of the leaves below is a site
+        if (ok_upper < L) {
+            // A check of level ok_upper fails: no placement below the current entry of that level is a
+            // site. Skip the rest of its subtree in one step (subtree_skip).
+            const int       bl = ok_upper;
             const uint32_t* PSL = rc.PS + bL + L;
-            remaining -= min(remaining, PSL[jb] - PSL[j]);
+            uint32_t        skip = PSL[jb] - PSL[j];   // at least the leaves below the current upper placement
+            if (PRUNE && bl < L - 1) {   // (heavy items only: the ordinary passes are sensitive to the extra code)
+                const uint32_t whole = subtree_skip(rc.idx, rc.aux, rc.N, rc.PS, rc.lbeg, bl, L);
+                if (whole) skip = whole;
+            }
+            remaining -= min(remaining, skip);
             j = jb;
         } else {
             uint32_t* base = EMIT ? dst + (size_t)npass * R : nullptr;
@@ -877,7 +910,7 @@ __device__ __forceinline__ uint32_t rank_chunk(const RankCtx& rc, uint32_t first
 // latter; their prefix gives every lane its place in the output, so the emit pass is a single
 // walk that writes the records where they belong (when `known` is missing it counts first):
 // canonical order, contiguous block per item.
-template <bool EMIT>
+template <bool EMIT, bool PRUNE>
 __device__ __forceinline__ uint64_t rank_walk(const RankCtx& rc, uint32_t first, uint32_t total, uint32_t module, uint32_t* __restrict__ out,
                                               const uint32_t* __restrict__ known, uint32_t& lane_sites)
 {
@@ -900,7 +933,7 @@ __device__ __forceinline__ uint64_t rank_walk(const RankCtx& rc, uint32_t first,
     }
     BSS_PHASE_BEGIN();
     // sites of this lane's run: recorded by the count pass, or counted now
-    lane_sites    = (EMIT && known) ? known[lane] : rank_chunk<false>(rc, mine, cnt, leaf_checks, module, nullptr);
+    lane_sites    = (EMIT && known) ? known[lane] : rank_chunk<false, PRUNE>(rc, mine, cnt, leaf_checks, module, nullptr);
     uint32_t incl = lane_sites;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -910,7 +943,7 @@ __device__ __forceinline__ uint64_t rank_walk(const RankCtx& rc, uint32_t first,
     const uint32_t sites = __shfl_sync(0xFFFFFFFFu, incl, 31);
     BSS_PHASE(9);
     if (EMIT && sites) {
-        rank_chunk<true>(rc, mine, cnt, leaf_checks, module, out + (size_t)(incl - lane_sites) * R);
+        rank_chunk<true, PRUNE>(rc, mine, cnt, leaf_checks, module, out + (size_t)(incl - lane_sites) * R);
         __syncwarp();
         BSS_PHASE(10);
     }
@@ -1176,7 +1209,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
                             if (HEAVY) {
                                 BSS_ASSERT(total == heavy_r, 11);
                                 const uint32_t* known = EMIT ? work.task_lane_counts + (size_t)slot * 32 : nullptr;
-                                if (rank_n) item_sites = rank_walk<EMIT>(rc, rank0, rank_n, module, EMIT ? records + out_words : nullptr, known, lane_sites);
+                                if (rank_n) item_sites = rank_walk<EMIT, true>(rc, rank0, rank_n, module, EMIT ? records + out_words : nullptr, known, lane_sites);
                             } else if (MODE == kModeCount && total >= plan.heavy_ranks) {
                                 uint32_t h = 0;   // park it: the heavy passes walk it block by block
                                 if (Gr::lane() == 0) h = (uint32_t)atomicAdd((unsigned long long*)(work.totals + 4), 1ull);
@@ -1188,7 +1221,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
                             }
                             if (!HEAVY && !parked && total) {
                                 const uint32_t* known = (EMIT && slot < work.lane_cap) ? work.lane_counts + (size_t)slot * 32 : nullptr;
-                                item_sites = rank_walk<EMIT>(rc, 0u, (uint32_t)total, module, EMIT ? records + out_words : nullptr, known, lane_sites);
+                                item_sites = rank_walk<EMIT, false>(rc, 0u, (uint32_t)total, module, EMIT ? records + out_words : nullptr, known, lane_sites);
                                 BSS_PHASE(5);
                             }
                         }
@@ -1449,7 +1482,7 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
         const double want = 1.4 * lib.list_density * max_len + 16.0;
         p.list_cap        = want > 1024.0 ? 1024u : want < 64.0 ? 64u : (((uint32_t)want + 31u) & ~31u);
     }
-    p.heavy_ranks = 1u << 17;
+    p.heavy_ranks = 1u << 15;
     if (const char* dbg = getenv("BSS_DEBUG_HEAVY")) p.heavy_ranks = (uint32_t)atoll(dbg);
     p.heavy_block = p.heavy_ranks / 4 ? p.heavy_ranks / 4 : 1;
     if (const char* dbg = getenv("BSS_DEBUG_CAP")) p.list_cap = p.group == 32 ? (uint32_t)atoi(dbg) : 0u;
