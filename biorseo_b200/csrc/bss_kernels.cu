@@ -4,27 +4,32 @@
 // query and materialising every placement before filtering it
 // (cppsrc/Motif.cpp:432-494, cppsrc/MOIP.cpp:1069-1085, 1126-1143, 1178-1212).
 //
-// Shape of the computation. One CTA owns one chunk = (sequence, contiguous range of units).
-// It first turns the query into per-symbol occurrence bit rows in shared memory
-// (bit q of row a = "sequence byte q is alphabet symbol a"). A group of G lanes
-// (G = 4..32, picked from the sequence length) then draws (sequence, unit) items from the
-// chunk's counter and, for each:
-//   1. match:  for every component, M_c = AND_j (occ[pattern_j] >> j), 32 positions per
-//              lane and step, with a one-bit-per-word summary for fast "next match" queries;
-//   2. thin:   components whose matches overlap on this sequence get T_c, the leftmost
-//              non-overlapping matches of every run of overlapping matches. The reference's
-//              candidates for a component in the suffix starting at t (sregex_iterator) are
-//              then: a greedy walk over M_c from t until it lands on a bit of T_c, and T_c
-//              itself from there on;
-//   3. walk:   lanes split the candidates of component 0 by mask word and enumerate the
-//              placements below each depth-first. Every base-pair check is tested as soon as
-//              both of its ends are placed, and a level whose component is tied by a check to
-//              an already placed position only scans the window the pair mask's band allows
-//              (pruning is result-neutral: SURVEY.md appendix B);
-//   4. count / emit: pass 1 counts sites per item, a scan turns counts into offsets,
-//              pass 2 repeats the walk and writes [module, p_0..p_{C-1}] records at their
-//              final, canonical (sequence, unit, depth-first) position. No sort, no atomics
-//              on the output.
+// Shape of the computation (DESIGN.md section 3 has the long version).
+// Once per query: occ_kernel turns every sequence into per-symbol (and per-symbol-pair)
+// occurrence bit rows, band_kernel finds the widest pair its mask allows.
+// Per search, search_kernel<G, MODE>; a group of G lanes (32, or 4..16 for large batches of short
+// sequences) owns one (sequence, unit) item at a time:
+//   count pass   one CTA per chunk = (sequence, contiguous unit range), groups draw units from the
+//                chunk's counter. Per item:
+//     1. match   M_c = AND over the component's match program of shifted occurrence rows, 32
+//                positions per lane and step, with a one-bit-per-word summary;
+//     2. thin    components whose matches overlap on this sequence get T_c, the leftmost
+//                non-overlapping matches of every run. The reference's candidates in the suffix
+//                starting at t (sregex_iterator) are: a greedy walk over M_c from t until it
+//                lands on a bit of T_c, and T_c itself from there on;
+//     3. walk    32-lane groups: sorted match lists, a backward counting programme (placements
+//                below every match before the checks; children are list ranges restricted by
+//                the band windows of adjacent checks), then every lane walks one of 32 equal
+//                runs of consecutive ranks with an odometer, testing the checks (rank-space
+//                walk). Narrow groups / oversized lists: per-lane depth-first walk with the same
+//                chain semantics and windows. Pruning is result-neutral;
+//                per-item counts, per-lane counts, the alive list and chunk totals are recorded;
+//   scan         chunk totals -> 64-bit offsets;
+//   emit pass    the groups stride over the alive list; every item re-derives its lists, takes
+//                its place from the scanned offsets and writes [module, p_0..p_{C-1}] records in
+//                canonical (sequence, unit, depth-first) order. No sort, no output atomics;
+//   heavy passes items with very many placements are parked by the count pass and walked as
+//                (item, block of ranks) tasks spread over a GPU-wide grid, with subtree pruning.
 // Not a contraction: integer/bit work only, no tensor cores.
 #include "bss_device.cuh"
 
@@ -1460,6 +1465,8 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
     // rank-space walk.
     const uint64_t n_items = (uint64_t)n_seqs * lib.n_units;
     p.group = (p.W > 16 || n_items <= (1u << 17)) ? 32 : p.W <= 4 ? 4 : p.W <= 8 ? 8 : 16;
+    // (BSS_DEBUG_* environment variables: developer knobs for experiments and for tests that force the rarely
+    //  taken paths — narrow groups, tiny list capacity, heavy-item blocks — on small inputs; not a tuning interface)
     if (const char* dbg = getenv("BSS_DEBUG_GROUP")) p.group = (uint32_t)atoi(dbg);
     const uint32_t groups = kThreads / p.group;
     // Several waves of CTAs, so that the hardware scheduler evens out chunks of unequal cost;

@@ -368,3 +368,13 @@ def test_working_set_limit_is_reported():
         dev.search(seq, synth.mask_all(16000))
     assert err.value.code == b.capi.BSS_ERR_LIMIT
     dev.close()
+
+
+@pytest.mark.parametrize("knob,value", [("BSS_DEBUG_CAP", "40"), ("BSS_DEBUG_GROUP", "32"), ("BSS_DEBUG_UPC", "3")])
+def test_rarely_taken_paths_forced_on_small_inputs(knob, value, monkeypatch):
+    """Tiny list capacity (items fall back to the depth-first walk inside 32-lane groups), 32-lane groups
+    on short sequences, odd chunk sizes."""
+    monkeypatch.setenv(knob, value)
+    test_random_tables_long_sequences(2)
+    test_random_tables_against_interpreter(4)
+    test_full_size_like_small(1)
