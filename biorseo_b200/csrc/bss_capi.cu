@@ -702,22 +702,45 @@ int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites*
     bss::Plan plan;
     bss::Work work;
     uint64_t  n_words = 0, n_sites = 0;
-    int       rc = run_count(lib, q, plan, work, n_words, n_sites);
+    int       rc = prepare_search(lib, q, plan, work);
     if (rc != BSS_OK) return rc;
 
     bss_sites* s = new bss_sites();
     s->lib       = lib;
-    s->n_words   = n_words;
-    s->n_sites   = n_sites;
     std::swap(s->d_records, lib->spare_records);
     std::swap(s->h_records, lib->spare_host);
     auto bail = [&](int code) { bss_sites_free(s); return code; };
-    cudaError_t e = s->d_records.reserve(std::max<uint64_t>(16, n_words * 4));
-    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(records)"));
-    rc = run_emit(lib, q, plan, work, static_cast<uint32_t*>(s->d_records.ptr), n_words);
-    if (rc != BSS_OK) return bail(rc);
-    s->seq_word_begin.assign(q->dev.n_seqs + 1, 0);
     cudaStream_t st = lib->stream;
+    cudaError_t  e  = cudaSuccess;
+    // The record buffer kept from the previous search is a guess of this one's size: the emit
+    // passes are queued right behind the count pass and write into it when the records fit (they
+    // take their sizes from device memory), so the host's wait for the totals overlaps them.
+    const uint64_t guess_words = s->d_records.cap / 4;
+    bool           emitted     = false;
+    rc = enqueue_count(lib, q, plan, work);
+    if (rc != BSS_OK) return bail(rc);
+    if (guess_words >= 16 && plan.n_chunks) {
+        e = bss::launch_emit(lib->dev, q->dev, plan, work, static_cast<uint32_t*>(s->d_records.ptr), 0xFFFFFFFFu, 0, guess_words, lib->sm_count, st);
+        if (e == cudaSuccess) e = cudaEventRecord(lib->ev[3], st);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "emit launch"));
+        emitted = true;
+    }
+    e = cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 40, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "count pass"));
+    rc = parse_totals(lib, q, plan, n_words, n_sites);
+    if (rc != BSS_OK) return bail(rc);
+    s->n_words = n_words;
+    s->n_sites = n_sites;
+    if (emitted && n_words <= guess_words) {
+        if (plan.n_chunks) lib->stats.kernel_launches += 1 + (plan.group == 32 && plan.list_cap ? 1 : 0);
+    } else {   // first search of this size: allocate, then emit with the sizes now known on the host
+        e = s->d_records.reserve(std::max<uint64_t>(16, n_words * 4));
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(records)"));
+        rc = run_emit(lib, q, plan, work, static_cast<uint32_t*>(s->d_records.ptr), n_words);
+        if (rc != BSS_OK) return bail(rc);
+    }
+    s->seq_word_begin.assign(q->dev.n_seqs + 1, 0);
     if (fetch) {
         e = s->h_records.reserve(std::max<uint64_t>(16, n_words * 4));
         if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost(records)"));
