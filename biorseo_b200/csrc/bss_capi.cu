@@ -112,7 +112,7 @@ struct bss_library {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t  ev[4]      = {nullptr, nullptr, nullptr, nullptr};
     bss::DevLibrary       dev{};
-    DeviceBuffer          d_blob, d_unit_off, d_unit_rlen;
+    DeviceBuffer          d_blob, d_unit_off, d_unit_rlen, d_unit_probe, d_prefilter;
     uint32_t              n_modules = 0, n_units = 0;
     std::vector<uint32_t> module_components;
     // work buffers, reused across searches
@@ -122,7 +122,7 @@ struct bss_library {
     struct GraphKey {
         uint64_t query_serial = 0, capacity = 0, dev_serial = 0;
         const void *records = nullptr, *seq_out = nullptr, *stream = nullptr, *counts = nullptr, *alive = nullptr, *lanes = nullptr, *heavy = nullptr,
-                   *chunk_sites = nullptr, *chunk_words = nullptr, *seq_begin = nullptr;
+                   *chunk_sites = nullptr, *chunk_words = nullptr, *seq_begin = nullptr, *prefilter = nullptr;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof *this) == 0; }
     } graph_key;
     cudaGraphExec_t graph_exec = nullptr;
@@ -191,6 +191,7 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     std::vector<uint32_t> blob, unit_off(n_all + 1, 0);
     std::vector<uint32_t> module_components(t->n_modules, 0);
     std::vector<float>    density;   // per searched unit: expected matches per nucleotide, all components
+    std::vector<uint16_t> unit_probe(4 * (size_t)std::max<uint32_t>(1, t->n_units), 0xFFFFu);   // k-mer probes of up to four components
     uint32_t              cmax = 1;
     for (uint32_t u = 0; u < n_all; u++) {
         unit_off[u] = (uint32_t)blob.size();
@@ -258,6 +259,22 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
                 d += f;
             }
             density.push_back((float)d);
+        }
+        if (u < t->n_units && alphabet.size() <= 4) {   // first window of kKmer consecutive literal symbols of the (up to four) probed patterns
+            uint32_t slot = 0;
+            for (uint32_t c = c0; c < c1 && slot < 4; c++) {
+                const uint32_t pb = t->comp_pat_begin[c], k = t->comp_pat_begin[c + 1] - pb;
+                uint32_t       run = 0;
+                for (uint32_t j = 0; j < k; j++) {
+                    run = t->pattern[pb + j] == '.' ? 0 : run + 1;
+                    if (run >= bss::kKmer) {
+                        uint32_t code = 0;
+                        for (uint32_t i = 0; i < bss::kKmer; i++) code |= (uint32_t)code_of[t->pattern[pb + j + 1 - bss::kKmer + i]] << (2 * i);
+                        unit_probe[4 * (size_t)u + slot++] = (uint16_t)code;
+                        break;
+                    }
+                }
+            }
         }
         const uint32_t pat_words = ((uint32_t)program.size() + 1) / 2;
         const uint32_t head      = 4 + 2 * C;
@@ -336,6 +353,8 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
         for (uint32_t u = 0; u < t->n_units; u++) rlen[u] = (uint8_t)(t->unit_comp_begin[u + 1] - t->unit_comp_begin[u] + 1);
         BSS_CUDA_LIB(lib->d_unit_rlen.reserve(rlen.size()));
         BSS_CUDA_LIB(cudaMemcpy(lib->d_unit_rlen.ptr, rlen.data(), rlen.size(), cudaMemcpyHostToDevice));
+        BSS_CUDA_LIB(lib->d_unit_probe.reserve(unit_probe.size() * 2));
+        BSS_CUDA_LIB(cudaMemcpy(lib->d_unit_probe.ptr, unit_probe.data(), unit_probe.size() * 2, cudaMemcpyHostToDevice));
     }
     BSS_CUDA_LIB(lib->h_totals.reserve(64));
     BSS_CUDA_LIB(lib->d_totals.reserve(64));
@@ -343,6 +362,9 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     lib->dev.blob      = static_cast<const uint32_t*>(lib->d_blob.ptr);
     lib->dev.unit_off  = static_cast<const uint32_t*>(lib->d_unit_off.ptr);
     lib->dev.unit_rlen = static_cast<const uint8_t*>(lib->d_unit_rlen.ptr);
+    lib->dev.unit_probe = nullptr;
+    for (uint16_t p : unit_probe)
+        if (p != 0xFFFFu) { lib->dev.unit_probe = static_cast<const uint16_t*>(lib->d_unit_probe.ptr); break; }
     lib->dev.n_units   = t->n_units;
     lib->dev.n_symbols = (uint32_t)alphabet.size();
     lib->dev.cmax      = cmax;
@@ -367,7 +389,7 @@ void bss_library_destroy(bss_library* lib)
     if (lib->graph_exec) cudaGraphExecDestroy(lib->graph_exec);
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
-    lib->oneshot.storage.release(); lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_heavy.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
+    lib->oneshot.storage.release(); lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_unit_probe.release(); lib->d_prefilter.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_heavy.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
     lib->d_chunk_words.release(); lib->d_totals.release(); lib->d_seq_word_begin.release(); lib->h_totals.release();
     lib->spare_records.release(); lib->spare_host.release();
     if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
@@ -426,7 +448,8 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     // one allocation: [seq_begin | mask_begin | band | occurrence table | masks | seqs]
     const uint32_t ns = lib->dev.n_symbols, occ_rows = ns + (lib->dev.pair_rows ? ns * ns : 0u);
     const uint32_t occ_stride = (max_len + 32) / 32 + bss::kOccPad;
-    const size_t   occ_words  = (size_t)n_seqs * occ_rows * occ_stride;
+    const bool     with_kmers = lib->dev.unit_probe != nullptr;
+    const size_t   occ_words  = (size_t)n_seqs * occ_rows * occ_stride + (with_kmers ? (size_t)n_seqs * bss::kKmerWords : 0);
     const size_t off_sb = 0, off_mb = off_sb + 8 * (size_t)(n_seqs + 1), off_band = off_mb + 8 * (size_t)(n_seqs + 1),
                  off_occ = off_band + 4 * (((size_t)n_seqs + 3) & ~(size_t)3), off_mask = off_occ + 4 * ((occ_words + 3) & ~(size_t)3),
                  off_seq = off_mask + 4 * total_mask, bytes = off_seq + total_len + 16;
@@ -446,6 +469,7 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     q->dev.masks      = reinterpret_cast<const uint32_t*>(d + off_mask);
     q->dev.seqs       = reinterpret_cast<const uint8_t*>(d + off_seq);
     q->dev.occ        = reinterpret_cast<const uint32_t*>(d + off_occ);
+    q->dev.kmers      = with_kmers ? q->dev.occ + (size_t)n_seqs * occ_rows * occ_stride : nullptr;
     q->dev.occ_rows   = occ_rows;
     q->dev.occ_stride = occ_stride;
     q->dev.n_seqs     = n_seqs;
@@ -454,7 +478,7 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     q->pair_rows      = lib->dev.pair_rows;
     std::memcpy(q->alphabet, lib->dev.alphabet, sizeof q->alphabet);
     // per-symbol (and per-symbol-pair) occurrence bit rows of every sequence, matched against by every unit
-    if (e == cudaSuccess) e = bss::launch_occ(lib->dev, q->dev, reinterpret_cast<uint32_t*>(d + off_occ), st);
+    if (e == cudaSuccess) e = bss::launch_occ(lib->dev, q->dev, reinterpret_cast<uint32_t*>(d + off_occ), const_cast<uint32_t*>(q->dev.kmers), st);
     // widest pair the mask allows, per sequence: bounds the window a tied component is searched in
     if (e == cudaSuccess && !device_mask) e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), st);   // (a device-built mask gets its band afterwards)
     // (copies from pageable host memory are staged before cudaMemcpyAsync returns: sb / mb may go out of scope)
@@ -610,6 +634,11 @@ int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::W
     BSS_CUDA(lib->d_chunk_sites.reserve(8 * (size_t)(plan.n_chunks + 1)));
     BSS_CUDA(lib->d_chunk_words.reserve(8 * (size_t)(plan.n_chunks + 1)));
     BSS_CUDA(lib->d_seq_word_begin.reserve(8 * (size_t)(q->dev.n_seqs + 1)));
+    work.prefilter = nullptr;
+    if (lib->dev.unit_probe && q->dev.kmers) {
+        BSS_CUDA(lib->d_prefilter.reserve(4 * ((n_items + 31) / 32) + 4));
+        work.prefilter = static_cast<uint32_t*>(lib->d_prefilter.ptr);
+    }
     work.counts         = static_cast<uint32_t*>(lib->d_counts.ptr);
     work.chunk_sites    = static_cast<uint64_t*>(lib->d_chunk_sites.ptr);
     work.chunk_words    = static_cast<uint64_t*>(lib->d_chunk_words.ptr);
@@ -654,18 +683,6 @@ int parse_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, ui
     lib->stats.d2h_bytes         = 40;
     if (tot[2] & 1) return fail(BSS_ERR_COUNT, "a unit has 2^32 or more sites on one sequence");
     return BSS_OK;
-}
-
-// count + scan, then the totals come back to the host (one synchronisation). On success `plan`
-// and `work` describe the pending emit.
-int run_count(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work, uint64_t& n_words, uint64_t& n_sites)
-{
-    int rc = prepare_search(lib, q, plan, work);
-    if (rc == BSS_OK) rc = enqueue_count(lib, q, plan, work);
-    if (rc != BSS_OK) return rc;
-    BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 40, cudaMemcpyDeviceToHost, lib->stream));
-    BSS_CUDA(cudaStreamSynchronize(lib->stream));
-    return parse_totals(lib, q, plan, n_words, n_sites);
 }
 
 int run_emit(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, uint32_t* d_records, uint64_t n_words)
@@ -793,7 +810,7 @@ int bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_reco
         key.query_serial = q->serial; key.capacity = capacity_words; key.dev_serial = lib->dev_serial;
         key.records = d_records; key.seq_out = d_seq_word_begin; key.stream = st; key.counts = work.counts; key.alive = work.alive;
         key.lanes = work.lane_counts; key.heavy = work.heavy_items; key.chunk_sites = work.chunk_sites; key.chunk_words = work.chunk_words;
-        key.seq_begin = work.seq_word_begin;
+        key.seq_begin = work.seq_word_begin; key.prefilter = work.prefilter;
         if (!lib->graph_exec || !(key == lib->graph_key)) {
             if (lib->graph_exec) { cudaGraphExecDestroy(lib->graph_exec); lib->graph_exec = nullptr; }
             cudaGraph_t graph = nullptr;

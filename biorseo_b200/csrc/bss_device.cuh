@@ -13,6 +13,8 @@ constexpr int      kBlobStage  = 64;           // unit descriptor words staged i
 constexpr uint32_t kNoGate     = 0xFFFFFFFFu;
 constexpr uint32_t kPairAlphabet = 8;          // largest alphabet that gets pair rows (row index must stay below 128)
 constexpr uint32_t kMaxChunkUnits = 2048;      // units per chunk (bounds the per-CTA offset table)
+constexpr uint32_t kKmer        = 6;           // k of the k-mer presence filter (alphabets of at most 4 symbols: 2 bits per symbol)
+constexpr uint32_t kKmerWords   = (1u << (2 * kKmer)) / 32;   // presence bits per sequence
 constexpr uint32_t kCompOverlap = 1u << 24;    // component flag: the pattern is compatible with a shifted copy of itself
 constexpr uint32_t kCheckFixed  = 1u << 24;    // check flag: no end moves at the check's level, or both do
 constexpr uint32_t kCheckOrdered = 1u << 25;   // check flag: 0 <= u < v < n holds for every placement (u = word 0's end)
@@ -38,6 +40,7 @@ struct DevLibrary {
     const uint32_t* blob;
     const uint32_t* unit_off;    // [n_units + n_gates + 1] word offsets into blob
     const uint8_t*  unit_rlen;   // [n_units] words per record of the unit: components + 1
+    const uint16_t* unit_probe;  // [n_units][4] k-mers (kKmer consecutive literal symbols) of up to four components, 0xFFFF = none; null: no filter
     uint32_t        n_units;     // searched units
     uint32_t        n_symbols;   // alphabet size
     uint32_t        cmax;        // max components per unit (gates included)
@@ -54,6 +57,7 @@ struct DevQuery {
     const uint64_t* mask_begin;   // [n_seqs + 1], in words
     const int32_t*  band;         // [n_seqs] max v-u over the set bits above the diagonal, -1 when there is none
     const uint32_t* occ;          // [n_seqs][occ_rows][occ_stride] occurrence table (see occ_kernel)
+    const uint32_t* kmers;        // [n_seqs][kKmerWords] k-mer presence bits, or null (alphabets of more than 4 symbols)
     uint32_t        occ_rows;     // n_symbols, plus n_symbols^2 pair rows for small alphabets
     uint32_t        occ_stride;   // words per row: ceil((max_len + 1) / 32) + kOccPad
     uint32_t        n_seqs;
@@ -78,6 +82,7 @@ struct Plan {
 
 struct Work {
     uint32_t* counts;        // [n_seqs * n_units] sites per item
+    uint32_t* prefilter;     // [ceil(n_items / 32)] bit per item: not ruled out by the k-mer presence filter; null: no filter
     uint64_t* chunk_sites;   // [n_chunks]
     uint64_t* chunk_words;   // [n_chunks] ; after the scan: exclusive prefix, [n_chunks] = total
     uint64_t* totals;        // [0] words, [1] sites, [2] error flags, [3] items with sites (length of `alive`), [4] heavy items
@@ -99,7 +104,7 @@ cudaError_t launch_pair_mask(const float* pij, uint32_t n, uint64_t row_stride, 
                              int sm_count, cudaStream_t s);
 cudaError_t launch_gather_cut(const uint32_t* blocks, uint32_t world, uint64_t block_words, uint32_t header_words, uint32_t* out,
                               uint64_t* counts, uint32_t* overflow, cudaStream_t s);
-cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, cudaStream_t s);
+cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, uint32_t* kmers, cudaStream_t s);
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, int sm_count, cudaStream_t s);
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s);
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,

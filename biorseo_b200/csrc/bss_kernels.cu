@@ -1135,6 +1135,10 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
             if (Gr::lane() == 0) u = atomicAdd(&next_unit, 1u);
             u = Gr::first(u);
             if (u >= u1) break;
+            if (work.prefilter) {   // ruled out by the k-mer presence filter (its count is already written)
+                const uint64_t item = sq.item0 + u;
+                if (!((__ldg(work.prefilter + (item >> 5)) >> (item & 31)) & 1u)) continue;
+            }
         } else {
             if (slot >= n_alive) break;
             const uint32_t item = work.alive[slot];
@@ -1156,7 +1160,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
         const uint32_t  blen  = __ldg(lib.unit_off + u + 1) - boff;
         const uint32_t* gblob = lib.blob + boff;
         const uint32_t* blob  = gblob;
-        if (blen <= kBlobStage) {
+        if (G == 32 && blen <= kBlobStage) {   // narrow groups read the descriptor in place (L1): staging it with 4-16 lanes costs more than it saves
             for (uint32_t i = Gr::lane(); i < blen; i += G) g_blob[i] = __ldg(gblob + i);
             blob = g_blob;
             Gr::sync();
@@ -1393,7 +1397,8 @@ __global__ void __launch_bounds__(256) band_kernel(const DevQuery query, int32_t
 // Occurrence table of every sequence: row a (a < n_symbols) bit q = (seq[q] == alphabet[a]);
 // with `pairs`, row n_symbols + a * n_symbols + b bit q = (seq[q] == alphabet[a] && seq[q+1] == alphabet[b]).
 // Rows are `stride` words long and zero beyond the sequence. One CTA per sequence.
-__global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const DevLibrary lib, uint32_t* __restrict__ occ)
+__global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const DevLibrary lib, uint32_t* __restrict__ occ,
+                                                  uint32_t* __restrict__ kmers)
 {
     const uint32_t qi = blockIdx.x;
     const uint64_t sb = query.seq_begin[qi];
@@ -1412,6 +1417,23 @@ __global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const De
             if (lane == 0) mine[a * WP + w] = bits;
         }
     }
+    if (kmers) {   // which kKmer-mers over the (<= 4 symbol) alphabet occur in the sequence
+        uint32_t* bits = kmers + (size_t)qi * kKmerWords;
+        for (int i = threadIdx.x; i < (int)kKmerWords; i += 128) bits[i] = 0;
+        __syncthreads();
+        for (int q = threadIdx.x; q + (int)kKmer <= n; q += 128) {
+            uint32_t code = 0;
+            bool     ok   = true;
+            for (int j = 0; j < (int)kKmer && ok; j++) {
+                const int byte = (int)__ldg(seq + q + j);
+                int       a    = 0;
+                while (a < ns && (int)lib.alphabet[a] != byte) a++;
+                ok = a < ns;
+                code |= (uint32_t)a << (2 * j);
+            }
+            if (ok) atomicOr(&bits[code >> 5], 1u << (code & 31));
+        }
+    }
     if ((int)query.occ_rows == ns) return;
     __syncthreads();
     for (int i = threadIdx.x; i < ns * ns * WP; i += 128) {
@@ -1419,6 +1441,42 @@ __global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const De
         const uint32_t lo = mine[b * WP + w], hi = w + 1 < WP ? mine[b * WP + w + 1] : 0u;
         mine[(ns + r) * WP + w] = mine[a * WP + w] & __funnelshift_r(lo, hi, 1);
     }
+}
+
+// k-mer presence filter, one thread per (sequence, unit) item: a component that contains kKmer
+// consecutive literal symbols cannot match a sequence in which that k-mer never occurs. Items
+// ruled out this way get their count (0) here and one bit in `prefilter`; the count pass skips
+// them before it touches their descriptor. Most search-bound items end here.
+__global__ void __launch_bounds__(256) prefilter_kernel(const DevLibrary lib, const DevQuery query, uint32_t* __restrict__ counts,
+                                                        uint32_t* __restrict__ prefilter, uint64_t n_items)
+{
+    for (uint64_t item = (uint64_t)blockIdx.x * 256 + threadIdx.x; item < ((n_items + 31) & ~31ull); item += (uint64_t)gridDim.x * 256) {
+        bool alive = false;
+        if (item < n_items) {
+            const uint32_t  qi = (uint32_t)(item / lib.n_units), u = (uint32_t)(item - (uint64_t)qi * lib.n_units);
+            const uint32_t* bits = query.kmers + (size_t)qi * kKmerWords;
+            const uint2     pr = __ldg(reinterpret_cast<const uint2*>(lib.unit_probe) + u);   // four u16 probes
+            alive = true;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t p = ((i < 2 ? pr.x : pr.y) >> (16 * (i & 1))) & 0xFFFFu;
+                if (p != 0xFFFFu && !((__ldg(bits + (p >> 5)) >> (p & 31)) & 1u)) alive = false;
+            }
+            if (!alive) counts[item] = 0;
+        }
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, alive);
+        if ((threadIdx.x & 31) == 0) prefilter[item >> 5] = word;
+    }
+}
+
+cudaError_t launch_prefilter(const DevLibrary& lib, const DevQuery& q, const Work& work, int sm_count, cudaStream_t s)
+{
+    const uint64_t n_items = (uint64_t)q.n_seqs * lib.n_units;
+    if (n_items == 0) return cudaSuccess;
+    uint64_t grid = (n_items + 255) / 256;
+    if (grid > (uint64_t)sm_count * 64) grid = (uint64_t)sm_count * 64;
+    prefilter_kernel<<<(uint32_t)grid, 256, 0, s>>>(lib, q, work.counts, work.prefilter, n_items);
+    return cudaGetLastError();
 }
 
 template <int MODE>
@@ -1511,16 +1569,17 @@ cudaError_t launch_band(const DevQuery& q, int32_t* band, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, cudaStream_t s)
+cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, uint32_t* kmers, cudaStream_t s)
 {
     if (q.n_seqs == 0) return cudaSuccess;
-    occ_kernel<<<q.n_seqs, 128, 0, s>>>(q, lib, occ);
+    occ_kernel<<<q.n_seqs, 128, 0, s>>>(q, lib, occ, kmers);
     return cudaGetLastError();
 }
 
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, int sm_count, cudaStream_t s)
 {
-    cudaError_t e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, 0, s);
+    cudaError_t e = work.prefilter ? launch_prefilter(lib, q, work, sm_count, s) : cudaSuccess;
+    if (e == cudaSuccess) e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, 0, s);
     // the blocks of the items the count pass parked on the heavy list (returns at once when there are none)
     if (e == cudaSuccess && plan.group == 32 && plan.list_cap) e = launch_search<kModeHeavyCount>(lib, q, plan, work, nullptr, 0, (uint32_t)sm_count * 4u, 0, s);
     return e;
