@@ -260,20 +260,19 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
             }
             density.push_back((float)d);
         }
-        if (u < t->n_units && alphabet.size() <= 4) {   // first window of kKmer consecutive literal symbols of the (up to four) probed patterns
+        if (u < t->n_units && alphabet.size() <= 4) {   // longest window (4..6) of consecutive literal symbols of the (up to four) probed patterns
             uint32_t slot = 0;
             for (uint32_t c = c0; c < c1 && slot < 4; c++) {
                 const uint32_t pb = t->comp_pat_begin[c], k = t->comp_pat_begin[c + 1] - pb;
-                uint32_t       run = 0;
-                for (uint32_t j = 0; j < k; j++) {
+                uint32_t       run = 0, best = 0, best_end = 0;
+                for (uint32_t j = 0; j < k && best < bss::kKmerMax; j++) {
                     run = t->pattern[pb + j] == '.' ? 0 : run + 1;
-                    if (run >= bss::kKmer) {
-                        uint32_t code = 0;
-                        for (uint32_t i = 0; i < bss::kKmer; i++) code |= (uint32_t)code_of[t->pattern[pb + j + 1 - bss::kKmer + i]] << (2 * i);
-                        unit_probe[4 * (size_t)u + slot++] = (uint16_t)code;
-                        break;
-                    }
+                    if (std::min(run, bss::kKmerMax) > best) { best = std::min(run, bss::kKmerMax); best_end = j + 1; }
                 }
+                if (best < bss::kKmerMin) continue;
+                uint32_t code = 0;
+                for (uint32_t i = 0; i < best; i++) code |= (uint32_t)code_of[t->pattern[pb + best_end - best + i]] << (2 * i);
+                unit_probe[4 * (size_t)u + slot++] = (uint16_t)(code | ((best - bss::kKmerMin) << 12));
             }
         }
         const uint32_t pat_words = ((uint32_t)program.size() + 1) / 2;

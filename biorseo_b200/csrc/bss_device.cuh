@@ -13,8 +13,11 @@ constexpr int      kBlobStage  = 64;           // unit descriptor words staged i
 constexpr uint32_t kNoGate     = 0xFFFFFFFFu;
 constexpr uint32_t kPairAlphabet = 8;          // largest alphabet that gets pair rows (row index must stay below 128)
 constexpr uint32_t kMaxChunkUnits = 2048;      // units per chunk (bounds the per-CTA offset table)
-constexpr uint32_t kKmer        = 6;           // k of the k-mer presence filter (alphabets of at most 4 symbols: 2 bits per symbol)
-constexpr uint32_t kKmerWords   = (1u << (2 * kKmer)) / 32;   // presence bits per sequence
+// k-mer presence filter (alphabets of at most 4 symbols, 2 bits per symbol): per sequence one bit per
+// possible 4-, 5- and 6-mer; a probe is code | table << 12 (table 0, 1, 2 = k 4, 5, 6), 0xFFFF = none
+constexpr uint32_t kKmerMin     = 4, kKmerMax = 6;
+constexpr uint32_t kKmerWords   = (256 + 1024 + 4096) / 32;   // presence bits per sequence, the three tables back to back
+__host__ __device__ constexpr uint32_t kmer_table_word(uint32_t table) { return table == 0 ? 0u : table == 1 ? 8u : 40u; }
 constexpr uint32_t kCompOverlap = 1u << 24;    // component flag: the pattern is compatible with a shifted copy of itself
 constexpr uint32_t kCheckFixed  = 1u << 24;    // check flag: no end moves at the check's level, or both do
 constexpr uint32_t kCheckOrdered = 1u << 25;   // check flag: 0 <= u < v < n holds for every placement (u = word 0's end)
@@ -40,7 +43,7 @@ struct DevLibrary {
     const uint32_t* blob;
     const uint32_t* unit_off;    // [n_units + n_gates + 1] word offsets into blob
     const uint8_t*  unit_rlen;   // [n_units] words per record of the unit: components + 1
-    const uint16_t* unit_probe;  // [n_units][4] k-mers (kKmer consecutive literal symbols) of up to four components, 0xFFFF = none; null: no filter
+    const uint16_t* unit_probe;  // [n_units][4] k-mer probes (longest window of 4..6 consecutive literal symbols) of up to four components, 0xFFFF = none; null: no filter
     uint32_t        n_units;     // searched units
     uint32_t        n_symbols;   // alphabet size
     uint32_t        cmax;        // max components per unit (gates included)

@@ -1417,21 +1417,23 @@ __global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const De
             if (lane == 0) mine[a * WP + w] = bits;
         }
     }
-    if (kmers) {   // which kKmer-mers over the (<= 4 symbol) alphabet occur in the sequence
+    if (kmers) {   // which 4-, 5- and 6-mers over the (<= 4 symbol) alphabet occur in the sequence
         uint32_t* bits = kmers + (size_t)qi * kKmerWords;
         for (int i = threadIdx.x; i < (int)kKmerWords; i += 128) bits[i] = 0;
         __syncthreads();
-        for (int q = threadIdx.x; q + (int)kKmer <= n; q += 128) {
+        for (int q = threadIdx.x; q + (int)kKmerMin <= n; q += 128) {
             uint32_t code = 0;
-            bool     ok   = true;
-            for (int j = 0; j < (int)kKmer && ok; j++) {
+            for (int j = 0; j < (int)kKmerMax && q + j < n; j++) {
                 const int byte = (int)__ldg(seq + q + j);
                 int       a    = 0;
                 while (a < ns && (int)lib.alphabet[a] != byte) a++;
-                ok = a < ns;
+                if (a >= ns) break;   // a byte outside the alphabet ends every k-mer that would contain it
                 code |= (uint32_t)a << (2 * j);
+                if (j + 1 >= (int)kKmerMin) {
+                    uint32_t* table = bits + kmer_table_word((uint32_t)(j + 1) - kKmerMin);
+                    atomicOr(&table[code >> 5], 1u << (code & 31));
+                }
             }
-            if (ok) atomicOr(&bits[code >> 5], 1u << (code & 31));
         }
     }
     if ((int)query.occ_rows == ns) return;
@@ -1443,7 +1445,7 @@ __global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const De
     }
 }
 
-// k-mer presence filter, one thread per (sequence, unit) item: a component that contains kKmer
+// k-mer presence filter, one thread per (sequence, unit) item: a component that contains 4 to 6
 // consecutive literal symbols cannot match a sequence in which that k-mer never occurs. Items
 // ruled out this way get their count (0) here and one bit in `prefilter`; the count pass skips
 // them before it touches their descriptor. Most search-bound items end here.
@@ -1460,7 +1462,10 @@ __global__ void __launch_bounds__(256) prefilter_kernel(const DevLibrary lib, co
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const uint32_t p = ((i < 2 ? pr.x : pr.y) >> (16 * (i & 1))) & 0xFFFFu;
-                if (p != 0xFFFFu && !((__ldg(bits + (p >> 5)) >> (p & 31)) & 1u)) alive = false;
+                if (p != 0xFFFFu) {
+                    const uint32_t code = p & 0xFFFu;
+                    if (!((__ldg(bits + kmer_table_word(p >> 12) + (code >> 5)) >> (code & 31)) & 1u)) alive = false;
+                }
             }
             if (!alive) counts[item] = 0;
         }
