@@ -1395,54 +1395,57 @@ __global__ void __launch_bounds__(256) band_kernel(const DevQuery query, int32_t
 }
 
 // Occurrence table of every sequence: row a (a < n_symbols) bit q = (seq[q] == alphabet[a]);
-// with `pairs`, row n_symbols + a * n_symbols + b bit q = (seq[q] == alphabet[a] && seq[q+1] == alphabet[b]).
-// Rows are `stride` words long and zero beyond the sequence. One CTA per sequence.
+// with pair rows, row n_symbols + a * n_symbols + b bit q = (seq[q] == alphabet[a] && seq[q+1] == alphabet[b]).
+// Rows are `stride` words long and zero beyond the sequence. With `kmers`, also the presence bits of
+// the sequence's 4-, 5- and 6-mers (zeroed by the caller; gathered in shared memory, then OR-ed in).
+// Grid (sequences, slices): a CTA handles kOccSliceWords words of every row of one sequence.
+constexpr int kOccSliceWords = 16;
+
 __global__ void __launch_bounds__(128) occ_kernel(const DevQuery query, const DevLibrary lib, uint32_t* __restrict__ occ,
                                                   uint32_t* __restrict__ kmers)
 {
+    __shared__ uint8_t  code_of[256];
+    __shared__ uint32_t bits[kKmerWords];
     const uint32_t qi = blockIdx.x;
     const uint64_t sb = query.seq_begin[qi];
     const int      n  = (int)(query.seq_begin[qi + 1] - sb);
     const uint8_t* seq = query.seqs + sb;
-    const int      WP = (int)query.occ_stride, ns = (int)lib.n_symbols;
-    uint32_t*      mine = occ + (size_t)qi * query.occ_rows * WP;
-    const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31, Wn = (n + 31) >> 5;
-    for (int i = threadIdx.x; i < ns * WP; i += 128)
-        if (i % WP >= Wn) mine[i] = 0;
-    for (int w = warp; w < Wn; w += 4) {
-        const int q    = (w << 5) + lane;
-        const int byte = q < n ? (int)__ldg(seq + q) : -1;
-        for (int a = 0; a < ns; a++) {
-            const uint32_t bits = __ballot_sync(0xFFFFFFFFu, byte == (int)lib.alphabet[a]);
-            if (lane == 0) mine[a * WP + w] = bits;
-        }
-    }
-    if (kmers) {   // which 4-, 5- and 6-mers over the (<= 4 symbol) alphabet occur in the sequence
-        uint32_t* bits = kmers + (size_t)qi * kKmerWords;
-        for (int i = threadIdx.x; i < (int)kKmerWords; i += 128) bits[i] = 0;
-        __syncthreads();
-        for (int q = threadIdx.x; q + (int)kKmerMin <= n; q += 128) {
-            uint32_t code = 0;
-            for (int j = 0; j < (int)kKmerMax && q + j < n; j++) {
-                const int byte = (int)__ldg(seq + q + j);
-                int       a    = 0;
-                while (a < ns && (int)lib.alphabet[a] != byte) a++;
-                if (a >= ns) break;   // a byte outside the alphabet ends every k-mer that would contain it
-                code |= (uint32_t)a << (2 * j);
-                if (j + 1 >= (int)kKmerMin) {
-                    uint32_t* table = bits + kmer_table_word((uint32_t)(j + 1) - kKmerMin);
-                    atomicOr(&table[code >> 5], 1u << (code & 31));
-                }
-            }
-        }
-    }
-    if ((int)query.occ_rows == ns) return;
+    const int      WP = (int)query.occ_stride, ns = (int)lib.n_symbols, rows = (int)query.occ_rows;
+    uint32_t*      mine = occ + (size_t)qi * rows * WP;
+    const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int      w_lo = blockIdx.y * kOccSliceWords, w_hi = min(WP, w_lo + kOccSliceWords);
+    for (int i = threadIdx.x; i < 256; i += 128) code_of[i] = 0xFF;
+    for (int i = threadIdx.x; i < (int)kKmerWords; i += 128) bits[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < ns * ns * WP; i += 128) {
-        const int      r = i / WP, w = i % WP, a = r / ns, b = r % ns;
-        const uint32_t lo = mine[b * WP + w], hi = w + 1 < WP ? mine[b * WP + w + 1] : 0u;
-        mine[(ns + r) * WP + w] = mine[a * WP + w] & __funnelshift_r(lo, hi, 1);
+    if ((int)threadIdx.x < ns) code_of[lib.alphabet[threadIdx.x]] = (uint8_t)threadIdx.x;
+    __syncthreads();
+    for (int w = w_lo + warp; w < w_hi; w += 4) {
+        const int q  = (w << 5) + lane;
+        const int c0 = q < n ? (int)code_of[__ldg(seq + q)] : 0xFF, c1 = q + 1 < n ? (int)code_of[__ldg(seq + q + 1)] : 0xFF;
+        for (int a = 0; a < ns; a++) {
+            const uint32_t one = __ballot_sync(0xFFFFFFFFu, c0 == a);
+            if (lane == 0) mine[a * WP + w] = one;
+            if (rows > ns)
+                for (int b = 0; b < ns; b++) {
+                    const uint32_t two = __ballot_sync(0xFFFFFFFFu, c0 == a && c1 == b);
+                    if (lane == 0) mine[(ns + a * ns + b) * WP + w] = two;
+                }
+        }
     }
+    if (!kmers) return;
+    for (int q = (w_lo << 5) + threadIdx.x; q < min(n, w_hi << 5) && q + (int)kKmerMin <= n; q += 128) {
+        uint32_t code = 0;
+        for (int j = 0; j < (int)kKmerMax && q + j < n; j++) {
+            const uint32_t a = code_of[__ldg(seq + q + j)];
+            if (a == 0xFFu) break;   // a byte outside the alphabet ends every k-mer that would contain it
+            code |= a << (2 * j);
+            if (j + 1 >= (int)kKmerMin) atomicOr(&bits[kmer_table_word((uint32_t)(j + 1) - kKmerMin) + (code >> 5)], 1u << (code & 31));
+        }
+    }
+    __syncthreads();
+    uint32_t* out = kmers + (size_t)qi * kKmerWords;
+    for (int i = threadIdx.x; i < (int)kKmerWords; i += 128)
+        if (bits[i]) atomicOr(&out[i], bits[i]);
 }
 
 // k-mer presence filter, one thread per (sequence, unit) item: a component that contains 4 to 6
@@ -1577,7 +1580,12 @@ cudaError_t launch_band(const DevQuery& q, int32_t* band, cudaStream_t s)
 cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, uint32_t* kmers, cudaStream_t s)
 {
     if (q.n_seqs == 0) return cudaSuccess;
-    occ_kernel<<<q.n_seqs, 128, 0, s>>>(q, lib, occ, kmers);
+    if (kmers) {
+        cudaError_t e = cudaMemsetAsync(kmers, 0, sizeof(uint32_t) * (size_t)q.n_seqs * kKmerWords, s);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(q.n_seqs, (q.occ_stride + kOccSliceWords - 1) / kOccSliceWords);
+    occ_kernel<<<grid, 128, 0, s>>>(q, lib, occ, kmers);
     return cudaGetLastError();
 }
 
