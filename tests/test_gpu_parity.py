@@ -378,3 +378,35 @@ def test_rarely_taken_paths_forced_on_small_inputs(knob, value, monkeypatch):
     test_random_tables_long_sequences(2)
     test_random_tables_against_interpreter(4)
     test_full_size_like_small(1)
+
+
+def test_full_size_c3_batch_properties_and_reference_sample(tmp_path):
+    """BASELINE config 3 at full size: 10 000 queries of 120 nt x the 1 000-module JSON library, one batched
+    search. Size-independent properties (offsets, determinism, batch = one-by-one on a sample) and a sample of
+    sequences checked against the reference's own matcher."""
+    n_seqs = 10000
+    seqs = [synth.sequence(120, 3 + i) for i in range(n_seqs)]
+    rng = np.random.default_rng(203)
+    masks = [synth.mask_canonical(s, seed=int(rng.integers(1 << 30)), keep=0.3) for s in seqs]
+    modules = synth.json_modules(1000, 101, "c1")
+    host = b.HostLibrary.from_json_modules(modules)
+    dev = host.to_device()
+    batch = b.HostBatch(seqs, masks)
+    first = dev.search_host(batch)
+    rec, begin = first.records(), first.seq_word_begin()
+    stats = dev.stats()
+    assert stats["placements_tested"] == 120 * n_seqs * 1000 and stats["n_words"] == rec.size == begin[-1]
+    assert begin[0] == 0 and np.all(np.diff(begin.astype(np.int64)) >= 0)
+    again = dev.search_host(batch)
+    assert np.array_equal(rec, again.records()) and np.array_equal(begin, again.seq_word_begin())
+    path = synth.write_json(str(tmp_path / "lib.json"), modules)
+    for i in list(range(0, n_seqs, 997)) + [n_seqs - 1]:
+        one = dev.search(seqs[i], masks[i])
+        mine = rec[begin[i]:begin[i + 1]]
+        assert np.array_equal(one.records(), mine), i
+        one.close()
+        if i % 3 == 0:
+            assert sorted(host.records_text(mine)) == util.best_oracle("jsonfolder", path, seqs[i], masks[i]), i
+    first.close()
+    again.close()
+    dev.close()
