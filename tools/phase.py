@@ -16,10 +16,16 @@ from biorseo_b200 import synth
 import bench
 names = ["fetch+blob", "gate+match", "thin", "lists", "DP", "walk(all)", "dfs", "tail/other", "tables", "walkA", "walkB"]
 for wname in sys.argv[1:]:
-    w = bench.make_workload(wname, 0)
     import tempfile
-    with tempfile.TemporaryDirectory() as tmp:
-        host, _ = bench.host_library(w, tmp)
+    if wname == "desc":   # 5000 .desc modules on the c4 query
+        from biorseo_b200 import synth
+        w = bench.make_workload("c4a", 0)
+        with tempfile.TemporaryDirectory() as tmp:
+            host = b.HostLibrary.load("descfolder", synth.write_desc_folder(os.path.join(tmp, "desc"), 5000, 11))
+    else:
+        w = bench.make_workload(wname, 0)
+        with tempfile.TemporaryDirectory() as tmp:
+            host, _ = bench.host_library(w, tmp)
     dev = host.to_device(0)
     q = dev.query(w["seqs"], w["masks"])
     lib = capi.load()
