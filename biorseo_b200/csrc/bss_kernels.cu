@@ -964,6 +964,7 @@ struct Smem {
     uint32_t* stack;     // [cmax][kThreads]
     uint32_t* idx;       // [2][cmax][kThreads] odometer columns of the rank-space walk
     uint32_t* rank;      // [groups][rank_words] rank-space scratch (32-lane groups only)
+    uint16_t* surv;      // [units_per_chunk] count pass: units of the chunk the k-mer prefilter left standing
 };
 
 // Rank-space scratch of one group, in words: N, PS, staging, then the u16 arrays.
@@ -979,7 +980,7 @@ __host__ __device__ inline uint32_t smem_words(uint32_t cmax, uint32_t W, uint32
 {
     uint32_t words = groups * (kBlobStage + 2 * cmax * (W + WS) + rank_words(cmax, W, cap, emit));
     words += (cap ? 3 : 1) * cmax * kThreads;
-    (void)units_per_chunk;
+    if (!emit && groups > kThreads / 32) words += (units_per_chunk + 1) / 2;   // survivors of the chunk (narrow groups)
     return words;
 }
 
@@ -996,6 +997,7 @@ __device__ __forceinline__ Smem carve(uint32_t* base, const DevLibrary& lib, con
     s.stack = base;               base += lib.cmax * kThreads;
     s.idx   = base;               base += (plan.list_cap ? 2 : 0) * lib.cmax * kThreads;
     s.rank  = base;               base += groups * rank_words(lib.cmax, plan.W, plan.list_cap, EMIT);
+    s.surv  = reinterpret_cast<uint16_t*>(base);
     return s;
 }
 
@@ -1054,7 +1056,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
     static_assert(!HEAVY || G == 32, "heavy items are a 32-lane-group matter");
     using Gr = Group<G>;
     extern __shared__ __align__(16) uint32_t smem_raw[];
-    __shared__ uint32_t next_unit;
+    __shared__ uint32_t next_unit, n_survivors;
     constexpr uint32_t groups = kThreads / G;
     const int          W = (int)plan.W, WS = (int)plan.WS, WP = (int)query.occ_stride;
 
@@ -1068,13 +1070,38 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
 
     // count pass: this CTA's chunk
     const uint32_t chunk = blockIdx.x;
-    uint32_t       u1 = 0;
+    uint32_t       u1 = 0, u0 = 0, n_draw = 0;
+    bool           compact = false;
     SeqCtx         sq{};
     if (MODE == kModeCount) {
-        const uint32_t u0 = (chunk % plan.chunks_per_seq) * plan.units_per_chunk;
+        u0 = (chunk % plan.chunks_per_seq) * plan.units_per_chunk;
         u1                = min(lib.n_units, u0 + plan.units_per_chunk);
         sq                = load_seq(lib, query, chunk / plan.chunks_per_seq);
-        if (threadIdx.x == 0) next_unit = u0;
+        if constexpr (G < 32) {
+            // Narrow groups (batches of short sequences, large chunks): only the units the k-mer prefilter
+            // left standing are drawn. (Kept out of the 32-lane instantiation, which is sensitive to extra code.)
+            n_draw  = u1 - u0;
+            compact = work.prefilter != nullptr;
+            if (compact) {
+                if (threadIdx.x < 32) {
+                    uint32_t n = 0;
+                    for (uint32_t b = u0; b < u1; b += 32) {
+                        const uint32_t v = b + threadIdx.x;
+                        const uint64_t item = sq.item0 + v;
+                        const bool     on = v < u1 && ((__ldg(work.prefilter + (item >> 5)) >> (item & 31)) & 1u);
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, on);
+                        if (on) sm.surv[n + __popc(bal & ((1u << threadIdx.x) - 1u))] = (uint16_t)(v - u0);
+                        n += __popc(bal);
+                    }
+                    if (threadIdx.x == 0) n_survivors = n;
+                }
+                __syncthreads();
+                n_draw = n_survivors;
+            }
+            if (threadIdx.x == 0) next_unit = 0;
+        } else {
+            if (threadIdx.x == 0) next_unit = u0;
+        }
         __syncthreads();
     }
     uint64_t my_sites = 0, my_words = 0;   // accumulated by lane 0 of each group (count pass)
@@ -1134,10 +1161,15 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
         } else if (!EMIT) {
             if (Gr::lane() == 0) u = atomicAdd(&next_unit, 1u);
             u = Gr::first(u);
-            if (u >= u1) break;
-            if (work.prefilter) {   // ruled out by the k-mer presence filter (its count is already written)
-                const uint64_t item = sq.item0 + u;
-                if (!((__ldg(work.prefilter + (item >> 5)) >> (item & 31)) & 1u)) continue;
+            if constexpr (G < 32) {
+                if (u >= n_draw) break;
+                u = u0 + (compact ? (uint32_t)sm.surv[u] : u);
+            } else {
+                if (u >= u1) break;
+                if (work.prefilter) {   // ruled out by the k-mer presence filter (its count is already written)
+                    const uint64_t item = sq.item0 + u;
+                    if (!((__ldg(work.prefilter + (item >> 5)) >> (item & 31)) & 1u)) continue;
+                }
             }
         } else {
             if (slot >= n_alive) break;
