@@ -284,24 +284,30 @@ def main():
         breakdown = [] if os.environ.get("BSS_BENCH_BREAKDOWN") else None   # debug: event after the search of every step
 
         def step():
+            """Queues one whole step on the stream — search (count -> scan -> emit as one CUDA graph) and, for
+            N > 1, the exchange — without waiting for the host anywhere; finish() then checks what it produced."""
             if padded:
-                # search straight into this rank's block, all-gather, cut: nothing waits for the host
+                # search straight into this rank's block, all-gather, cut
                 # (the block was sized from the first search; an overflow would show in the flag checked after the loop)
                 head, rec = gatherer.block()
-                rc, nw, ns = dev.search_query_into(query, rec.data_ptr(), rec.numel(), seq_begin_ptr=head.data_ptr())
-                assert rc == 0 and nw == n_words
+                dev.search_query_into_async(query, rec.data_ptr(), rec.numel(), seq_begin_ptr=head.data_ptr())
                 if breakdown is not None:
                     breakdown.append(torch.cuda.Event(enable_timing=True))
                     breakdown[-1].record(stream)
                 gathered.append(gatherer.exchange_async(dev, stream.cuda_stream))
                 return
-            rc, nw, ns = dev.search_query_into(query, records.data_ptr(), records.numel())
-            assert rc == 0 and nw == n_words
+            dev.search_query_into_async(query, records.data_ptr(), records.numel())
             if world > 1 and with_collective:
-                sharded.allgatherv(records[:nw])
+                sharded.allgatherv(records[:n_words])
+
+        def finish():
+            rc, nw, ns = dev.search_wait()
+            assert rc == 0 and nw == n_words and ns == n_sites
+            return dev.stats()
 
         for _ in range(warmup):
             step()
+            finish()
         sampler = ClockSampler(local_rank)
         sampler.start()
         step_ms, kernel_ms = [], {"count_ms": [], "scan_ms": [], "emit_ms": []}
@@ -317,7 +323,7 @@ def main():
             step()
             e1.record(stream)
             torch.cuda.synchronize()
-            st = dev.stats()                    # per-kernel device times of that search (read outside the timed region)
+            st = finish()                       # sizes checked, per-kernel device times read: outside the timed region
             step_ms.append(e0.elapsed_time(e1))
             if breakdown:
                 sys.stderr.write(f"rank {rank}: search {e0.elapsed_time(breakdown[-1]):.3f} ms, exchange {breakdown[-1].elapsed_time(e1):.3f} ms, "

@@ -358,6 +358,19 @@ class DeviceLibrary:
             _check(rc)
         return rc, nw.value, ns.value
 
+    def search_query_into_async(self, query, device_ptr, capacity_words, seq_begin_ptr=None):
+        """Queues the whole search on the library's stream and returns at once (see search_wait)."""
+        _check(self._lib.bss_search_query_into_async(self._h, query._h, C.c_void_p(device_ptr), capacity_words,
+                                                     C.c_void_p(seq_begin_ptr) if seq_begin_ptr else None))
+
+    def search_wait(self):
+        """Blocks until the last queued search is complete. Returns (rc, n_words, n_sites)."""
+        nw, ns = C.c_uint64(), C.c_uint64()
+        rc = self._lib.bss_search_wait(self._h, C.byref(nw), C.byref(ns))
+        if rc not in (capi.BSS_OK, capi.BSS_ERR_OVERFLOW):
+            _check(rc)
+        return rc, nw.value, ns.value
+
     def search(self, seq, mask):
         """One-shot: host sequence + mask in, host records out."""
         seq = seq.encode() if isinstance(seq, str) else bytes(seq)

@@ -51,6 +51,8 @@ SIGNATURES = {
     "bss_query_create_pij": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.POINTER(C.c_void_p)]),
     "bss_search_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "bss_search_query_into": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, u64p, u64p]),
+    "bss_search_query_into_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "bss_search_wait": (C.c_int, [C.c_void_p, u64p, u64p]),
     "bss_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "bss_search_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, u64p, C.c_void_p, u64p, C.POINTER(C.c_void_p)]),
     "bss_gather_cut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

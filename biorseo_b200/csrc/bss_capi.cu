@@ -126,6 +126,14 @@ struct bss_library {
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof *this) == 0; }
     } graph_key;
     cudaGraphExec_t graph_exec = nullptr;
+    // a search queued by bss_search_query_into_async and not yet waited for
+    struct Pending {
+        bool            active = false, emitting = false, has_records = false;
+        const bss_query* q = nullptr;
+        bss::Plan       plan{};
+        uint64_t        capacity = 0;
+        uint64_t*       seq_out = nullptr;
+    } pending;
     bool            graphs_ok  = true;
     uint64_t        dev_serial = 1;   // bumped when launch parameters held by value change (module base)
     bss_query    oneshot;       // storage of the host-buffer entry points (bss_search, bss_search_batch), reused across calls
@@ -778,11 +786,18 @@ int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites*
 int bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_records, uint64_t capacity_words,
                           uint64_t* d_seq_word_begin, uint64_t* n_words_out, uint64_t* n_sites_out)
 {
-    if (!lib || !q || !n_words_out || !n_sites_out) return fail(BSS_ERR_INVALID, "null argument");
+    if (!n_words_out || !n_sites_out) return fail(BSS_ERR_INVALID, "null argument");
+    const int rc = bss_search_query_into_async(lib, q, d_records, capacity_words, d_seq_word_begin);
+    if (rc != BSS_OK) return rc;
+    return bss_search_wait(lib, n_words_out, n_sites_out);
+}
+
+int bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* d_records, uint64_t capacity_words, uint64_t* d_seq_word_begin)
+{
+    if (!lib || !q) return fail(BSS_ERR_INVALID, "null argument");
     if (q->device != lib->device) return fail(BSS_ERR_INVALID, "query and library live on different devices");
     bss::Plan plan;
     bss::Work work;
-    uint64_t  n_words = 0, n_sites = 0;
     // Everything is queued at once — count, scan, emit — and the host reads the totals only at the
     // end: the emit passes take their sizes from device memory and write nothing when the records
     // would not fit `capacity_words`. While the arguments stay the same (a query stream searched
@@ -838,17 +853,36 @@ int bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_reco
         rc = enqueue(false);
         if (rc != BSS_OK) return rc;
     }
+    lib->pending.active      = true;
+    lib->pending.emitting    = emitting;
+    lib->pending.has_records = d_records != nullptr;
+    lib->pending.q           = q;
+    lib->pending.plan        = plan;
+    lib->pending.capacity    = capacity_words;
+    lib->pending.seq_out     = d_seq_word_begin;
+    return BSS_OK;
+}
+
+int bss_search_wait(bss_library* lib, uint64_t* n_words_out, uint64_t* n_sites_out)
+{
+    if (!lib) return fail(BSS_ERR_INVALID, "null argument");
+    if (!lib->pending.active) return fail(BSS_ERR_INVALID, "no search is pending on this library");
+    lib->pending.active = false;
+    const bss_library::Pending& p  = lib->pending;
+    cudaStream_t                st = lib->stream;
+    uint64_t                    n_words = 0, n_sites = 0;
+    BSS_CUDA(cudaSetDevice(lib->device));
     BSS_CUDA(cudaStreamSynchronize(st));
-    rc           = parse_totals(lib, q, plan, n_words, n_sites);
-    *n_words_out = n_words;
-    *n_sites_out = n_sites;
+    int rc = parse_totals(lib, p.q, p.plan, n_words, n_sites);
+    if (n_words_out) *n_words_out = n_words;
+    if (n_sites_out) *n_sites_out = n_sites;
     if (rc != BSS_OK) return rc;
-    if (n_words > capacity_words || (n_words && !d_records)) return fail(BSS_ERR_OVERFLOW, "output buffer too small");
-    if (d_seq_word_begin && !emitting) {   // nothing was queued for the output: the offsets are all zero
-        BSS_CUDA(cudaMemsetAsync(d_seq_word_begin, 0, 8 * (size_t)(q->dev.n_seqs + 1), st));
+    if (n_words > p.capacity || (n_words && !p.has_records)) return fail(BSS_ERR_OVERFLOW, "output buffer too small");
+    if (p.seq_out && !p.emitting) {   // nothing was queued for the output: the offsets are all zero
+        BSS_CUDA(cudaMemsetAsync(p.seq_out, 0, 8 * (size_t)(p.q->dev.n_seqs + 1), st));
         BSS_CUDA(cudaStreamSynchronize(st));
     }
-    if (plan.n_chunks) lib->stats.kernel_launches += 1 + (plan.group == 32 && plan.list_cap ? 1 : 0);
+    if (p.plan.n_chunks) lib->stats.kernel_launches += 1 + (p.plan.group == 32 && p.plan.list_cap ? 1 : 0);
     return finish_stats(lib);
 }
 

@@ -168,6 +168,15 @@ int  bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites
 int  bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_records, uint64_t capacity_words,
                            uint64_t* d_seq_word_begin, uint64_t* n_words, uint64_t* n_sites);
 
+/* The same in two halves, for callers that keep the device busy (a stream of queries, a sharded
+ * exchange queued right behind the search): _async queues everything on the library's stream and
+ * returns at once; bss_search_wait blocks until the last queued search is complete and reports its
+ * sizes / errors exactly like bss_search_query_into. Queuing several searches before one wait is
+ * allowed (each overwrites the previous one's totals: only the last one is reported). */
+int  bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* d_records, uint64_t capacity_words,
+                                 uint64_t* d_seq_word_begin);
+int  bss_search_wait(bss_library* lib, uint64_t* n_words, uint64_t* n_sites);
+
 /* One-shot, host buffers in, host records out: upload, search, download. */
 int  bss_search(bss_library* lib, const char* seq, uint32_t n, const uint32_t* mask, bss_sites** out);
 int  bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin,
