@@ -85,3 +85,17 @@ def test_table_shapes_and_limits(tmp_path):
     wide = "&".join(["ACGU"] * 17)
     host2 = b.HostLibrary.from_json_modules([("wide", wide, wide.replace("A", "(").replace("U", ")").replace("C", ".").replace("G", "."))])
     assert host2.rejected() == [("wide", "L")]
+
+
+def test_host_batch_packs_the_flat_buffers_of_the_c_abi():
+    """HostBatch = the packed inputs of bss_search_batch: concatenated sequences + offsets, masks + offsets."""
+    import numpy as np
+    seqs = ["ACGUACGUA", "", "GGGAAACCC", "A"]
+    masks = [synth.mask_all(len(s)) for s in seqs]
+    hb = b.HostBatch(seqs, masks)
+    assert hb.n_seqs == 4 and hb.seq_begin.tolist() == [0, 9, 9, 18, 19]
+    assert bytes(hb.seqs[:19]) == "".join(seqs).encode()
+    assert hb.mask_begin.tolist() == [0, 9, 9, 18, 19]          # n * ceil(n/32) words each
+    for i, m in enumerate(masks):
+        assert np.array_equal(hb.masks[int(hb.mask_begin[i]):int(hb.mask_begin[i + 1])], np.asarray(m, dtype=np.uint32).reshape(-1))
+    assert hb.h2d_bytes == 19 + 4 * 19 + 16 * 5
