@@ -1,5 +1,8 @@
 #include "site_search.h"
 
+#include <cstdlib>
+#include <fstream>
+
 namespace bsh {
 
 std::vector<uint32_t> build_pair_mask(size_t n, const std::function<bool(size_t, size_t)>& allowed)
@@ -44,6 +47,62 @@ bool InsertionSiteSearch::run(const std::string& seq, const std::vector<uint32_t
     sites.reserve(sites.size() + bss_sites_count(found));
     for (uint64_t at = 0; at < end; at += library_.record_words(rec[at])) sites.push_back(library_.rebuild(rec + at));
     bss_sites_free(found);
+    return true;
+}
+
+namespace {
+
+// std::stoi as the reference uses it: optional blanks and sign, digits, trailing garbage ignored;
+// anything else throws there (= undefined for us).
+bool stoi_like(const std::string& s, int& out)
+{
+    const char* p   = s.c_str();
+    char*       end = nullptr;
+    const long  v   = std::strtol(p, &end, 10);
+    if (end == p || v < -2147483647L - 1 || v > 2147483647L) return false;
+    out = (int)v;
+    return true;
+}
+
+}   // namespace
+
+bool InsertionSiteSearch::run_csv(const std::string& path, const std::function<bool(size_t, size_t)>& allowed, std::vector<Motif>& sites,
+                                  std::vector<std::string>& skipped, std::string& err)
+{
+    std::ifstream in(path);
+    if (!in) { err = "cannot open " + path; return false; }
+    std::string line;
+    std::getline(in, line);   // header
+    while (std::getline(in, line)) {
+        std::vector<std::string> tokens;   // boost::split(is_any_of(",")): no token compression, n commas -> n + 1 tokens
+        size_t                   at = 0;
+        for (;;) {
+            const size_t comma = line.find(',', at);
+            tokens.push_back(line.substr(at, comma == std::string::npos ? std::string::npos : comma - at));
+            if (comma == std::string::npos) break;
+            at = comma + 1;
+        }
+        int  score = 0;
+        bool ok    = tokens.size() >= 2 && stoi_like(tokens[1], score) && line.find("True") == std::string::npos &&
+                  line.find("False") == std::string::npos;
+        std::vector<Component> comps;
+        for (size_t i = 2; ok && i + 1 < tokens.size(); i += 2) {   // pairs (start, end); kept when start < end (cppsrc/Motif.cpp:36-44)
+            int a = 0, b = 0;
+            ok = stoi_like(tokens[i], a) && stoi_like(tokens[i + 1], b);
+            if (ok && a < b) comps.push_back(Component(std::make_pair(a, b)));
+        }
+        if (!ok || comps.empty()) {
+            skipped.push_back(line);
+            continue;
+        }
+        if (!allowed(comps.front().pos.first, comps.back().pos.second)) continue;
+        bool keep = true;
+        for (size_t j = 0; keep && j + 1 < comps.size(); j++) keep = allowed(comps[j].pos.second, comps[j + 1].pos.first);
+        if (!keep) continue;
+        Motif m(comps, tokens[0], CSV);
+        m.score_ = score;
+        sites.push_back(m);
+    }
     return true;
 }
 

@@ -39,6 +39,15 @@ class InsertionSiteSearch
         return run(seq, build_pair_mask(seq.size(), allowed), sites, err);
     }
 
+    // The `--pre-placed` CSV source (cppsrc/MOIP.cpp:114-145, cppsrc/Motif.cpp:17-47): motifs already
+    // placed by BayesPairing, one per line after a header ("id,score,start,end,start,end,..."); no
+    // search, only the closing-pair filter (first nucleotide of the first component with the last of the
+    // last one, and every component's end with the next one's start). Host-only: needs no GPU.
+    // Lines on which the reference's behaviour is undefined (non-numeric fields, no component: it reads
+    // comp[0] of an empty vector; jar3d lines: it calls stoi("True")) are skipped and reported in `skipped`.
+    static bool run_csv(const std::string& path, const std::function<bool(size_t, size_t)>& allowed, std::vector<Motif>& sites,
+                        std::vector<std::string>& skipped, std::string& err);
+
     const ModuleLibrary& library() const { return library_; }
 
   private:

@@ -39,8 +39,23 @@ int main(int argc, char** argv)
         return a != b && b < n && ((mask[a * W + (b >> 5)] >> (b & 31)) & 1u) != 0;
     };
 
+    std::string err;
+    if (std::string(argv[1]) == "csvfile") {   // pre-placed motifs: host-only filter, no library, no GPU
+        std::vector<Motif>       placed;
+        std::vector<std::string> skipped;
+        if (!bsh::InsertionSiteSearch::run_csv(argv[2], allowed, placed, skipped, err)) {
+            std::cerr << "ERR: " << err << "\n";
+            return 3;
+        }
+        for (const Motif& m : placed) {
+            std::cout << m.get_identifier() << '\t';
+            for (size_t j = 0; j < m.comp.size(); j++) std::cout << (j ? " " : "") << m.comp[j].pos.first << '-' << m.comp[j].pos.second;
+            std::cout << "\t\n";
+        }
+        std::cerr << placed.size() << " pre-placed motifs kept, " << skipped.size() << " lines skipped\n";
+        return 0;
+    }
     bsh::InsertionSiteSearch search;
-    std::string              err;
     if (!search.open(argv[1], argv[2], -1, err)) {
         std::cerr << "ERR: " << err << "\n";
         return 3;

@@ -68,3 +68,50 @@ def test_random_libraries_through_the_cpp_dropin(dropin, source, n, tmp_path):
     res = _run(dropin, source, lib, seq, mask, tmp_path)
     assert res.returncode == 0, res.stderr
     assert sorted(line for line in res.stdout.split("\n") if line) == util.best_oracle(source, lib, seq, mask)
+
+
+def _csv_lines(rng, n, count):
+    lines = ["motif,score,positions"]
+    for i in range(count):
+        comps = int(rng.integers(1, 4))
+        at = int(rng.integers(0, n // 2))
+        fields = []
+        for c in range(comps):
+            k = int(rng.integers(2, 8))
+            fields += [at, at + k - 1] if rng.random() > 0.1 or c == 0 else [at + 3, at]     # start >= end: that component is dropped
+            at += k + int(rng.integers(1, 25))
+        lines.append(f"bp_{i}.{int(rng.integers(1, 99))},{int(rng.integers(-5, 60))}," + ",".join(str(x) for x in fields))
+    return lines
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref is not built")
+@pytest.mark.parametrize("seed,n", [(1, 73), (2, 120), (3, 230)])
+def test_pre_placed_csv_matches_the_reference(dropin, seed, n, tmp_path):
+    """Row "next" #4: the --pre-placed CSV source (cppsrc/MOIP.cpp:114-145). Host-only, so it runs here."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    seq = synth.sequence(n, seed)
+    mask = synth.mask_canonical(seq, seed=seed, keep=0.9)
+    csv = tmp_path / "placed.csv"
+    csv.write_text("\n".join(_csv_lines(rng, n, 400)) + "\n")
+    res = _run(dropin, "csvfile", csv, seq, mask, tmp_path)
+    assert res.returncode == 0, res.stderr
+    mine = sorted(line for line in res.stdout.split("\n") if line)
+    assert len(mine) > 0
+    assert mine == util.run_ref("csvfile", csv, seq, mask, mode="ctor")
+
+
+def test_pre_placed_csv_skips_lines_the_reference_cannot_read(dropin, tmp_path):
+    seq = synth.sequence(60, 4)
+    csv = tmp_path / "bad.csv"
+    csv.write_text("motif,score,positions\n"
+                   "ok,3,2,5,40,44\n"            # kept if the closing pairs are allowed
+                   "jar3d,True,12,2,5,-,-\n"     # the reference calls stoi(\"True\")
+                   "nonnum,x,2,5\n"
+                   "nocomp,3,9,2\n"              # start >= end: no component left, the reference reads comp[0] of an empty vector
+                   "short\n")
+    res = _run(dropin, "csvfile", csv, seq, synth.mask_all(60), tmp_path)
+    assert res.returncode == 0, res.stderr
+    assert [line.split("\t")[0] for line in res.stdout.split("\n") if line] == ["ok"]
+    assert "4 lines skipped" in res.stderr
