@@ -206,7 +206,8 @@ def cpu_search(w, sample_modules, repeat, threads=None):
 
 
 def sample_size(name):
-    return {"c4": 1500, "c4a": 20000, "c4b": 800, "c4b_all": 800, "c3": 1000, "c2": 400, "c1": 1000}[name]
+    # bounded samples: about 1.5 s of Pool-threaded CPU search per pass on a 16-core host
+    return {"c4": 15000, "c4a": 50000, "c4b": 8000, "c4b_all": 800, "c3": 1000, "c2": 400, "c1": 1000}[name]
 
 
 # ----------------------------------------------------------------------------------------
@@ -230,7 +231,7 @@ def main():
         if rank != 0:
             return
         w = make_workload(args.workload, 0)
-        res = cpu_search(w, sample_size(args.workload), repeat=max(1, args.steps))
+        res = cpu_search(w, sample_size(args.workload), repeat=max(1, min(args.steps, 20)))   # about 30 s of CPU search at most
         if res is None:
             print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/biorseo_ref nor oracle/_build/biorseo_port is built"}))
             return
@@ -461,7 +462,7 @@ def main():
             line.setdefault("also", {})["pair_mask_from_pij_16000"] = {"error": str(exc)[:200]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_search(w, sample_size(args.workload), repeat=1)
+        cb = cpu_search(w, sample_size(args.workload), repeat=3)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "sites_per_s")} if cb else None
 
     if rank == 0:
