@@ -683,7 +683,9 @@ int parse_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, ui
     n_sites             = tot[1];
     lib->n_alive        = (uint32_t)tot[3];
     lib->n_heavy        = (uint32_t)std::min<uint64_t>(tot[4], 1024);
-    lib->stats.kernel_launches   = (plan.n_chunks ? 1u : 0u) + 1u + (plan.group == 32 && plan.list_cap && plan.n_chunks ? 1u : 0u);
+    // prefilter (when the library has k-mer probes), count, heavy count (32-lane groups), scan
+    lib->stats.kernel_launches   = (plan.n_chunks ? 1u : 0u) + 1u + (plan.group == 32 && plan.list_cap && plan.n_chunks ? 1u : 0u) +
+                                 (lib->dev.unit_probe && q->dev.kmers && plan.n_chunks ? 1u : 0u);
     lib->stats.placements_tested = q->total_len * lib->n_units;
     lib->stats.n_sites           = n_sites;
     lib->stats.n_words           = n_words;
@@ -757,7 +759,7 @@ int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites*
     s->n_words = n_words;
     s->n_sites = n_sites;
     if (emitted && n_words <= guess_words) {
-        if (plan.n_chunks) lib->stats.kernel_launches += 1 + (plan.group == 32 && plan.list_cap ? 1 : 0);
+        lib->stats.kernel_launches += 1 + (plan.group == 32 && plan.list_cap ? 1 : 0);   // emit, heavy emit (queued blind)
     } else {   // first search of this size: allocate, then emit with the sizes now known on the host
         e = s->d_records.reserve(std::max<uint64_t>(16, n_words * 4));
         if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(records)"));
@@ -882,7 +884,7 @@ int bss_search_wait(bss_library* lib, uint64_t* n_words_out, uint64_t* n_sites_o
         BSS_CUDA(cudaMemsetAsync(p.seq_out, 0, 8 * (size_t)(p.q->dev.n_seqs + 1), st));
         BSS_CUDA(cudaStreamSynchronize(st));
     }
-    if (p.plan.n_chunks) lib->stats.kernel_launches += 1 + (p.plan.group == 32 && p.plan.list_cap ? 1 : 0);
+    if (p.emitting) lib->stats.kernel_launches += 1 + (p.plan.group == 32 && p.plan.list_cap ? 1 : 0) + (p.seq_out ? 1 : 0);   // emit, heavy emit, offsets copy
     return finish_stats(lib);
 }
 
