@@ -103,6 +103,16 @@ def algorithmic_bytes(table, seq_lens, n_words):
     return b_in, 4 * int(n_words)
 
 
+def algorithmic_int_ops(table, seq_lens, n_sites):
+    """SURVEY.md 8(d), integer regime: one funnel shift + one AND per pattern byte per 32-position word of
+    every (query, unit, component) — the shift-AND lower bound of the match phase — plus 2 per placement
+    (chain step + pair test); the emitted sites stand in for the placements (a lower bound of that term)."""
+    n_units = int(table["n_units"])
+    ucb = table["unit_comp_begin"].astype(np.int64)
+    k = np.diff(table["comp_pat_begin"].astype(np.int64))[: int(ucb[n_units])]
+    return int(2 * int(k.sum()) * sum((n + 31) // 32 for n in seq_lens) + 2 * int(n_sites))
+
+
 # ----------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------
@@ -408,6 +418,30 @@ def main():
                 "algorithmic_bytes_per_launch": algo, "kernel_ms": km[name], "peak_source": peak_src,
                 "all_kernels_ms": km}
 
+    int_peak = {"value": None}
+
+    def roofline_int(res):
+        """Second roofline of the search: thread-level shift / logic operations against the rate an SHF + LOP3 only
+        kernel sustains on this GPU (measured here, bss_measure_int_issue). `achieved` counts ALGORITHMIC operations
+        (the shift-AND lower bound), so the fraction says how far the whole pass is from a pure bit-parallel scan;
+        the executed instruction counts are in profiles/ (ncu)."""
+        if int_peak["value"] is None:
+            try:
+                host = b.HostLibrary.from_json_modules(make_workload("c1", 0)["modules"][:8])
+                dev = host.to_device(local_rank)
+                int_peak["value"] = dev.measure_int_issue()
+                dev.close()
+            except Exception:
+                int_peak["value"] = 0.0
+        km = res["kernel_ms"]
+        ops = algorithmic_int_ops(res["table"], res["seq_lens"], res["sites"])
+        t = (km["count_ms"] + km["emit_ms"]) * 1e-3
+        achieved = ops / t / 1e9 if t > 0 else 0.0
+        peak_g = int_peak["value"] / 1e9
+        return {"bound": "int_issue", "kernels": "prefilter + count + emit", "achieved": achieved, "peak": peak_g, "unit": "Gop/s (thread-level SHF/LOP3)",
+                "frac": achieved / peak_g if peak_g else None, "algorithmic_ops_per_step": ops, "kernel_ms": km["count_ms"] + km["emit_ms"],
+                "peak_source": "bss_measure_int_issue: SHF + LOP3 only, 8 independent chains per thread, 8 CTAs x 256 threads per SM, measured in this run"}
+
     line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
@@ -415,7 +449,7 @@ def main():
                        "parallelism": f"library-sharded x{world}, all-gather-v of site records" if world > 1 else "single GPU",
                        "l2": "flushed between steps (256 MiB write, outside the timed events)"},
             "sites_per_s": main_res["sites_per_s"], "sites_per_step_per_gpu": main_res["sites"],
-            "roofline": roofline(main_res), "clocks": main_res["clocks"], "e2e": main_res.get("e2e"),
+            "roofline": roofline(main_res), "roofline_int": roofline_int(main_res) if rank == 0 else None, "clocks": main_res["clocks"], "e2e": main_res.get("e2e"),
             "gpu_launches": main_res["launches"], "wall_s_timed_region": main_res["wall_s"]}
 
     if rank == 0 and world == 1 and not args.no_extra:
@@ -426,7 +460,8 @@ def main():
             try:
                 r = run_workload(name, max(3, args.steps // 4), 3, with_e2e=True)
                 also[name] = {"describe": r["workload"]["describe"], "value": r["value"], "ms_per_step": r["ms_per_step"],
-                              "sites_per_s": r["sites_per_s"], "sites_per_step": r["sites"], "e2e": r.get("e2e"), "roofline": roofline(r)}
+                              "sites_per_s": r["sites_per_s"], "sites_per_step": r["sites"], "e2e": r.get("e2e"), "roofline": roofline(r),
+                              "roofline_int": roofline_int(r)}
             except Exception as exc:   # a secondary workload must never take the headline down
                 also[name] = {"error": str(exc)[:200]}
         line["also"] = also
@@ -460,6 +495,51 @@ def main():
             dev.close()
         except Exception as exc:
             line.setdefault("also", {})["pair_mask_from_pij_16000"] = {"error": str(exc)[:200]}
+
+    if rank == 0 and world == 1 and not args.no_extra:
+        # Insertion-variable index (row "next" #1: cppsrc/MOIP.cpp:302-328 variables, :507-586 c3 / c4 from the site
+        # list), built on the device right behind a search. HBM/L2-bound integer streams: records + pair mask in,
+        # variables table + overlap lists + pair adjacency out. Device time by CUDA events inside the library.
+        def index_bench(name, modules, mask):
+            seq = synth_mod.sequence(2000, 4)
+            host = b.HostLibrary.from_json_modules(modules)
+            dev = host.to_device(local_rank)
+            dev.set_stream(bench_stream.cuda_stream)
+            q = dev.query([seq], [mask])
+            sites = dev.search_query(q, fetch=False)
+            ms, launches, idx = [], 0, None
+            for i in range(6):
+                flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda").fill_(1)
+                del flush
+                idx = dev.site_index(q, sites.device_pointer(), 0, fetch=False)
+                if i >= 2:
+                    ms.append(idx.build_ms)
+                    launches += idx.kernel_launches
+                counts = {sec: idx.count(sec) for sec in b.capi.IDX_SECTIONS}
+                idx.close()
+            n = len(seq)
+            nbytes = 4 * sites.n_words + n * ((n + 31) // 32) * 4 + 4 * sum(counts.values())
+            t = float(np.mean(ms))
+            res = {"describe": name, "sites": sites.n_sites, "variables": counts["var_first"], "overlap_entries": counts["overlap_vars"],
+                   "allowed_pairs": counts["pair_partner"] // 2, "ms": t, "sites_per_s": sites.n_sites / (t * 1e-3), "bound": "hbm",
+                   "algorithmic_bytes": nbytes, "achieved": nbytes / (t * 1e-3) / 1e9, "unit": "GB/s", "peak": peak,
+                   "frac": nbytes / (t * 1e-3) / 1e9 / peak, "gpu_launches": launches,
+                   "note": "device timeline of the whole build, two host round trips for the sizes included"}
+            sites.close()
+            q.close()
+            dev.close()
+            return res
+        try:
+            from biorseo_b200 import synth as synth_mod
+            seq4 = synth_mod.sequence(2000, 4)
+            line["also"]["site_index"] = {
+                "c4": index_bench("index of the c4 sites (2000 nt x 50000 units, banded mask)", make_workload("c4", 0)["modules"],
+                                  synth_mod.mask_canonical(seq4, seed=204, keep=0.3, span=100)),
+                "c4b_all_2000": index_bench("index of 2000 units of c4b with the all-allowed mask (output-heavy)",
+                                            synth_mod.json_modules(2000, 104, "c4b"), synth_mod.mask_all(2000)),
+            }
+        except Exception as exc:
+            line.setdefault("also", {})["site_index"] = {"error": str(exc)[:300]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_search(w, sample_size(args.workload), repeat=3)

@@ -267,6 +267,49 @@ class Sites:
             pass
 
 
+class SiteIndex:
+    """Insertion-variable index of one searched sequence (bss_site_index_build): the C_{x,i,p} variables,
+    the c3 term counts, the per-nucleotide overlap lists (c4) and the pair adjacency, as u32 arrays."""
+
+    def __init__(self, handle):
+        self._lib = capi.load()
+        self._h = handle
+        self.build_ms = float(self._lib.bss_site_index_ms(handle))
+        self.kernel_launches = int(self._lib.bss_site_index_launches(handle))
+
+    def count(self, section):
+        return int(self._lib.bss_site_index_count(self._h, capi.IDX_SECTIONS.index(section)))
+
+    def section(self, section):
+        """Host copy of one section (requires fetch=True at build time)."""
+        i = capi.IDX_SECTIONS.index(section)
+        n = int(self._lib.bss_site_index_count(self._h, i))
+        ptr = self._lib.bss_site_index_host(self._h, i)
+        if not ptr:
+            raise RuntimeError("the index was built without fetch")
+        return np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].copy()
+
+    def sections(self):
+        return {name: self.section(name) for name in capi.IDX_SECTIONS}
+
+    def device_pointer(self, section):
+        return self._lib.bss_site_index_device(self._h, capi.IDX_SECTIONS.index(section))
+
+    def nbytes(self):
+        return 4 * sum(self.count(name) for name in capi.IDX_SECTIONS)
+
+    def close(self):
+        if self._h:
+            self._lib.bss_site_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DeviceLibrary:
     """Flat component table resident on one GPU + the search entry points."""
 
@@ -401,9 +444,26 @@ class DeviceLibrary:
                                           batch.masks.ctypes.data_as(C.c_void_p), batch.mask_begin.ctypes.data_as(capi.u64p), C.byref(h)))
         return Sites(h, batch.n_seqs)
 
+    def site_index(self, query, records_ptr, seq=0, c3_rule=None, fetch=True):
+        """Index of the sites of sequence `seq` of the LAST search on this library (made with `query`;
+        None = the last host-buffer search). records_ptr: device pointer of that search's record stream.
+        c3_rule defaults to the library's source (descfolder: interior nucleotides)."""
+        if c3_rule is None:
+            c3_rule = capi.C3_INTERIOR if (self.host is not None and self.host.kind == capi.KIND_DESC) else capi.C3_COMPONENT_LESS_LINKS
+        h = C.c_void_p()
+        _check(self._lib.bss_site_index_build(self._h, query._h if query is not None else None, int(seq),
+                                              C.c_void_p(records_ptr) if records_ptr else None, int(c3_rule), 1 if fetch else 0, C.byref(h)))
+        return SiteIndex(h)
+
     def gather_cut(self, blocks_ptr, world, block_words, header_words, out_ptr, counts_ptr, overflow_ptr, cuda_stream=None):
         _check(self._lib.bss_gather_cut(self._h, C.c_void_p(blocks_ptr), world, block_words, header_words, C.c_void_p(out_ptr), C.c_void_p(counts_ptr),
                                         C.c_void_p(overflow_ptr), C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def measure_int_issue(self):
+        """Thread-level 32-bit shift / logic operations per second this GPU sustains (SHF + LOP3 probe)."""
+        v = C.c_double()
+        _check(self._lib.bss_measure_int_issue(self._h, C.byref(v)))
+        return v.value
 
     def stats(self):
         s = capi.BssStats()

@@ -13,6 +13,9 @@ BSS_OK = 0
 BSS_ERR_INVALID, BSS_ERR_NO_DEVICE, BSS_ERR_CUDA, BSS_ERR_LIMIT = -1, -2, -3, -4
 BSS_ERR_BAD_SEQUENCE, BSS_ERR_OVERFLOW, BSS_ERR_COUNT = -5, -6, -7
 KIND_JSON, KIND_RIN, KIND_DESC = 0, 1, 2
+C3_COMPONENT_LESS_LINKS, C3_INTERIOR = 0, 1
+IDX_SECTIONS = ("var_begin", "var_first", "var_second", "var_c3_terms", "overlap_begin", "overlap_vars", "pair_begin", "pair_partner",
+                "row_first_pair")
 KIND_OF_SOURCE = {"jsonfolder": KIND_JSON, "rinfolder": KIND_RIN, "descfolder": KIND_DESC}
 
 u32p = C.POINTER(C.c_uint32)
@@ -62,6 +65,14 @@ SIGNATURES = {
     "bss_sites_device_records": (C.c_void_p, [C.c_void_p]),
     "bss_sites_seq_word_begin": (u64p, [C.c_void_p]),
     "bss_sites_free": (None, [C.c_void_p]),
+    "bss_site_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "bss_site_index_count": (C.c_uint64, [C.c_void_p, C.c_int]),
+    "bss_site_index_host": (u32p, [C.c_void_p, C.c_int]),
+    "bss_site_index_device": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "bss_site_index_ms": (C.c_float, [C.c_void_p]),
+    "bss_site_index_launches": (C.c_uint32, [C.c_void_p]),
+    "bss_site_index_free": (None, [C.c_void_p]),
+    "bss_measure_int_issue": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "bss_last_stats": (C.c_int, [C.c_void_p, C.POINTER(BssStats)]),
     "bsh_last_error": (C.c_char_p, []),
     "bsh_library_load": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),

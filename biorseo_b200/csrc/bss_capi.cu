@@ -142,6 +142,9 @@ struct bss_library {
     DeviceBuffer spare_records;
     PinnedBuffer spare_host;
     bss_stats    stats{};
+    // insertion-variable index (bss_site_index_build): scratch, and the query of the last search
+    DeviceBuffer d_idx_work, d_idx_hist;
+    uint64_t     last_query_serial = 0;
 };
 
 struct bss_sites {
@@ -397,6 +400,7 @@ void bss_library_destroy(bss_library* lib)
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
     lib->oneshot.storage.release(); lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_unit_probe.release(); lib->d_prefilter.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_heavy.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
+    lib->d_idx_work.release(); lib->d_idx_hist.release();
     lib->d_chunk_words.release(); lib->d_totals.release(); lib->d_seq_word_begin.release(); lib->h_totals.release();
     lib->spare_records.release(); lib->spare_host.release();
     if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
@@ -652,6 +656,7 @@ int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::W
     work.totals         = static_cast<uint64_t*>(lib->d_totals.ptr);
     work.seq_word_begin = static_cast<uint64_t*>(lib->d_seq_word_begin.ptr);
     lib->stats          = bss_stats{};
+    lib->last_query_serial = q->serial;
     return BSS_OK;
 }
 
@@ -938,6 +943,207 @@ void bss_sites_free(bss_sites* s)
     s->d_records.release();
     s->h_records.release();
     delete s;
+}
+
+}   // extern "C"
+
+struct bss_site_index {
+    bss_library* lib = nullptr;
+    uint32_t     n = 0, launches = 0;
+    float        ms = 0.0f;
+    bool         fetched = false;
+    DeviceBuffer d_main, d_overlap;
+    PinnedBuffer h_main, h_overlap;
+    uint64_t     offset[BSS_IDX_SECTIONS] = {}, count[BSS_IDX_SECTIONS] = {};   // in u32 elements; OVERLAP_VARS lives in its own buffer
+};
+
+extern "C" {
+
+int bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, const uint32_t* d_records, int c3_rule, int fetch,
+                         bss_site_index** out)
+{
+    if (!lib || !out) return fail(BSS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (!q) q = &lib->oneshot;   // the query of the host-buffer entry points (bss_search, bss_search_batch)
+    if (q->device != lib->device) return fail(BSS_ERR_INVALID, "query and library live on different devices");
+    if (seq >= q->dev.n_seqs) return fail(BSS_ERR_INVALID, "sequence index out of range");
+    if (c3_rule != BSS_C3_COMPONENT_LESS_LINKS && c3_rule != BSS_C3_INTERIOR) return fail(BSS_ERR_INVALID, "unknown c3 rule");
+    if (lib->pending.active) return fail(BSS_ERR_INVALID, "a search is pending on this library: call bss_search_wait first");
+    if (lib->last_query_serial != q->serial || !lib->d_counts.ptr || !lib->d_seq_word_begin.ptr)
+        return fail(BSS_ERR_INVALID, "the last search on this library was not made with this query");
+    BSS_CUDA(cudaSetDevice(lib->device));
+    cudaStream_t st = lib->stream;
+
+    // where the sequence, its mask and its records start
+    uint64_t span[2] = {0, 0}, mask_at = 0, word_at = 0;
+    BSS_CUDA(cudaMemcpyAsync(span, q->dev.seq_begin + seq, 16, cudaMemcpyDeviceToHost, st));
+    BSS_CUDA(cudaMemcpyAsync(&mask_at, q->dev.mask_begin + seq, 8, cudaMemcpyDeviceToHost, st));
+    BSS_CUDA(cudaMemcpyAsync(&word_at, static_cast<const uint64_t*>(lib->d_seq_word_begin.ptr) + seq, 8, cudaMemcpyDeviceToHost, st));
+    BSS_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n = (uint32_t)(span[1] - span[0]), NU = lib->n_units;
+    const uint32_t* mask = q->dev.masks + mask_at;
+    if (lib->stats.n_words && !d_records) return fail(BSS_ERR_INVALID, "null record stream");
+
+    // scratch: [unit_site_begin | unit_var_begin | totals] u64, then [row_pairs | degree | row_first_pair | pair_begin | overlap_total] u32
+    const size_t n64 = 2 * (size_t)(NU + 1) + 8, n1 = (size_t)n + 1;
+    BSS_CUDA(lib->d_idx_work.reserve(8 * n64 + 4 * 5 * n1));
+    uint64_t* unit_site_begin = static_cast<uint64_t*>(lib->d_idx_work.ptr);
+    uint64_t* unit_var_begin  = unit_site_begin + NU + 1;
+    uint64_t* totals          = unit_var_begin + NU + 1;
+    uint32_t* row_pairs       = reinterpret_cast<uint32_t*>(totals + 8);
+    uint32_t* degree          = row_pairs + n1;
+    uint32_t* row_first_tmp   = degree + n1;
+    uint32_t* pair_begin_tmp  = row_first_tmp + n1;
+    uint32_t* overlap_total   = pair_begin_tmp + n1;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    BSS_CUDA(cudaEventCreate(&ev0));
+    BSS_CUDA(cudaEventCreate(&ev1));
+    bss_site_index* x = new bss_site_index();
+    x->lib = lib;
+    x->n   = n;
+    auto bail = [&](int code) {
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        bss_site_index_free(x);
+        return code;
+    };
+    uint64_t    tot[8] = {};
+    cudaError_t e      = cudaMemsetAsync(totals, 0, 64, st);
+    if (e == cudaSuccess) e = cudaEventRecord(ev0, st);
+    if (e == cudaSuccess)
+        e = bss::launch_index_scan(lib->dev, static_cast<const uint32_t*>(lib->d_counts.ptr) + (size_t)seq * NU, unit_site_begin, unit_var_begin, mask, n,
+                                   row_pairs, degree, row_first_tmp, pair_begin_tmp, totals, lib->sm_count, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tot, totals, 64, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "index scan"));
+    x->launches += n ? 3 : 2;
+    const uint64_t S = tot[0], V = tot[1], P2 = tot[2];
+    if (S >= 0xFFFFFFFFull || V >= 0xFFFFFFFFull) return bail(fail(BSS_ERR_LIMIT, "more than 2^32 sites or variables in one index"));
+
+    uint64_t at = 0;
+    auto place = [&](int section, uint64_t count) {
+        x->offset[section] = at;
+        x->count[section]  = count;
+        at += count;
+    };
+    place(BSS_IDX_VAR_BEGIN, S + 1);
+    place(BSS_IDX_VAR_FIRST, V);
+    place(BSS_IDX_VAR_SECOND, V);
+    place(BSS_IDX_VAR_C3_TERMS, V);
+    place(BSS_IDX_OVERLAP_BEGIN, n1);
+    place(BSS_IDX_PAIR_BEGIN, n1);
+    place(BSS_IDX_ROW_FIRST_PAIR, n1);
+    place(BSS_IDX_PAIR_PARTNER, P2);
+    e = x->d_main.reserve(4 * at + 16);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(index)"));
+    uint32_t* base = static_cast<uint32_t*>(x->d_main.ptr);
+    auto dev_at = [&](int section) { return base + x->offset[section]; };
+    const uint32_t n_blocks = bss::index_overlap_blocks(V, lib->sm_count);
+    e = lib->d_idx_hist.reserve(4 * (size_t)n_blocks * n + 16);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(index histogram)"));
+    uint32_t* hist = static_cast<uint32_t*>(lib->d_idx_hist.ptr);
+    e = cudaMemcpyAsync(dev_at(BSS_IDX_PAIR_BEGIN), pair_begin_tmp, 4 * n1, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dev_at(BSS_IDX_ROW_FIRST_PAIR), row_first_tmp, 4 * n1, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess)
+        e = bss::launch_index_vars(lib->dev, unit_site_begin, unit_var_begin, d_records ? d_records + word_at : nullptr, (uint32_t)S, (uint32_t)V, mask, n,
+                                   dev_at(BSS_IDX_PAIR_BEGIN), c3_rule, dev_at(BSS_IDX_PAIR_PARTNER), dev_at(BSS_IDX_VAR_BEGIN), dev_at(BSS_IDX_VAR_FIRST),
+                                   dev_at(BSS_IDX_VAR_SECOND), dev_at(BSS_IDX_VAR_C3_TERMS), hist, n_blocks, overlap_total, dev_at(BSS_IDX_OVERLAP_BEGIN),
+                                   totals, lib->sm_count, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tot, totals, 64, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "index variables"));
+    x->launches += n ? 5 : 3;
+    if (tot[4] & 1) return bail(fail(BSS_ERR_INVALID, "the records are not those of the last search on this library"));
+    const uint64_t E = tot[3];
+    if (E >= 0xFFFFFFFFull) return bail(fail(BSS_ERR_LIMIT, "more than 2^32 overlap entries in one index"));
+    x->offset[BSS_IDX_OVERLAP_VARS] = 0;
+    x->count[BSS_IDX_OVERLAP_VARS]  = E;
+    e = x->d_overlap.reserve(4 * E + 16);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(overlap lists)"));
+    if (E) {
+        e = bss::launch_index_fill(dev_at(BSS_IDX_VAR_FIRST), dev_at(BSS_IDX_VAR_SECOND), (uint32_t)V, n, hist, n_blocks, dev_at(BSS_IDX_OVERLAP_BEGIN),
+                                   static_cast<uint32_t*>(x->d_overlap.ptr), st);
+        x->launches++;
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(ev1, st);
+    if (e == cudaSuccess && fetch) {
+        e = x->h_main.reserve(4 * at + 16);
+        if (e == cudaSuccess) e = x->h_overlap.reserve(4 * E + 16);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(x->h_main.ptr, x->d_main.ptr, 4 * at, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && E) e = cudaMemcpyAsync(x->h_overlap.ptr, x->d_overlap.ptr, 4 * E, cudaMemcpyDeviceToHost, st);
+        x->fetched = e == cudaSuccess;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "index overlap lists"));
+    cudaEventElapsedTime(&x->ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    *out = x;
+    return BSS_OK;
+}
+
+uint64_t bss_site_index_count(const bss_site_index* x, int section)
+{
+    return (x && section >= 0 && section < BSS_IDX_SECTIONS) ? x->count[section] : 0;
+}
+
+const uint32_t* bss_site_index_host(const bss_site_index* x, int section)
+{
+    if (!x || !x->fetched || section < 0 || section >= BSS_IDX_SECTIONS) return nullptr;
+    const void* b = section == BSS_IDX_OVERLAP_VARS ? x->h_overlap.ptr : x->h_main.ptr;
+    return static_cast<const uint32_t*>(b) + x->offset[section];
+}
+
+const uint32_t* bss_site_index_device(const bss_site_index* x, int section)
+{
+    if (!x || section < 0 || section >= BSS_IDX_SECTIONS) return nullptr;
+    const void* b = section == BSS_IDX_OVERLAP_VARS ? x->d_overlap.ptr : x->d_main.ptr;
+    return static_cast<const uint32_t*>(b) + x->offset[section];
+}
+
+float    bss_site_index_ms(const bss_site_index* x) { return x ? x->ms : 0.0f; }
+uint32_t bss_site_index_launches(const bss_site_index* x) { return x ? x->launches : 0; }
+
+void bss_site_index_free(bss_site_index* x)
+{
+    if (!x) return;
+    if (x->lib) cudaSetDevice(x->lib->device);
+    x->d_main.release();
+    x->d_overlap.release();
+    x->h_main.release();
+    x->h_overlap.release();
+    delete x;
+}
+
+int bss_measure_int_issue(bss_library* lib, double* thread_ops_per_s)
+{
+    if (!lib || !thread_ops_per_s) return fail(BSS_ERR_INVALID, "null argument");
+    BSS_CUDA(cudaSetDevice(lib->device));
+    BSS_CUDA(lib->d_idx_work.reserve(64));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    BSS_CUDA(cudaEventCreate(&e0));
+    BSS_CUDA(cudaEventCreate(&e1));
+    double   best = 0.0;
+    uint64_t ops  = 0;
+    for (int rep = 0; rep < 4; rep++) {   // the first launch warms the clocks up
+        cudaError_t e = cudaEventRecord(e0, lib->stream);
+        if (e == cudaSuccess) e = bss::launch_int_issue_probe(rep == 0 ? 2000 : 20000, lib->sm_count, static_cast<uint32_t*>(lib->d_idx_work.ptr), &ops, lib->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(e1, lib->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return cuda_fail(e, "integer-issue probe");
+        }
+        if (rep && ms > 0.0f) best = std::max(best, (double)ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *thread_ops_per_s = best;
+    return BSS_OK;
 }
 
 int bss_last_stats(const bss_library* lib, bss_stats* out)

@@ -114,4 +114,21 @@ cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& pl
                         uint32_t n_alive, uint32_t n_heavy, uint64_t capacity_words, int sm_count, cudaStream_t s);
 cudaError_t launch_guarded_copy(const Work& work, uint64_t capacity_words, uint64_t* dst, uint32_t n, cudaStream_t s);
 
+// Integer-issue probe (bss_probe.cu): SHF + LOP3 only, all SMs; *thread_ops = operations issued by the launch.
+cudaError_t launch_int_issue_probe(uint32_t iters, int sm_count, uint32_t* sink, uint64_t* thread_ops, cudaStream_t s);
+
+// Insertion-variable index (bss_index.cu). totals: [0] sites, [1] variables, [2] pair ends (2 x allowed pairs),
+// [3] overlap entries, [4] error flags (bit 0: the records are not those of the last search).
+uint32_t    index_overlap_blocks(uint64_t n_vars, int sm_count);
+cudaError_t launch_index_scan(const DevLibrary& lib, const uint32_t* counts, uint64_t* unit_site_begin, uint64_t* unit_var_begin,
+                              const uint32_t* mask, uint32_t n, uint32_t* row_pairs, uint32_t* degree, uint32_t* row_first_pair,
+                              uint32_t* pair_begin, uint64_t* totals, int sm_count, cudaStream_t s);
+cudaError_t launch_index_vars(const DevLibrary& lib, const uint64_t* unit_site_begin, const uint64_t* unit_var_begin, const uint32_t* records,
+                              uint32_t n_sites, uint32_t n_vars, const uint32_t* mask, uint32_t n, const uint32_t* pair_begin, int c3_rule,
+                              uint32_t* pair_partner, uint32_t* var_begin, uint32_t* var_first, uint32_t* var_second, uint32_t* var_c3,
+                              uint32_t* hist, uint32_t n_blocks, uint32_t* overlap_total, uint32_t* overlap_begin, uint64_t* totals,
+                              int sm_count, cudaStream_t s);
+cudaError_t launch_index_fill(const uint32_t* var_first, const uint32_t* var_second, uint32_t n_vars, uint32_t n, const uint32_t* hist,
+                              uint32_t n_blocks, const uint32_t* overlap_begin, uint32_t* overlap_vars, cudaStream_t s);
+
 }   // namespace bss

@@ -35,7 +35,8 @@ bool InsertionSiteSearch::open(const std::string& source, const std::string& sou
     return true;
 }
 
-bool InsertionSiteSearch::run(const std::string& seq, const std::vector<uint32_t>& pair_mask, std::vector<Motif>& sites, std::string& err)
+bool InsertionSiteSearch::run(const std::string& seq, const std::vector<uint32_t>& pair_mask, std::vector<Motif>& sites, VariableIndex* index,
+                              std::string& err)
 {
     if (!device_library_) { err = "no library open"; return false; }
     const size_t n = seq.size();
@@ -46,6 +47,29 @@ bool InsertionSiteSearch::run(const std::string& seq, const std::vector<uint32_t
     const uint64_t  end = bss_sites_words(found);
     sites.reserve(sites.size() + bss_sites_count(found));
     for (uint64_t at = 0; at < end; at += library_.record_words(rec[at])) sites.push_back(library_.rebuild(rec + at));
+    if (index) {
+        bss_site_index* x    = nullptr;
+        const int       rule = library_.kind() == KIND_DESC ? BSS_C3_INTERIOR : BSS_C3_COMPONENT_LESS_LINKS;
+        if (bss_site_index_build(device_library_, nullptr, 0, bss_sites_device_records(found), rule, 1, &x) != BSS_OK) {
+            err = bss_last_error();
+            bss_sites_free(found);
+            return false;
+        }
+        auto take = [&](int section, std::vector<uint32_t>& out) {
+            const uint32_t* p = bss_site_index_host(x, section);
+            out.assign(p, p + bss_site_index_count(x, section));
+        };
+        take(BSS_IDX_VAR_BEGIN, index->var_begin);
+        take(BSS_IDX_VAR_FIRST, index->var_first);
+        take(BSS_IDX_VAR_SECOND, index->var_second);
+        take(BSS_IDX_VAR_C3_TERMS, index->var_c3_terms);
+        take(BSS_IDX_OVERLAP_BEGIN, index->overlap_begin);
+        take(BSS_IDX_OVERLAP_VARS, index->overlap_vars);
+        take(BSS_IDX_PAIR_BEGIN, index->pair_begin);
+        take(BSS_IDX_PAIR_PARTNER, index->pair_partner);
+        take(BSS_IDX_ROW_FIRST_PAIR, index->row_first_pair);
+        bss_site_index_free(x);
+    }
     bss_sites_free(found);
     return true;
 }

@@ -19,6 +19,17 @@ namespace bsh {
 // predicate is the reference's MOIP::allowed_basepair (cppsrc/MOIP.cpp:896-910).
 std::vector<uint32_t> build_pair_mask(size_t n, const std::function<bool(size_t, size_t)>& allowed);
 
+// What the MOIP constructor derives from insertion_sites_ with host loops (cppsrc/MOIP.cpp:302-328 C_{x,i,p}
+// variables, :507-566 c3, :569-586 c4, :74-90 / :472-487 the pair side), built on the device behind the search
+// (bss_site_index_build, include/biorseo_b200.h). Site x of the returned list owns the variables
+// [var_begin[x], var_begin[x+1]), i.e. index_of_first_components[x] = var_begin[x] and
+// index_of_Cxip_[x][j] = var_begin[x] + j.
+struct VariableIndex {
+    std::vector<uint32_t> var_begin, var_first, var_second, var_c3_terms;   // variables table
+    std::vector<uint32_t> overlap_begin, overlap_vars;                       // per nucleotide: variables covering it (c4)
+    std::vector<uint32_t> pair_begin, pair_partner, row_first_pair;          // per nucleotide: allowed partners; y numbering
+};
+
 class InsertionSiteSearch
 {
   public:
@@ -33,7 +44,12 @@ class InsertionSiteSearch
 
     // Appends every insertion site of the library on `seq` to `sites`, in canonical
     // (module, placement) order. There is no CPU fallback: fails when no GPU is usable.
-    bool run(const std::string& seq, const std::vector<uint32_t>& pair_mask, std::vector<Motif>& sites, std::string& err);
+    bool run(const std::string& seq, const std::vector<uint32_t>& pair_mask, std::vector<Motif>& sites, std::string& err)
+    {
+        return run(seq, pair_mask, sites, nullptr, err);
+    }
+    // The same, also filling the variable index of the sites found (`sites` must come in empty for the site numbers to line up).
+    bool run(const std::string& seq, const std::vector<uint32_t>& pair_mask, std::vector<Motif>& sites, VariableIndex* index, std::string& err);
     bool run(const std::string& seq, const std::function<bool(size_t, size_t)>& allowed, std::vector<Motif>& sites, std::string& err)
     {
         return run(seq, build_pair_mask(seq.size(), allowed), sites, err);

@@ -200,11 +200,57 @@ const uint32_t* bss_sites_device_records(const bss_sites* s);  /* device memory 
 const uint64_t* bss_sites_seq_word_begin(const bss_sites* s);  /* [n_seqs + 1] host            */
 void            bss_sites_free(bss_sites* s);
 
+/* ---- insertion-variable index (row "next" of the path: the consumer of the site list) ---- */
+/* What the MOIP constructor derives from insertion_sites_ with host loops, built on the device from the
+ * records of the LAST search on `lib` (it reads the per-unit site counts that search left behind, so it
+ * must run before the next search; a pending asynchronous search must have been waited for):
+ *   - the C_{x,i,p} variables, numbered like index_of_first_components / index_of_Cxip_
+ *     (cppsrc/MOIP.cpp:302-328): site x owns the variables [VAR_BEGIN[x], VAR_BEGIN[x+1]), one per
+ *     component, with the component's first and last nucleotide (the "[first,second]" of the name);
+ *   - per variable, the number of y_{u,v} terms of its "c3" constraint (cppsrc/MOIP.cpp:507-566; the
+ *     constraint is only added when that number is > 0): c3_rule BSS_C3_COMPONENT_LESS_LINKS for
+ *     jsonfolder / rinfolder (every allowed pair with an end on the component, the site's own links
+ *     left out), BSS_C3_INTERIOR for descfolder (allowed pairs with an end strictly inside it);
+ *   - per nucleotide u, the variables whose component covers u, in variable order: the terms of the
+ *     "c4" overlap constraint (cppsrc/MOIP.cpp:569-586), OVERLAP_VARS[OVERLAP_BEGIN[u] .. OVERLAP_BEGIN[u+1]);
+ *   - the pair side: ROW_FIRST_PAIR[u] = number of allowed pairs (u', v) with u' < u, i.e. the y index of
+ *     the first pair of row u (index_of_yuv_, cppsrc/MOIP.cpp:74-90), and per nucleotide its allowed
+ *     partners in increasing order, PAIR_PARTNER[PAIR_BEGIN[u] .. PAIR_BEGIN[u+1]) — the terms of "c1"
+ *     (cppsrc/MOIP.cpp:472-487) and, restricted to a component, of c3.
+ * q == NULL names the query of the last host-buffer search (bss_search, bss_search_batch).
+ * `seq` selects the sequence of a batch query; d_records is the start of the whole record stream of that
+ * search (bss_sites_device_records, or the caller's buffer of bss_search_query_into). fetch != 0 also
+ * copies every section to pinned host memory. All sections are u32 arrays. */
+#define BSS_C3_COMPONENT_LESS_LINKS 0
+#define BSS_C3_INTERIOR             1
+#define BSS_IDX_VAR_BEGIN       0   /* [sites + 1]                    */
+#define BSS_IDX_VAR_FIRST       1   /* [variables]                    */
+#define BSS_IDX_VAR_SECOND      2   /* [variables]                    */
+#define BSS_IDX_VAR_C3_TERMS    3   /* [variables]                    */
+#define BSS_IDX_OVERLAP_BEGIN   4   /* [n + 1]                        */
+#define BSS_IDX_OVERLAP_VARS    5   /* [sum of component lengths]     */
+#define BSS_IDX_PAIR_BEGIN      6   /* [n + 1]                        */
+#define BSS_IDX_PAIR_PARTNER    7   /* [2 x allowed pairs]            */
+#define BSS_IDX_ROW_FIRST_PAIR  8   /* [n + 1]                        */
+#define BSS_IDX_SECTIONS        9
+typedef struct bss_site_index bss_site_index;
+int  bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, const uint32_t* d_records, int c3_rule, int fetch,
+                          bss_site_index** out);
+uint64_t        bss_site_index_count(const bss_site_index* x, int section);    /* elements of a section            */
+const uint32_t* bss_site_index_host(const bss_site_index* x, int section);     /* pinned host memory, or NULL      */
+const uint32_t* bss_site_index_device(const bss_site_index* x, int section);   /* device memory                    */
+float           bss_site_index_ms(const bss_site_index* x);                    /* device time of the build kernels */
+uint32_t        bss_site_index_launches(const bss_site_index* x);              /* kernels launched by the build    */
+void            bss_site_index_free(bss_site_index* x);
+
 /* ---- diagnostics ---- */
 int         bss_last_stats(const bss_library* lib, bss_stats* out);
 const char* bss_last_error(void);   /* thread-local, never NULL */
 int         bss_abi_version(void);
 int         bss_device_count(void);
+/* Measured integer-issue rate of the device (thread-level 32-bit shift / logic operations per second, all SMs
+ * busy with nothing else, at the clocks the GPU runs at): the denominator of the search's integer roofline. */
+int         bss_measure_int_issue(bss_library* lib, double* thread_ops_per_s);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,11 @@
 //   biorseo_ref ctor  <source> <library> <seqfile> <maskfile>
 //       runs MOIP::MOIP (cppsrc/MOIP.cpp:58) end to end with the stubbed solver and dumps
 //       insertion_sites_.
+//   biorseo_ref model <source> <library> <seqfile> <maskfile>
+//       as `ctor`, with the recording solver shim switched on (oracle/shims/ilconcert/ilomodel.h):
+//       dumps insertion_sites_ in the order the constructor numbered them ("S" lines) and every
+//       constraint of define_problem_constraints (cppsrc/MOIP.cpp:467-694) that involves an
+//       insertion variable C_{x,i,p} ("K <op> <rhs> <coef>*<name> ..." lines, terms of lhs - rhs).
 //   biorseo_ref jobs  <source> <library> <seqfile> <maskfile> [threads]
 //       runs only the search: the per-module jobs MOIP::allowed_motifs_from_{json,rin,desc}
 //       (cppsrc/MOIP.cpp:912-1213) on the reference's Pool, dispatched the way
@@ -207,7 +212,7 @@ int main(int argc, char** argv)
     if (argc >= 5 && string(argv[1]) == "fno") return run_fno(argc, argv);
     if (argc >= 6 && string(argv[1]) == "pairmask") return run_pairmask(argc, argv);
     if (argc < 6) {
-        std::fprintf(stderr, "usage: %s ctor|jobs|bench <source> <library> <seqfile> <maskfile> [threads] [repeat] [max_modules]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s ctor|model|jobs|bench <source> <library> <seqfile> <maskfile> [threads] [repeat] [max_modules]\n", argv[0]);
         return 2;
     }
     const string cmd = argv[1], source = argv[2], lib = argv[3];
@@ -231,6 +236,37 @@ int main(int argc, char** argv)
     if (cmd == "ctor") {
         MOIP moip(rna, source, lib, theta, false);
         dump_sites(moip.insertion_sites_);
+        return 0;
+    }
+    if (cmd == "model") {
+        ilo_shim::recording() = true;
+        MOIP moip(rna, source, lib, theta, false);
+        string out;
+        // "S" lines: the sites in the order of insertion_sites_ (= the x of C_{x,i,p})
+        for (const Motif& m : moip.insertion_sites_) {
+            out += "S\t" + m.get_identifier() + '\t';
+            for (size_t j = 0; j < m.comp.size(); j++)
+                out += (j ? " " : "") + std::to_string(m.comp[j].pos.first) + "-" + std::to_string(m.comp[j].pos.second);
+            out += '\t';
+            for (size_t j = 0; j < m.links_.size(); j++)
+                out += (j ? " " : "") + std::to_string(m.links_[j].nts.first) + "-" + std::to_string(m.links_[j].nts.second);
+            out += '\n';
+        }
+        char buf[64];
+        for (const ilo_shim::Constraint& k : moip.model_.added) {
+            bool has_c = false;
+            for (const auto& t : k.terms) has_c = has_c || ilo_shim::names()[t.second][0] == 'C';
+            if (!has_c) continue;
+            std::snprintf(buf, sizeof buf, "K %c %g", k.op, k.rhs);
+            out += buf;
+            for (const auto& t : k.terms) {
+                std::snprintf(buf, sizeof buf, " %g*", t.first);
+                out += buf;
+                out += ilo_shim::names()[t.second];
+            }
+            out += '\n';
+        }
+        std::fwrite(out.data(), 1, out.size(), stdout);
         return 0;
     }
 

@@ -3,7 +3,11 @@
 // search with an allowed_basepair predicate, walk the resulting vector<Motif> — and dumps the
 // sites in the oracle's text format (identifier \t first-second ... \t a-b ...).
 //
-//   dropin <jsonfolder|rinfolder|descfolder> <library path> <seq.txt> <mask.bin>
+//   dropin <jsonfolder|rinfolder|descfolder> <library path> <seq.txt> <mask.bin> [index]
+//
+// With `index` the sites are followed by the variable index the patched constructor would use instead of its
+// loops over insertion_sites_ (cppsrc/MOIP.cpp:302-328, 507-586): one "V x j first second c3terms" line per
+// C_{x,i,p} variable and one "O u v v ..." line per nucleotide covered by more than one variable (the c4 rows).
 //
 // Exit codes: 0 ok, 3 search failed (e.g. no GPU: there is no CPU fallback), 2 usage / input.
 #include <cstdint>
@@ -18,7 +22,8 @@
 
 int main(int argc, char** argv)
 {
-    if (argc != 5) {
+    const bool with_index = argc == 6 && std::string(argv[5]) == "index";
+    if (argc != 5 && !with_index) {
         std::cerr << "usage: dropin <source> <library> <seq.txt> <mask.bin>\n";
         return 2;
     }
@@ -61,7 +66,8 @@ int main(int argc, char** argv)
         return 3;
     }
     std::vector<Motif> insertion_sites_;
-    if (!search.run(seq, allowed, insertion_sites_, err)) {
+    bsh::VariableIndex index;
+    if (!search.run(seq, bsh::build_pair_mask(n, allowed), insertion_sites_, with_index ? &index : nullptr, err)) {
         std::cerr << "ERR: " << err << "\n";
         return 3;
     }
@@ -71,6 +77,18 @@ int main(int argc, char** argv)
         std::cout << '\t';
         for (size_t j = 0; j < m.links_.size(); j++) std::cout << (j ? " " : "") << m.links_[j].nts.first << '-' << m.links_[j].nts.second;
         std::cout << '\n';
+    }
+    if (with_index) {
+        for (size_t x = 0; x + 1 < index.var_begin.size(); x++)
+            for (uint32_t v = index.var_begin[x]; v < index.var_begin[x + 1]; v++)
+                std::cout << "V " << x << ' ' << v - index.var_begin[x] << ' ' << index.var_first[v] << ' ' << (int)index.var_second[v] << ' '
+                          << index.var_c3_terms[v] << '\n';
+        for (size_t u = 0; u + 1 < index.overlap_begin.size(); u++) {
+            if (index.overlap_begin[u + 1] - index.overlap_begin[u] < 2) continue;
+            std::cout << "O " << u;
+            for (uint32_t i = index.overlap_begin[u]; i < index.overlap_begin[u + 1]; i++) std::cout << ' ' << index.overlap_vars[i];
+            std::cout << '\n';
+        }
     }
     std::cerr << insertion_sites_.size() << " candidate motifs on " << search.library().n_seen() << " (" << search.library().rejected().size()
               << " ignored motifs), Motif::delay = " << Motif::delay << "\n";

@@ -29,9 +29,9 @@ def dropin():
     return BIN
 
 
-def _run(binary, source, library, seq, mask, tmp):
+def _run(binary, source, library, seq, mask, tmp, *extra):
     seq_path, mask_path = util.write_query(str(tmp), seq, mask)
-    return subprocess.run([binary, source, str(library), seq_path, mask_path], capture_output=True, text=True, timeout=300)
+    return subprocess.run([binary, source, str(library), seq_path, mask_path, *extra], capture_output=True, text=True, timeout=300)
 
 
 def test_fails_loudly_without_a_gpu(dropin, tmp_path):
@@ -115,3 +115,29 @@ def test_pre_placed_csv_skips_lines_the_reference_cannot_read(dropin, tmp_path):
     assert res.returncode == 0, res.stderr
     assert [line.split("\t")[0] for line in res.stdout.split("\n") if line] == ["ok"]
     assert "4 lines skipped" in res.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["A2_json", "A4_rin_canonical", "A5_desc", "seed12_rin"])
+def test_variable_index_through_the_cpp_dropin(dropin, name, tmp_path):
+    """bsh::InsertionSiteSearch::run(..., &index): the C_{x,i,p} table and the c4 rows the patched constructor
+    would use (cppsrc/MOIP.cpp:302-328, 569-586) against the plain-Python restatement."""
+    import index_ref
+    case = next(c for c in cases.CASES if c["name"] == name)
+    lib = cases.materialise(case, tmp_path)
+    seq, mask = case["seq"], cases.mask_of(case["mask"], case["seq"])
+    res = _run(dropin, case["source"], lib, seq, mask, tmp_path, "index")
+    assert res.returncode == 0, res.stderr
+    lines = [line for line in res.stdout.split("\n") if line]
+    sites = [line for line in lines if line[:2] not in ("V ", "O ")]
+    want = index_ref.build(sites, len(seq), mask, 1 if case["source"] == "descfolder" else 0)
+    got_v = [tuple(int(x) for x in line.split()[1:]) for line in lines if line.startswith("V ")]
+    exp_v = []
+    for x in range(len(sites)):
+        for v in range(int(want["var_begin"][x]), int(want["var_begin"][x + 1])):
+            exp_v.append((x, v - int(want["var_begin"][x]), int(want["var_first"][v]), int(want["var_second"][v].astype("int32")), int(want["var_c3_terms"][v])))
+    assert got_v == exp_v
+    got_o = [tuple(int(x) for x in line.split()[1:]) for line in lines if line.startswith("O ")]
+    ob, ov = want["overlap_begin"], want["overlap_vars"]
+    exp_o = [(u, *[int(v) for v in ov[int(ob[u]):int(ob[u + 1])]]) for u in range(len(seq)) if int(ob[u + 1]) - int(ob[u]) > 1]
+    assert got_o == exp_o
