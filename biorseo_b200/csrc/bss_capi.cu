@@ -104,6 +104,7 @@ struct bss_query {
     uint8_t       alphabet[32] = {};
     uint64_t      total_len = 0;
     uint64_t      h2d_bytes = 0;
+    std::vector<uint64_t> h_seq_begin, h_mask_begin;   // host copies of the offsets (relative to the first sequence)
 };
 
 struct bss_library {
@@ -143,7 +144,8 @@ struct bss_library {
     PinnedBuffer spare_host;
     bss_stats    stats{};
     // insertion-variable index (bss_site_index_build): scratch, and the query of the last search
-    DeviceBuffer d_idx_work, d_idx_hist;
+    DeviceBuffer d_idx_work, d_idx_hist, spare_idx_main, spare_idx_overlap;   // spares: recycled by bss_site_index_free
+    PinnedBuffer spare_idx_host_main, spare_idx_host_overlap, h_idx_totals;
     uint64_t     last_query_serial = 0;
 };
 
@@ -400,7 +402,8 @@ void bss_library_destroy(bss_library* lib)
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
     lib->oneshot.storage.release(); lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_unit_probe.release(); lib->d_prefilter.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_heavy.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
-    lib->d_idx_work.release(); lib->d_idx_hist.release();
+    lib->d_idx_work.release(); lib->d_idx_hist.release(); lib->spare_idx_main.release(); lib->spare_idx_overlap.release();
+    lib->spare_idx_host_main.release(); lib->spare_idx_host_overlap.release(); lib->h_idx_totals.release();
     lib->d_chunk_words.release(); lib->d_totals.release(); lib->d_seq_word_begin.release(); lib->h_totals.release();
     lib->spare_records.release(); lib->spare_host.release();
     if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
@@ -497,6 +500,8 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     if (e != cudaSuccess) return cuda_fail(e, "query upload");
     q->total_len      = total_len;
     q->h2d_bytes      = 16 * (uint64_t)(n_seqs + 1) + 4 * total_mask + total_len;
+    q->h_seq_begin    = sb;
+    q->h_mask_begin   = mb;
     return BSS_OK;
 }
 
@@ -974,15 +979,13 @@ int bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, con
     BSS_CUDA(cudaSetDevice(lib->device));
     cudaStream_t st = lib->stream;
 
-    // where the sequence, its mask and its records start
-    uint64_t span[2] = {0, 0}, mask_at = 0, word_at = 0;
-    BSS_CUDA(cudaMemcpyAsync(span, q->dev.seq_begin + seq, 16, cudaMemcpyDeviceToHost, st));
-    BSS_CUDA(cudaMemcpyAsync(&mask_at, q->dev.mask_begin + seq, 8, cudaMemcpyDeviceToHost, st));
-    BSS_CUDA(cudaMemcpyAsync(&word_at, static_cast<const uint64_t*>(lib->d_seq_word_begin.ptr) + seq, 8, cudaMemcpyDeviceToHost, st));
-    BSS_CUDA(cudaStreamSynchronize(st));
-    const uint32_t n = (uint32_t)(span[1] - span[0]), NU = lib->n_units;
-    const uint32_t* mask = q->dev.masks + mask_at;
+    // where the sequence and its mask start (host copies of the query's offsets)
+    if (q->h_seq_begin.size() != (size_t)q->dev.n_seqs + 1) return fail(BSS_ERR_INVALID, "query without host offsets");
+    const uint32_t  n = (uint32_t)(q->h_seq_begin[seq + 1] - q->h_seq_begin[seq]), NU = lib->n_units;
+    const uint32_t* mask = q->dev.masks + q->h_mask_begin[seq];
     if (lib->stats.n_words && !d_records) return fail(BSS_ERR_INVALID, "null record stream");
+    BSS_CUDA(lib->h_idx_totals.reserve(128));
+    uint64_t* tot = static_cast<uint64_t*>(lib->h_idx_totals.ptr);   // pinned: [0..7] totals, [8] first record word of the sequence
 
     // scratch: [unit_site_begin | unit_var_begin | totals] u64, then [row_pairs | degree | row_first_pair | pair_begin | overlap_total] u32
     const size_t n64 = 2 * (size_t)(NU + 1) + 8, n1 = (size_t)n + 1;
@@ -1002,21 +1005,26 @@ int bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, con
     bss_site_index* x = new bss_site_index();
     x->lib = lib;
     x->n   = n;
+    std::swap(x->d_main, lib->spare_idx_main);
+    std::swap(x->d_overlap, lib->spare_idx_overlap);
+    std::swap(x->h_main, lib->spare_idx_host_main);
+    std::swap(x->h_overlap, lib->spare_idx_host_overlap);
     auto bail = [&](int code) {
         cudaEventDestroy(ev0);
         cudaEventDestroy(ev1);
         bss_site_index_free(x);
         return code;
     };
-    uint64_t    tot[8] = {};
-    cudaError_t e      = cudaMemsetAsync(totals, 0, 64, st);
+    cudaError_t e = cudaMemsetAsync(totals, 0, 64, st);
     if (e == cudaSuccess) e = cudaEventRecord(ev0, st);
     if (e == cudaSuccess)
         e = bss::launch_index_scan(lib->dev, static_cast<const uint32_t*>(lib->d_counts.ptr) + (size_t)seq * NU, unit_site_begin, unit_var_begin, mask, n,
                                    row_pairs, degree, row_first_tmp, pair_begin_tmp, totals, lib->sm_count, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(tot, totals, 64, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tot + 8, static_cast<const uint64_t*>(lib->d_seq_word_begin.ptr) + seq, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return bail(cuda_fail(e, "index scan"));
+    const uint64_t word_at = tot[8];
     x->launches += n ? 3 : 2;
     const uint64_t S = tot[0], V = tot[1], P2 = tot[2];
     if (S >= 0xFFFFFFFFull || V >= 0xFFFFFFFFull) return bail(fail(BSS_ERR_LIMIT, "more than 2^32 sites or variables in one index"));
@@ -1039,7 +1047,7 @@ int bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, con
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(index)"));
     uint32_t* base = static_cast<uint32_t*>(x->d_main.ptr);
     auto dev_at = [&](int section) { return base + x->offset[section]; };
-    const uint32_t n_blocks = bss::index_overlap_blocks(V, lib->sm_count);
+    const uint32_t n_blocks = bss::index_overlap_blocks(V, n, lib->sm_count);
     e = lib->d_idx_hist.reserve(4 * (size_t)n_blocks * n + 16);
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(index histogram)"));
     uint32_t* hist = static_cast<uint32_t*>(lib->d_idx_hist.ptr);
@@ -1108,7 +1116,14 @@ uint32_t bss_site_index_launches(const bss_site_index* x) { return x ? x->launch
 void bss_site_index_free(bss_site_index* x)
 {
     if (!x) return;
-    if (x->lib) cudaSetDevice(x->lib->device);
+    if (x->lib) {
+        cudaSetDevice(x->lib->device);
+        // keep the largest buffers around for the next build
+        if (x->d_main.cap > x->lib->spare_idx_main.cap) std::swap(x->d_main, x->lib->spare_idx_main);
+        if (x->d_overlap.cap > x->lib->spare_idx_overlap.cap) std::swap(x->d_overlap, x->lib->spare_idx_overlap);
+        if (x->h_main.cap > x->lib->spare_idx_host_main.cap) std::swap(x->h_main, x->lib->spare_idx_host_main);
+        if (x->h_overlap.cap > x->lib->spare_idx_host_overlap.cap) std::swap(x->h_overlap, x->lib->spare_idx_host_overlap);
+    }
     x->d_main.release();
     x->d_overlap.release();
     x->h_main.release();

@@ -119,7 +119,7 @@ cudaError_t launch_int_issue_probe(uint32_t iters, int sm_count, uint32_t* sink,
 
 // Insertion-variable index (bss_index.cu). totals: [0] sites, [1] variables, [2] pair ends (2 x allowed pairs),
 // [3] overlap entries, [4] error flags (bit 0: the records are not those of the last search).
-uint32_t    index_overlap_blocks(uint64_t n_vars, int sm_count);
+uint32_t    index_overlap_blocks(uint64_t n_vars, uint32_t n, int sm_count);
 cudaError_t launch_index_scan(const DevLibrary& lib, const uint32_t* counts, uint64_t* unit_site_begin, uint64_t* unit_var_begin,
                               const uint32_t* mask, uint32_t n, uint32_t* row_pairs, uint32_t* degree, uint32_t* row_first_pair,
                               uint32_t* pair_begin, uint64_t* totals, int sm_count, cudaStream_t s);

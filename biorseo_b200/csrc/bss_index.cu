@@ -21,6 +21,8 @@
 // counts the search left in the library's work buffers: it has to run before the next search.
 #include "bss_device.cuh"
 
+#include <algorithm>
+
 namespace bss {
 namespace {
 
@@ -245,18 +247,25 @@ __global__ void __launch_bounds__(32) idx_overlap_hist_kernel(const uint32_t* __
     }
 }
 
-// Pass 2: per nucleotide, exclusive scan over the CTAs' counts (in place) and the nucleotide's total.
+// Pass 2: per nucleotide, exclusive scan over the CTAs' counts (in place) and the nucleotide's total. One warp per
+// nucleotide, lanes over the CTAs; the 8 warps of a CTA take 8 neighbouring nucleotides, i.e. the same 32-byte sectors.
 __global__ void __launch_bounds__(256) idx_overlap_colscan_kernel(uint32_t* __restrict__ hist, uint32_t n_blocks, uint32_t n, uint32_t* __restrict__ total)
 {
-    const uint32_t u = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, u = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (u >= n) return;
-    uint32_t run = 0;
-    for (uint32_t b = 0; b < n_blocks; b++) {
-        const uint32_t t = hist[(uint64_t)b * n + u];
-        hist[(uint64_t)b * n + u] = run;
-        run += t;
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 32) {
+        const uint32_t b = b0 + lane;
+        const uint32_t t = b < n_blocks ? hist[(uint64_t)b * n + u] : 0u;
+        uint32_t       x = t;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if ((int)lane >= d) x += y;
+        }
+        if (b < n_blocks) hist[(uint64_t)b * n + u] = carry + x - t;
+        carry += __shfl_sync(0xFFFFFFFFu, x, 31);
     }
-    total[u] = run;
+    if (lane == 0) total[u] = carry;
 }
 
 __global__ void __launch_bounds__(kScanThreads) idx_overlap_scan_kernel(const uint32_t* __restrict__ total, uint32_t n, uint32_t* __restrict__ overlap_begin,
@@ -302,10 +311,14 @@ __global__ void __launch_bounds__(32) idx_overlap_fill_kernel(const uint32_t* __
 
 }   // namespace
 
-uint32_t index_overlap_blocks(uint64_t n_vars, int sm_count)
+// One warp per CTA, each walking its slice of the variables in order: enough CTAs to fill the GPU (32 per SM), at
+// least 128 variables each, and a histogram (n_blocks x n words) of at most 128 MB.
+uint32_t index_overlap_blocks(uint64_t n_vars, uint32_t n, int sm_count)
 {
-    const uint64_t want = (n_vars + 255) / 256, cap = (uint64_t)sm_count * 8;
-    return (uint32_t)(want < 1 ? 1 : want > cap ? cap : want);
+    uint64_t want = (n_vars + 127) / 128;
+    want = std::min<uint64_t>(want, (uint64_t)sm_count * 32);
+    want = std::min<uint64_t>(want, (32ull << 20) / std::max<uint32_t>(n, 1u));
+    return (uint32_t)std::max<uint64_t>(want, 1);
 }
 
 cudaError_t launch_index_scan(const DevLibrary& lib, const uint32_t* counts, uint64_t* unit_site_begin, uint64_t* unit_var_begin,
@@ -342,7 +355,7 @@ cudaError_t launch_index_vars(const DevLibrary& lib, const uint64_t* unit_site_b
         if (e != cudaSuccess) return e;
     }
     idx_overlap_hist_kernel<<<n_blocks, 32, smem, s>>>(var_first, var_second, n_vars, per, n, hist);
-    if (n) idx_overlap_colscan_kernel<<<(n + 255) / 256, 256, 0, s>>>(hist, n_blocks, n, overlap_total);
+    if (n) idx_overlap_colscan_kernel<<<(n + 7) / 8, 256, 0, s>>>(hist, n_blocks, n, overlap_total);
     idx_overlap_scan_kernel<<<1, kScanThreads, 0, s>>>(overlap_total, n, overlap_begin, totals);
     return cudaGetLastError();
 }
