@@ -1025,7 +1025,7 @@ int bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, con
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return bail(cuda_fail(e, "index scan"));
     const uint64_t word_at = tot[8];
-    x->launches += n ? 3 : 2;
+    x->launches += n ? 4 : 2;
     const uint64_t S = tot[0], V = tot[1], P2 = tot[2];
     if (S >= 0xFFFFFFFFull || V >= 0xFFFFFFFFull) return bail(fail(BSS_ERR_LIMIT, "more than 2^32 sites or variables in one index"));
 

@@ -75,28 +75,38 @@ __global__ void __launch_bounds__(kScanThreads) idx_unit_scan_kernel(const uint3
     }
 }
 
-// Allowed pairs per row (u < v) and partners per nucleotide, from the pair mask. One thread per word.
-__global__ void __launch_bounds__(256) idx_degree_kernel(const uint32_t* __restrict__ mask, uint32_t n, uint32_t Wm, uint32_t* __restrict__ row_pairs,
-                                                         uint32_t* __restrict__ degree)
+// Allowed pairs per row (u < v), from the pair mask: one warp per row, popcount of the words right of the diagonal.
+// degree[u] starts as the row's count; the column kernel adds the partners below u.
+__global__ void __launch_bounds__(256) idx_row_pairs_kernel(const uint32_t* __restrict__ mask, uint32_t n, uint32_t Wm, uint32_t* __restrict__ row_pairs,
+                                                            uint32_t* __restrict__ degree)
 {
-    const uint32_t words = n * Wm;
-    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < words; i += gridDim.x * 256) {
-        const uint32_t u = i / Wm, w = i - u * Wm;
-        uint32_t       bits = mask[i];
-        // keep v > u and v < n
-        if ((w << 5) + 31 <= u) continue;
-        if ((w << 5) <= u) bits &= (u & 31) == 31 ? 0u : ~0u << ((u & 31) + 1);
-        if (((w + 1) << 5) > n) bits &= (n & 31) ? (1u << (n & 31)) - 1u : ~0u;
-        if (!bits) continue;
-        const uint32_t c = __popc(bits);
-        atomicAdd(row_pairs + u, c);
-        atomicAdd(degree + u, c);
-        while (bits) {
-            const uint32_t b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            atomicAdd(degree + (w << 5) + b, 1u);
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t u = blockIdx.x * 8 + (threadIdx.x >> 5); u < n; u += gridDim.x * 8) {
+        uint32_t c = 0;
+        for (uint32_t w = (u >> 5) + lane; w < Wm; w += 32) {
+            uint32_t bits = mask[(uint64_t)u * Wm + w];
+            if ((w << 5) <= u) bits &= (u & 31) == 31 ? 0u : ~0u << ((u & 31) + 1);      // keep v > u
+            if (((w + 1) << 5) > n) bits &= (n & 31) ? (1u << (n & 31)) - 1u : ~0u;     // and v < n
+            c += __popc(bits);
+        }
+        for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+        if (lane == 0) {
+            row_pairs[u] = c;
+            atomicAdd(degree + u, c);
         }
     }
+}
+
+// Partners below every nucleotide (column v above the diagonal): thread = column, CTA = 256 columns x 64 rows; the 32
+// lanes of a warp read the same word of a row. One atomic per (row chunk, column) instead of one per pair.
+__global__ void __launch_bounds__(256) idx_col_pairs_kernel(const uint32_t* __restrict__ mask, uint32_t n, uint32_t Wm, uint32_t* __restrict__ degree)
+{
+    const uint32_t v = blockIdx.x * 256 + threadIdx.x, u0 = blockIdx.y * 64;
+    if (v >= n) return;
+    const uint32_t u1 = min(min(u0 + 64, n), v);
+    uint32_t       c  = 0;
+    for (uint32_t u = u0; u < u1; u++) c += (mask[(uint64_t)u * Wm + (v >> 5)] >> (v & 31)) & 1u;
+    if (c) atomicAdd(degree + v, c);
 }
 
 __global__ void __launch_bounds__(kScanThreads) idx_pair_scan_kernel(const uint32_t* __restrict__ row_pairs, const uint32_t* __restrict__ degree, uint32_t n,
@@ -254,16 +264,24 @@ __global__ void __launch_bounds__(256) idx_overlap_colscan_kernel(uint32_t* __re
     const uint32_t lane = threadIdx.x & 31, u = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (u >= n) return;
     uint32_t carry = 0;
-    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 32) {
-        const uint32_t b = b0 + lane;
-        const uint32_t t = b < n_blocks ? hist[(uint64_t)b * n + u] : 0u;
-        uint32_t       x = t;
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-            if ((int)lane >= d) x += y;
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 128) {   // four independent loads in flight per lane
+        uint32_t t[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t b = b0 + 32 * i + lane;
+            t[i] = b < n_blocks ? hist[(uint64_t)b * n + u] : 0u;
         }
-        if (b < n_blocks) hist[(uint64_t)b * n + u] = carry + x - t;
-        carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t b = b0 + 32 * i + lane;
+            uint32_t       x = t[i];
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                if ((int)lane >= d) x += y;
+            }
+            if (b < n_blocks) hist[(uint64_t)b * n + u] = carry + x - t[i];
+            carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+        }
     }
     if (lane == 0) total[u] = carry;
 }
@@ -301,10 +319,19 @@ __global__ void __launch_bounds__(32) idx_overlap_fill_kernel(const uint32_t* __
             k = min(k, n - min(f, n));
         }
         const uint32_t cnt = min(32u, v1 - base);
+#pragma unroll 4
         for (uint32_t j = 0; j < cnt; j++) {
             const uint32_t fj = __shfl_sync(0xFFFFFFFFu, f, j), kj = __shfl_sync(0xFFFFFFFFu, k, j);
-            for (uint32_t t = lane; t < kj; t += 32) overlap_vars[cursor[fj + t]++] = base + j;
-            __syncwarp();
+            if (kj <= 32) {   // the usual case: one nucleotide per lane
+                if (lane < kj) {
+                    const uint32_t at = cursor[fj + lane];
+                    cursor[fj + lane] = at + 1;
+                    overlap_vars[at]  = base + j;
+                }
+            } else {
+                for (uint32_t t = lane; t < kj; t += 32) overlap_vars[cursor[fj + t]++] = base + j;
+            }
+            __syncwarp();   // the next variable may cover the same nucleotides from other lanes
         }
     }
 }
@@ -331,8 +358,8 @@ cudaError_t launch_index_scan(const DevLibrary& lib, const uint32_t* counts, uin
     if (e != cudaSuccess) return e;
     idx_unit_scan_kernel<<<1, kScanThreads, 0, s>>>(counts, lib.unit_rlen, lib.n_units, unit_site_begin, unit_var_begin, totals);
     if (n) {
-        const uint32_t words = n * Wm;
-        idx_degree_kernel<<<min((words + 255) / 256, (uint32_t)sm_count * 16), 256, 0, s>>>(mask, n, Wm, row_pairs, degree);
+        idx_row_pairs_kernel<<<min((n + 7) / 8, (uint32_t)sm_count * 8), 256, 0, s>>>(mask, n, Wm, row_pairs, degree);
+        idx_col_pairs_kernel<<<dim3((n + 255) / 256, (n + 63) / 64), 256, 0, s>>>(mask, n, Wm, degree);
     }
     idx_pair_scan_kernel<<<1, kScanThreads, 0, s>>>(row_pairs, degree, n, row_first_pair, pair_begin, totals);
     return cudaGetLastError();
