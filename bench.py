@@ -529,6 +529,20 @@ def main():
             q.close()
             dev.close()
             return res
+        def index_cpu(modules, mask):
+            """The reference's own host loops for the same thing (cppsrc/MOIP.cpp:307-328, 507-586), restated without the
+            solver objects in oracle/port (`index` mode) and timed on one host core on a bounded sample of the library."""
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import util
+            if not util.have_port():
+                return None
+            with tempfile.TemporaryDirectory() as tmp:
+                lib = synth_mod.write_json(os.path.join(tmp, "lib.json"), modules)
+                seq_path, mask_path = util.write_query(tmp, synth_mod.sequence(2000, 4), mask)
+                out = subprocess.run([util.PORT_BIN, "index", "jsonfolder", lib, seq_path, mask_path], capture_output=True, text=True, check=True).stdout
+            r = json.loads(out.strip().splitlines()[-1])
+            return {"kind": "port", "cores": 1, "sites": r["sites"], "seconds": r["seconds"], "sites_per_s": r["sites"] / r["seconds"],
+                    "sample": f"{len(modules)} modules of the same library, host loops only (search excluded)"}
         try:
             from biorseo_b200 import synth as synth_mod
             seq4 = synth_mod.sequence(2000, 4)
@@ -538,6 +552,8 @@ def main():
                 "c4b_all_2000": index_bench("index of 2000 units of c4b with the all-allowed mask (output-heavy)",
                                             synth_mod.json_modules(2000, 104, "c4b"), synth_mod.mask_all(2000)),
             }
+            if not args.no_cpu_baseline:
+                line["also"]["site_index"]["c4b_all_2000"]["cpu_baseline"] = index_cpu(synth_mod.json_modules(2000, 104, "c4b")[:30], synth_mod.mask_all(2000))
         except Exception as exc:
             line.setdefault("also", {})["site_index"] = {"error": str(exc)[:300]}
 

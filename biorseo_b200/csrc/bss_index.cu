@@ -318,32 +318,49 @@ __global__ void __launch_bounds__(32) idx_overlap_fill_kernel(const uint32_t* __
             if (f >= n) k = 0;
             k = min(k, n - min(f, n));
         }
-        const uint32_t cnt = min(32u, v1 - base);
-#pragma unroll 4
-        for (uint32_t j = 0; j < cnt; j++) {
-            const uint32_t fj = __shfl_sync(0xFFFFFFFFu, f, j), kj = __shfl_sync(0xFFFFFFFFu, k, j);
-            if (kj <= 32) {   // the usual case: one nucleotide per lane
-                if (lane < kj) {
-                    const uint32_t at = cursor[fj + lane];
-                    cursor[fj + lane] = at + 1;
-                    overlap_vars[at]  = base + j;
+        const uint32_t cnt = min(32u, v1 - base), kmax = __reduce_max_sync(0xFFFFFFFFu, k);
+        if (kmax == 0) continue;
+        if (kmax <= 32) {
+            // Groups of 4, 8, 16 or 32 lanes (the smallest that holds the longest component of the batch) take one
+            // variable each per step, lanes over its nucleotides. Lanes of different groups that cover the same
+            // nucleotide find each other with a match; their lane order is the variable order, so the rank among
+            // them is the place in the list, and the last of them moves the cursor.
+            const uint32_t lg = kmax <= 4 ? 2u : kmax <= 8 ? 3u : kmax <= 16 ? 4u : 5u;
+            const uint32_t g = lane >> lg, l = lane & ((1u << lg) - 1u), ng = 32u >> lg, lt = (1u << lane) - 1u;
+            for (uint32_t s0 = 0; s0 < cnt; s0 += ng) {
+                const uint32_t src = s0 + g;   // < 32; variables past the end of the slice have k = 0
+                const uint32_t fj = __shfl_sync(0xFFFFFFFFu, f, src), kj = __shfl_sync(0xFFFFFFFFu, k, src);
+                const bool     on = l < kj;
+                const uint32_t u  = on ? fj + l : 0xFFFFFFFFu - lane;
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, u);
+                if (on) {
+                    const uint32_t at = cursor[u] + __popc(peers & lt);
+                    overlap_vars[at]  = base + src;
+                    if ((peers >> lane) == 1u) cursor[u] = at + 1;
                 }
-            } else {
-                for (uint32_t t = lane; t < kj; t += 32) overlap_vars[cursor[fj + t]++] = base + j;
+                __syncwarp();   // the next step may cover the same nucleotides from other lanes
             }
-            __syncwarp();   // the next variable may cover the same nucleotides from other lanes
+        } else {
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint32_t fj = __shfl_sync(0xFFFFFFFFu, f, j), kj = __shfl_sync(0xFFFFFFFFu, k, j);
+                for (uint32_t t = lane; t < kj; t += 32) overlap_vars[cursor[fj + t]++] = base + j;
+                __syncwarp();
+            }
         }
     }
 }
 
 }   // namespace
 
-// One warp per CTA, each walking its slice of the variables in order: enough CTAs to fill the GPU (32 per SM), at
-// least 128 variables each, and a histogram (n_blocks x n words) of at most 128 MB.
+// One warp per CTA, each walking its slice of the variables in order: at most ONE wave of CTAs (as many as are
+// resident at once: 32 per SM, fewer when the per-nucleotide cursors of a long sequence take the shared memory),
+// at least 128 variables each, and a histogram (n_blocks x n words) of at most 128 MB.
 uint32_t index_overlap_blocks(uint64_t n_vars, uint32_t n, int sm_count)
 {
-    uint64_t want = (n_vars + 127) / 128;
-    want = std::min<uint64_t>(want, (uint64_t)sm_count * 32);
+    const uint64_t smem     = 4ull * (n + 1) + 1024;   // dynamic + reserved per CTA
+    const uint64_t resident = std::max<uint64_t>(1, std::min<uint64_t>(32, (227ull << 10) / smem));
+    uint64_t       want     = (n_vars + 127) / 128;
+    want = std::min<uint64_t>(want, (uint64_t)sm_count * resident);
     want = std::min<uint64_t>(want, (32ull << 20) / std::max<uint32_t>(n, 1u));
     return (uint32_t)std::max<uint64_t>(want, 1);
 }

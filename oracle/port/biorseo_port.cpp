@@ -14,6 +14,7 @@
 // line, "identifier \t first-second ... \t a-b ...". Inputs on which the reference's
 // behaviour is undefined make the program exit with status 3.
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -623,7 +624,7 @@ int main(int argc, char** argv)
         return 0;
     }
     if (argc < 6) {
-        std::fprintf(stderr, "usage: %s jobs|ctor <source> <library> <seqfile> <maskfile>\n", argv[0]);
+        std::fprintf(stderr, "usage: %s jobs|ctor|index <source> <library> <seqfile> <maskfile>\n", argv[0]);
         return 2;
     }
     const string source = argv[2], lib = argv[3];
@@ -665,6 +666,60 @@ int main(int argc, char** argv)
                 allowed_motifs_from_desc(q, p, sites);
             }
         }
+    }
+
+    if (string(argv[1]) == "index") {
+        // The loops of the reference that turn insertion_sites_ into variables and constraints, restated without the
+        // solver objects and timed: cppsrc/MOIP.cpp:307-328 (one C_{x,i,p} per component), :507-566 (c3: the y terms of
+        // every variable), :569-586 (c4: per nucleotide, the variables covering it). Prints the sizes (to be compared
+        // with the device-built index) and the seconds the host loops took.
+        const bool desc = source == "descfolder";
+        const auto t0   = std::chrono::steady_clock::now();
+        vector<size_t>         index_of_first_components;
+        vector<vector<size_t>> index_of_Cxip;
+        size_t                 i = 0;
+        for (const Site& m : sites) {
+            index_of_first_components.push_back(i);
+            index_of_Cxip.push_back(vector<size_t>());
+            for (size_t j = 0; j < m.comp.size(); j++) index_of_Cxip.back().push_back(i++);
+        }
+        unsigned long long c3_terms = 0, c3_constraints = 0, c4_entries = 0, c4_constraints = 0, checksum = 0;
+        for (size_t x = 0; x < sites.size(); x++) {
+            const Site& m = sites[x];
+            for (size_t j = 0; j < m.comp.size(); j++) {
+                const Comp& c = m.comp[j];
+                uint count = 0;
+                if (!desc) {
+                    for (uint u = c.first; u <= c.second; u++)
+                        for (uint v = 0; v < q.n; v++)
+                            if (q.allowed_basepair(u, v)) {
+                                bool is_link = false;
+                                for (const Link& l : m.links)
+                                    if ((u == l.a && v == l.b) || (u == l.b && v == l.a)) { is_link = true; break; }
+                                if (!is_link) { count++; checksum += (unsigned long long)u * 31 + v; }
+                            }
+                } else {
+                    for (uint u = c.first + 1; u < c.second; u++)
+                        for (uint v = 0; v < q.n; v++)
+                            if (q.allowed_basepair(u, v)) { count++; checksum += (unsigned long long)u * 31 + v; }
+                }
+                c3_terms += count;
+                if (count > 0) c3_constraints++;
+            }
+        }
+        for (uint u = 0; u < q.n; u++) {
+            uint nterms = 0;
+            for (size_t x = 0; x < sites.size(); x++)
+                for (size_t j = 0; j < sites[x].comp.size(); j++)
+                    if (u >= sites[x].comp[j].first && u <= sites[x].comp[j].second) { nterms++; checksum += index_of_Cxip[x][j]; }
+            c4_entries += nterms;
+            if (nterms > 1) c4_constraints++;
+        }
+        const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("{\"sites\": %zu, \"variables\": %zu, \"c3_terms\": %llu, \"c3_constraints\": %llu, \"c4_entries\": %llu, "
+                    "\"c4_constraints\": %llu, \"checksum\": %llu, \"seconds\": %.6f}\n",
+                    sites.size(), i, c3_terms, c3_constraints, c4_entries, c4_constraints, checksum, seconds);
+        return 0;
     }
 
     string out;

@@ -89,6 +89,31 @@ def test_restatement_equals_committed_fixture(name, tmp_path):
     assert index_ref.constraints_from_index(index, lines, len(seq), mask, rule) == _from_json(entry["constraints"])
 
 
+def run_port_index(source, library, seq, mask):
+    """oracle/port `index` mode: the reference's variable / c3 / c4 loops restated in C++ (sizes + seconds)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        seq_path, mask_path = util.write_query(tmp, seq, mask)
+        res = subprocess.run([util.PORT_BIN, "index", source, str(library), seq_path, mask_path], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.skipif(not util.have_port(), reason="needs oracle/_build/biorseo_port")
+@pytest.mark.parametrize("name", ["A2_json", "A4_rin_canonical", "desc_all_mask", "seed12_rin"])
+def test_port_index_loops_equal_restatement(name, tmp_path):
+    case = next(c for c in cases.CASES if c["name"] == name)
+    lib = cases.materialise(case, tmp_path)
+    seq, mask = case["seq"], cases.mask_of(case["mask"], case["seq"])
+    host = b.HostLibrary.load(case["source"], lib)
+    lines = canonical_sites(host, case["source"], lib, seq, mask)
+    index = index_ref.build(lines, len(seq), mask, RULE[case["source"]])
+    port = run_port_index(case["source"], lib, seq, mask)
+    assert port["sites"] == len(lines) and port["variables"] == index["var_first"].size
+    assert port["c3_terms"] == int(index["var_c3_terms"].sum()) and port["c3_constraints"] == int((index["var_c3_terms"] > 0).sum())
+    assert port["c4_entries"] == index["overlap_vars"].size
+    assert port["c4_constraints"] == int((np.diff(index["overlap_begin"].astype(np.int64)) > 1).sum())
+
+
 # ---------------------------------------------------------------------------------------
 # GPU
 # ---------------------------------------------------------------------------------------
@@ -202,6 +227,40 @@ def test_gpu_index_many_sites_properties():
     sites.close()
     q.close()
     dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not util.have_port(), reason="needs oracle/_build/biorseo_port")
+def test_gpu_index_totals_equal_host_loops(tmp_path):
+    """20 000 sites: the device index against the reference's host loops (restated in oracle/port, `index` mode)."""
+    n = 2000
+    seq, mask = synth.sequence(n, 4), synth.mask_all(n)
+    mods = synth.json_modules(2000, 104, "c4b")[:20]
+    path = synth.write_json(str(tmp_path / "lib.json"), mods)
+    host = b.HostLibrary.load("jsonfolder", path)
+    rec, got = _device_index(host, seq, mask)
+    port = run_port_index("jsonfolder", path, seq, mask)
+    assert port["sites"] == got["var_begin"].size - 1 and port["variables"] == got["var_first"].size
+    assert port["c3_terms"] == int(got["var_c3_terms"].astype(np.int64).sum())
+    assert port["c3_constraints"] == int((got["var_c3_terms"] > 0).sum())
+    assert port["c4_entries"] == got["overlap_vars"].size
+    assert port["c4_constraints"] == int((np.diff(got["overlap_begin"].astype(np.int64)) > 1).sum())
+
+
+@pytest.mark.gpu
+def test_gpu_index_long_and_short_components():
+    """Components longer than a warp (the overlap lists' sequential step) next to short ones (4-, 8-, 16-lane groups)."""
+    n = 150
+    seq = synth.sequence(n, 77)
+    mask = synth.mask_all(n)
+    mods = [("long", seq[5:45], "(" + "." * 38 + ")"), ("long2", seq[20:55] + "&" + seq[70:110], "(" + "." * 34 + "&" + "." * 39 + ")"),
+            ("mid", seq[30:42] + "&" + seq[60:66], "(" + "." * 11 + "&" + "." * 5 + ")")]
+    mods += [(f"s{i}", seq[i:i + 3] + "&" + seq[i + 9:i + 13], "(..&...)") for i in range(0, 120, 7)]
+    host = b.HostLibrary.from_json_modules(sorted(mods))
+    rec, got = _device_index(host, seq, mask)
+    lines = host.records_text(rec)
+    assert any(line.startswith("JSONlong\t") for line in lines) and any(line.startswith("JSONlong2\t") for line in lines)
+    _assert_index_equal(got, index_ref.build(lines, n, mask, 0))
 
 
 @pytest.mark.gpu
