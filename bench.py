@@ -267,6 +267,8 @@ def main():
     bench_stream = torch.cuda.Stream()
     torch.cuda.set_stream(bench_stream)
 
+    exchange_name = {"value": None}
+
     def run_workload(name, steps, warmup, with_e2e=True, with_collective=True):
         w = make_workload(name, rank)
         with tempfile.TemporaryDirectory() as tmp:
@@ -290,6 +292,16 @@ def main():
         # take the exact-size point-to-point all-gather-v instead (no padding, no final cut).
         padded = world > 1 and with_collective and n_words <= (4 << 20)
         gatherer = sharded.PaddedGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=int(1.25 * n_words) + 1024) if padded else None
+        # The exchange of choice: ONE kernel over NVLink peer memory (counts, records and completion flags as peer-to-peer
+        # stores); the padded NCCL all-gather + cut kernel when peer mapping is unavailable (BSS_EXCHANGE=nccl forces it).
+        peer = None
+        if padded and os.environ.get("BSS_EXCHANGE", "p2p") == "p2p":
+            try:
+                peer = sharded.PeerGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=int(1.25 * n_words) + 1024)
+            except RuntimeError as exc:
+                if rank == 0:
+                    sys.stderr.write(f"bench: {exc}; using the NCCL all-gather\n")
+        exchange_name["value"] = "peer-memory kernel (bss_exchange)" if peer is not None else "NCCL all_gather_into_tensor + cut kernel" if padded else "NCCL grouped send/recv"
 
         gathered = []
         breakdown = [] if os.environ.get("BSS_BENCH_BREAKDOWN") else None   # debug: event after the search of every step
@@ -297,6 +309,16 @@ def main():
         def step():
             """Queues one whole step on the stream — search (count -> scan -> emit as one CUDA graph) and, for
             N > 1, the exchange — without waiting for the host anywhere; finish() then checks what it produced."""
+            if peer is not None:
+                head_ptr, rec_ptr, cap = peer.block_pointers()
+                dev.search_query_into_async(query, rec_ptr, cap, seq_begin_ptr=head_ptr)
+                if breakdown is not None:
+                    breakdown.append(torch.cuda.Event(enable_timing=True))
+                    breakdown[-1].record(stream)
+                gathered.append(peer.exchange_async(stream.cuda_stream))
+                if len(gathered) > 2:
+                    gathered.pop(0)     # the output is double-buffered: only the last two are valid
+                return
             if padded:
                 # search straight into this rank's block, all-gather, cut
                 # (the block was sized from the first search; an overflow would show in the flag checked after the loop)
@@ -346,7 +368,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         wall = time.perf_counter() - wall0
-        if gathered:   # the exchanges were complete and consistent: no overflow, every rank's count, canonical order
+        if gathered and peer is not None:   # complete and consistent: no overflow, no timeout, every rank's count, canonical order
+            out, result = gathered[-1]
+            result = result.tolist()
+            assert result[world + 1] == 0, f"exchange flags {result[world + 1]}"
+            counts = result[:world]
+            assert counts[rank] == n_words and result[world] == sum(counts)
+            mine = out[sum(counts[:rank]):sum(counts[:rank + 1])]
+            assert torch.equal(mine, peer.records(n_words))
+            every = [torch.empty(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(every, out[:sum(counts)].to(torch.int64).sum().reshape(1))     # every rank holds the same concatenation
+            assert all(int(e.item()) == int(every[0].item()) for e in every)
+            launches += steps    # one exchange kernel per step
+        elif gathered:   # the exchanges were complete and consistent: no overflow, every rank's count, canonical order
             out, counts, overflow = gathered[-1]
             assert int(overflow.item()) == 0
             counts = counts.tolist()
@@ -389,6 +423,8 @@ def main():
                           "path": "bss_search_batch (C ABI): pinned host sequences + masks in, pinned host records out"}
         query.close()
         dev.close()
+        if peer is not None:
+            peer.close()
         return res
 
     main_res = run_workload(args.workload, args.steps, args.warmup)
@@ -446,7 +482,7 @@ def main():
             "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": args.workload, "describe": w["describe"], "units_per_gpu": int(table["n_units"]),
-                       "parallelism": f"library-sharded x{world}, all-gather-v of site records" if world > 1 else "single GPU",
+                       "parallelism": f"library-sharded x{world}, all-gather-v of site records: {exchange_name['value']}" if world > 1 else "single GPU",
                        "l2": "flushed between steps (256 MiB write, outside the timed events)"},
             "sites_per_s": main_res["sites_per_s"], "sites_per_step_per_gpu": main_res["sites"],
             "roofline": roofline(main_res), "roofline_int": roofline_int(main_res) if rank == 0 else None, "clocks": main_res["clocks"], "e2e": main_res.get("e2e"),

@@ -59,6 +59,13 @@ SIGNATURES = {
     "bss_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "bss_search_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, u64p, C.c_void_p, u64p, C.POINTER(C.c_void_p)]),
     "bss_gather_cut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bss_exchange_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "bss_exchange_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bss_exchange_open": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bss_exchange_block": (C.c_void_p, [C.c_void_p]),
+    "bss_exchange_capacity": (C.c_uint64, [C.c_void_p]),
+    "bss_exchange_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "bss_exchange_destroy": (None, [C.c_void_p]),
     "bss_sites_count": (C.c_uint64, [C.c_void_p]),
     "bss_sites_words": (C.c_uint64, [C.c_void_p]),
     "bss_sites_records": (u32p, [C.c_void_p]),

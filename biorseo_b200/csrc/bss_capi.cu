@@ -94,6 +94,8 @@ bool can_self_overlap(const uint8_t* p, uint32_t k)
 
 }   // namespace
 
+int bss::set_error(int code, const std::string& what) { return fail(code, what); }
+
 struct bss_query {
     uint64_t      serial = 0;   // distinguishes queries that reuse an address (CUDA graph cache key)
     int           device = 0;

@@ -4,7 +4,12 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include <string>
+
 namespace bss {
+
+// Sets the thread-local message behind bss_last_error() and returns `code` (bss_capi.cu).
+int set_error(int code, const std::string& what);
 
 constexpr int      kThreads    = 128;          // threads per CTA (4 warps)
 constexpr uint32_t kWildcard   = 0xFFu;        // pattern symbol code of '.'

@@ -142,3 +142,87 @@ class PaddedGatherer:
             out, counts = self.exchange()
             if out is not None:
                 return out, counts
+
+
+class _DevicePointer:
+    """Wraps raw device memory owned by the library as a __cuda_array_interface__ object (for torch.as_tensor)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerGatherer:
+    """The same exchange as PaddedGatherer.exchange_async, in ONE kernel over NVLink peer memory (bss_exchange_*,
+    biorseo_b200/csrc/bss_exchange.cu): every rank's buffers are mapped into its peers through CUDA IPC once; per
+    step the ranks trade their counts with peer-to-peer stores, copy their records straight into every peer's
+    output at the right displacement and wait for each other's completion flags — no NCCL call, no padding, no cut
+    kernel, no host round trip. torch.distributed only carries the 64-byte IPC handles at set-up.
+
+    Raises RuntimeError (on every rank alike) when peer mapping is not possible on this box (devices hidden from
+    each other, no peer access): callers then fall back to PaddedGatherer."""
+
+    def __init__(self, device, n_seqs=1, capacity_words=1 << 14, group=None):
+        import ctypes as C
+        from . import capi
+        self._lib = capi.load()
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.header_words = 2 * (n_seqs + 1)
+        self.device = torch.device(device)
+        cap = torch.tensor([int(capacity_words)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)       # one geometry on every rank
+        self._h = C.c_void_p()
+        ok = self.world <= 16 and self._lib.bss_exchange_create(self.device.index, self.world, self.rank, int(cap.item()), self.header_words, C.byref(self._h)) == 0
+        handle = torch.zeros(64, dtype=torch.uint8)
+        if ok:
+            buf = (C.c_uint8 * 64)()
+            ok = self._lib.bss_exchange_handle(self._h, buf) == 0
+            handle = torch.tensor(list(buf), dtype=torch.uint8)
+        ok = self._all_ok(ok)
+        if ok:
+            every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, handle.to(self.device), group=group)
+            raw = bytes(every.cpu().tolist())
+            ok = self._all_ok(self._lib.bss_exchange_open(self._h, raw) == 0)
+        if not ok:
+            message = (self._lib.bss_last_error() or b"").decode()
+            self.close()
+            raise RuntimeError(f"peer-memory exchange unavailable: {message}")
+        self.capacity = int(self._lib.bss_exchange_capacity(self._h))
+        self._block = int(self._lib.bss_exchange_block(self._h))
+
+    def _all_ok(self, ok):
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(t.item())
+
+    def block_pointers(self):
+        """(header pointer, records pointer, records capacity in words): what the search fills."""
+        return self._block, self._block + 4 * self.header_words, self.capacity
+
+    def records(self, n_words):
+        """This rank's own records in its block, as a tensor (for checks)."""
+        return torch.as_tensor(_DevicePointer(self._block + 4 * self.header_words, n_words, "<i4"), device=self.device)
+
+    def exchange_async(self, cuda_stream):
+        """Queues the exchange kernel on `cuda_stream` (the stream of the search). Returns (out, result) device
+        tensors: out = the canonical concatenation (world * capacity words of room), result = int64
+        [counts of the ranks..., total words, flags (1 overflow, 2 timeout)]."""
+        import ctypes as C
+        out, res = C.c_void_p(), C.c_void_p()
+        rc = self._lib.bss_exchange_run_async(self._h, C.c_void_p(cuda_stream), C.byref(out), C.byref(res))
+        if rc != 0:
+            raise RuntimeError((self._lib.bss_last_error() or b"").decode())
+        return (torch.as_tensor(_DevicePointer(out.value, self.world * self.capacity, "<i4"), device=self.device),
+                torch.as_tensor(_DevicePointer(res.value, self.world + 2, "<i8"), device=self.device))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bss_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

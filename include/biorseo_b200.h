@@ -192,6 +192,28 @@ int  bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const
 int  bss_gather_cut(bss_library* lib, const uint32_t* d_blocks, uint32_t world, uint64_t block_words, uint32_t header_words,
                     uint32_t* d_out, uint64_t* d_counts, uint32_t* d_overflow, void* cuda_stream);
 
+/* ---- multi-GPU: all-gather-v of the shards' record streams in one kernel over NVLink peer memory ---- */
+/* One process per GPU. Every rank creates an exchange of the same geometry, publishes its 64-byte CUDA IPC handle
+ * to all ranks (any transport: the callers here use a torch.distributed all-gather), and opens the peers' handles.
+ * The search then writes straight into the rank's block — bss_search_query_into(_async) with
+ * d_seq_word_begin = bss_exchange_block() and d_records = bss_exchange_block() + header_words (header_words =
+ * 2 * (n_seqs + 1): the u64 word offsets, whose last entry is the number of record words) — and
+ * bss_exchange_run_async, called by EVERY rank on the stream of its search, exchanges the counts, copies the
+ * rank's records into every peer's output at the rank's displacement (peer-to-peer stores) and returns when all
+ * peers' records have landed: *d_out is then the rank-order concatenation (= canonical (module, placement) order
+ * with bss_library_set_module_base), d_result[0..world) the per-rank word counts, d_result[world] their sum and
+ * d_result[world + 1] flags (1: a rank's stream exceeds capacity_words — nothing was copied; 2: a peer did not
+ * show up within about two seconds). No host round trip; the output is double-buffered (valid until the second
+ * next run). At most 16 ranks. */
+typedef struct bss_exchange bss_exchange;
+int       bss_exchange_create(int device, uint32_t world, uint32_t rank, uint64_t capacity_words, uint32_t header_words, bss_exchange** out);
+int       bss_exchange_handle(const bss_exchange* x, void* handle64);
+int       bss_exchange_open(bss_exchange* x, const void* handles /* world x 64 bytes, in rank order */);
+uint32_t* bss_exchange_block(const bss_exchange* x);      /* device memory: [header_words | capacity_words] */
+uint64_t  bss_exchange_capacity(const bss_exchange* x);   /* record words per rank (rounded up to a multiple of 4) */
+int       bss_exchange_run_async(bss_exchange* x, void* cuda_stream, const uint32_t** d_out, const uint64_t** d_result);
+void      bss_exchange_destroy(bss_exchange* x);
+
 /* ---- results ---- */
 uint64_t        bss_sites_count(const bss_sites* s);
 uint64_t        bss_sites_words(const bss_sites* s);
