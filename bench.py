@@ -343,31 +343,44 @@ def main():
             finish()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        step_ms, kernel_ms = [], {"count_ms": [], "scan_ms": [], "emit_ms": []}
-        launches = 0
+        kernel_ms = {"count_ms": [], "scan_ms": [], "emit_ms": []}
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         wall0 = time.perf_counter()
+        # The K timed steps are queued back to back — flush, event, search (+ exchange), event — and the host waits once,
+        # behind the last one: the device never idles on the host and, for N > 1, the ranks stay in step with each other
+        # through their exchanges instead of drifting apart by host jitter. Each step is timed by its own pair of events
+        # (the flush in between is outside them).
+        events = []
         for _ in range(steps):
             flush.fill_(1)                      # evict the previous step's lines from L2
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             step()
             e1.record(stream)
+            events.append((e0, e1))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        st = finish()                           # sizes of the last search checked (every step runs the same search)
+        step_ms = [a.elapsed_time(z) for a, z in events]
+        launches = steps * st["kernel_launches"]
+        # per-kernel device times (the library's own events belong to the last search queued): a few more steps, one at a time, untimed
+        for _ in range(3):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step()
+            e1.record(stream)
             torch.cuda.synchronize()
-            st = finish()                       # sizes checked, per-kernel device times read: outside the timed region
-            step_ms.append(e0.elapsed_time(e1))
+            st = finish()
             if breakdown:
                 sys.stderr.write(f"rank {rank}: search {e0.elapsed_time(breakdown[-1]):.3f} ms, exchange {breakdown[-1].elapsed_time(e1):.3f} ms, "
                                  f"kernels {st['count_ms'] + st['scan_ms'] + st['emit_ms']:.3f} ms\n")
             for k in kernel_ms:
                 kernel_ms[k].append(st[k])
-            launches += st["kernel_launches"]
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - wall0
         if gathered and peer is not None:   # complete and consistent: no overflow, no timeout, every rank's count, canonical order
             out, result = gathered[-1]
             result = result.tolist()
