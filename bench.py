@@ -341,6 +341,26 @@ def main():
         for _ in range(warmup):
             step()
             finish()
+        if peer is not None:
+            # The peer-memory exchange proves itself on the warm-up steps before it is timed: no flag raised and the very
+            # concatenation NCCL's exact-size all-gather-v gives. Otherwise every rank drops to the NCCL exchange together.
+            out, result = gathered[-1]
+            result = result.tolist()
+            ok = result[world + 1] == 0 and result[rank] == n_words
+            want, counts = sharded.allgatherv(peer.records(n_words).clone())
+            ok = ok and counts == result[:world] and torch.equal(out[:sum(counts)], want)
+            agree = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if not int(agree.item()):
+                if rank == 0:
+                    sys.stderr.write("bench: the peer-memory exchange failed its warm-up check; using the NCCL all-gather\n")
+                peer.close()
+                peer = None
+                exchange_name["value"] = "NCCL all_gather_into_tensor + cut kernel (peer-memory exchange failed its check)"
+                gathered.clear()
+                for _ in range(warmup):
+                    step()
+                    finish()
         sampler = ClockSampler(local_rank)
         sampler.start()
         kernel_ms = {"count_ms": [], "scan_ms": [], "emit_ms": []}

@@ -2,22 +2,22 @@
 // the one exchange step of the library-sharded search).
 //
 // Every rank (one process per GPU) owns one allocation that its peers map through CUDA IPC:
-//   control  counts[2][world] u64 (epoch << 40 | words), done[2][world] u64 (epoch)
+//   control  arrived[2][world] u64 (epoch << 40 | words)
+//   inbox    2 x world x capacity u32: slot [parity][r] receives rank r's records
 //   out      2 x world x capacity u32: the canonical concatenation, double-buffered by epoch parity
 // and a local block [header | records] that bss_search_query_into fills (the header's last u64 is the
-// number of record words). The kernel, launched by every rank right behind its search, needs no host:
-//   1. CTA (p, *) stores this rank's packed count into peer p's counts[parity][rank]          (P2P store)
-//   2. every CTA waits until all counts of this epoch have arrived in the LOCAL control block,
-//      and takes this rank's displacement = sum of the lower ranks' counts                    (local spin)
-//   3. the CTAs of peer p copy this rank's records into peer p's out[parity] at the displacement
-//      (16-byte P2P stores over NVLink / NVSwitch; for p == rank a local copy)
-//   4. the last CTA of peer p fences and stores the epoch into peer p's done[parity][rank]; CTA (p, 0)
-//      waits for peer p's epoch in the local done[parity][p]: when the kernel ends, every peer's
-//      records have landed and out[parity] is the rank-order concatenation = canonical order.
+// number of record words). The kernel, launched by every rank right behind its search, needs no host
+// and ONE trip over the links:
+//   1. the CTAs of peer p copy this rank's records into peer p's inbox[parity][rank] (16-byte peer-to-peer
+//      stores over NVLink / NVSwitch); the last of them fences and stores (epoch, words) into peer p's
+//      arrived[parity][rank]. The rank's own records go straight from the block to its output.
+//   2. every CTA waits until all ranks' (epoch, words) have arrived in the LOCAL control block — the
+//      counts and the completion of the data in one flag — takes the displacements (prefix sums of the
+//      counts) and the CTAs of peer p move inbox[parity][p] to out[parity] + displacement[p] (local).
+// When the kernel ends, out[parity] is the rank-order concatenation = canonical order.
 // Waiting is bounded: a peer that never shows up raises the timeout flag instead of hanging the GPU.
-// Reuse of a parity two epochs later is safe in stream order: a rank enters epoch e + 1 only after its
-// consumers of epoch e's output (queued before it on the same stream), and epoch e + 2 of any peer
-// cannot finish its step 2 before every rank has entered epoch e + 2.
+// Reuse of a parity two epochs later is safe: a rank enters epoch e + 2 only after finishing e + 1, for
+// which it needed every peer's flag of e + 1, which a peer sends only after its kernel of epoch e ended.
 #include "biorseo_b200.h"
 #include "bss_device.cuh"
 
@@ -28,7 +28,7 @@
 namespace {
 
 constexpr int      kCtasPerPeer = 4;
-constexpr uint64_t kSpinLimit   = 1ull << 22;   // x ~0.5 us of back-off: about two seconds
+constexpr uint64_t kSpinLimit   = 1ull << 22;   // tight at first, then x ~0.4 us of back-off: about two seconds
 
 __device__ __forceinline__ uint64_t load_sys(const uint64_t* p)
 {
@@ -48,42 +48,76 @@ struct ExchangeArgs {
     uint32_t        world, rank;
     uint64_t        capacity;       // record words per rank
     uint64_t        epoch;
-    uint64_t*       local_ctrl;     // counts[2][world], done[2][world]
+    uint64_t*       local_ctrl;     // arrived[2][world]
+    uint32_t*       local_inbox;    // [2][world][capacity]
     uint32_t*       local_out;      // [2][world * capacity]
     uint64_t*       peer_ctrl[16];
-    uint32_t*       peer_out[16];
+    uint32_t*       peer_inbox[16];
     uint32_t*       arrivals;       // [world] local: CTAs of a peer that finished their copy
     uint64_t*       result;         // local: [0..world) counts, [world] total words, [world + 1] flags (1 overflow, 2 timeout)
 };
 
+// dst[i] = src[i] for i in [i0, i1), 16 bytes at a time when both sides are 16-byte aligned at i0 (i0 is a multiple of 4)
+__device__ __forceinline__ void copy_words(uint32_t* dst, const uint32_t* src, uint64_t i0, uint64_t i1)
+{
+    if ((((uintptr_t)(dst + i0) | (uintptr_t)(src + i0)) & 15) == 0) {
+        const uint64_t v1 = i0 + ((i1 - i0) & ~3ull);
+        for (uint64_t i = i0 + 4ull * threadIdx.x; i < v1; i += 4ull * 256) *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+        for (uint64_t i = v1 + threadIdx.x; i < i1; i += 256) dst[i] = src[i];
+    } else {
+        for (uint64_t i = i0 + threadIdx.x; i < i1; i += 256) dst[i] = src[i];
+    }
+}
+
 __global__ void __launch_bounds__(256) exchange_kernel(ExchangeArgs a)
 {
     const uint32_t p = blockIdx.x / kCtasPerPeer, c = blockIdx.x % kCtasPerPeer, par = (uint32_t)(a.epoch & 1);
-    const uint64_t tag = a.epoch & 0xFFFFFFull;
+    const uint64_t tag  = a.epoch & 0xFFFFFFull;
     const uint64_t mine = *reinterpret_cast<const uint64_t*>(a.block + a.header_words - 2);
-    __shared__ uint64_t s_disp, s_total;
+    const bool     fits = mine <= a.capacity;
+    // 1. this rank's records into peer p's inbox (nothing when they do not fit: the count alone tells the peers)
+    if (p != a.rank) {
+        if (fits) {
+            const uint64_t per = ((mine + kCtasPerPeer - 1) / kCtasPerPeer + 3) & ~3ull;
+            const uint64_t i0 = min(mine, c * per), i1 = min(mine, i0 + per);
+            copy_words(a.peer_inbox[p] + ((uint64_t)par * a.world + a.rank) * a.capacity, a.block + a.header_words, i0, i1);
+        }
+        __syncthreads();   // the CTA's stores happen before thread 0's fence
+        if (threadIdx.x == 0) {
+            __threadfence_system();   // release: this CTA's peer stores, before its arrival is counted
+            if (atomicAdd(a.arrivals + p, 1u) == kCtasPerPeer - 1) {   // the last CTA of peer p publishes (epoch, words)
+                a.arrivals[p] = 0;
+                __threadfence_system();   // acquire side of the arrival counter, and release of the flag
+                store_sys(a.peer_ctrl[p] + par * a.world + a.rank, (tag << 40) | (mine & 0xFFFFFFFFFFull));
+            }
+        }
+    } else if (threadIdx.x == 0 && c == 0) {
+        store_sys(a.local_ctrl + par * a.world + a.rank, (tag << 40) | (mine & 0xFFFFFFFFFFull));
+    }
+    // 2. all counts (= all data) have arrived: displacements, then inbox -> output
+    __shared__ uint64_t s_disp, s_count;
     __shared__ uint32_t s_flags;
     if (threadIdx.x == 0) {
-        if (c == 0) store_sys(a.peer_ctrl[p] + par * a.world + a.rank, (tag << 40) | (mine & 0xFFFFFFFFFFull));
-        uint64_t disp = 0, total = 0;
+        uint64_t disp = 0, total = 0, count = 0;
         uint32_t flags = 0;
         for (uint32_t r = 0; r < a.world; r++) {
             const uint64_t* slot = a.local_ctrl + par * a.world + r;
             uint64_t        v    = load_sys(slot), spins = 0;
             while ((v >> 40) != tag && spins < kSpinLimit) {
-                __nanosleep(200);
+                if (spins > 4096) __nanosleep(200);
                 v = load_sys(slot);
                 spins++;
             }
             if ((v >> 40) != tag) flags |= 2u;
             const uint64_t n = v & 0xFFFFFFFFFFull;
             if (n > a.capacity) flags |= 1u;
-            if (r < a.rank) disp += n;
+            if (r < p) disp += n;
+            if (r == p) count = n;
             total += n;
             if (blockIdx.x == 0) a.result[r] = n;
         }
         s_disp  = disp;
-        s_total = total;
+        s_count = count;
         s_flags = flags;
         if (blockIdx.x == 0) {
             a.result[a.world]     = total;
@@ -92,37 +126,16 @@ __global__ void __launch_bounds__(256) exchange_kernel(ExchangeArgs a)
     }
     __syncthreads();
     if (s_flags == 0) {
-        // this CTA's slice of the records, in 16-byte pieces where the alignment allows (source and destination)
-        const uint32_t* src = a.block + a.header_words;
-        uint32_t*       dst = a.peer_out[p] + (uint64_t)par * a.world * a.capacity + s_disp;
-        const uint64_t  per = ((mine + kCtasPerPeer - 1) / kCtasPerPeer + 3) & ~3ull;
-        const uint64_t  i0 = min(mine, c * per), i1 = min(mine, i0 + per);
-        if (((s_disp | (uint64_t)(a.header_words)) & 3ull) == 0) {
-            const uint64_t v1 = i0 + ((i1 - i0) & ~3ull);
-            for (uint64_t i = i0 + 4ull * threadIdx.x; i < v1; i += 4ull * 256)
-                *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
-            for (uint64_t i = v1 + threadIdx.x; i < i1; i += 256) dst[i] = src[i];
+        const uint64_t  n   = s_count;
+        const uint64_t  per = ((n + kCtasPerPeer - 1) / kCtasPerPeer + 3) & ~3ull;
+        const uint64_t  i0 = min(n, c * per), i1 = min(n, i0 + per);
+        const uint32_t* src = p == a.rank ? a.block + a.header_words : a.local_inbox + ((uint64_t)par * a.world + p) * a.capacity;
+        uint32_t*       dst = a.local_out + (uint64_t)par * a.world * a.capacity + s_disp;
+        if (p == a.rank) {
+            copy_words(dst, src, i0, i1);
         } else {
-            for (uint64_t i = i0 + threadIdx.x; i < i1; i += 256) dst[i] = src[i];
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // the last of this peer's CTAs tells the peer that this rank's records are in place
-        if (atomicAdd(a.arrivals + p, 1u) == kCtasPerPeer - 1) {
-            a.arrivals[p] = 0;
-            __threadfence_system();
-            store_sys(a.peer_ctrl[p] + (2 + par) * a.world + a.rank, a.epoch);
-        }
-        if (c == 0) {   // and this rank waits for peer p's records
-            const uint64_t* slot = a.local_ctrl + (2 + par) * a.world + p;
-            uint64_t        spins = 0;
-            while (load_sys(slot) != a.epoch && spins < kSpinLimit) {
-                __nanosleep(200);
-                spins++;
-            }
-            if (load_sys(slot) != a.epoch) atomicOr((unsigned long long*)(a.result + a.world + 1), 2ull);
+            // peer-written memory: read it past L1
+            for (uint64_t i = i0 + threadIdx.x; i < i1; i += 256) dst[i] = __ldcg(src + i);
         }
     }
 }
@@ -133,8 +146,9 @@ struct bss_exchange {
     int          device = 0;
     uint32_t     world = 0, rank = 0, header_words = 0;
     uint64_t     capacity = 0, epoch = 0;
-    void*        shared = nullptr;   // control + out, mapped by the peers
+    void*        shared = nullptr;   // control + inbox, mapped by the peers
     size_t       shared_bytes = 0, ctrl_bytes = 0;
+    uint32_t*    outbuf = nullptr;   // local [2][world * capacity]
     uint32_t*    block = nullptr;    // local [header | records]
     uint32_t*    arrivals = nullptr;
     uint64_t*    result = nullptr;
@@ -155,10 +169,11 @@ int bss_exchange_create(int device, uint32_t world, uint32_t rank, uint64_t capa
     bss_exchange* x = new bss_exchange();
     x->device = device; x->world = world; x->rank = rank; x->header_words = header_words;
     x->capacity     = (capacity_words + 3) & ~3ull;
-    x->ctrl_bytes   = (4 * (size_t)world * 8 + 255) & ~(size_t)255;
+    x->ctrl_bytes   = (2 * (size_t)world * 8 + 255) & ~(size_t)255;
     x->shared_bytes = x->ctrl_bytes + 2 * (size_t)world * x->capacity * 4;
     e = cudaMalloc(&x->shared, x->shared_bytes);
     if (e == cudaSuccess) e = cudaMemset(x->shared, 0, x->ctrl_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->outbuf), 2 * (size_t)world * x->capacity * 4);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->block), ((size_t)header_words + x->capacity) * 4);
     if (e == cudaSuccess) e = cudaMemset(x->block, 0, (size_t)header_words * 4);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->arrivals), 4 * (size_t)world);
@@ -222,11 +237,12 @@ int bss_exchange_run_async(bss_exchange* x, void* cuda_stream, const uint32_t** 
     x->epoch++;
     ExchangeArgs a{};
     a.block = x->block; a.header_words = x->header_words; a.world = x->world; a.rank = x->rank; a.capacity = x->capacity; a.epoch = x->epoch;
-    a.local_ctrl = static_cast<uint64_t*>(x->shared);
-    a.local_out  = reinterpret_cast<uint32_t*>(static_cast<char*>(x->shared) + x->ctrl_bytes);
+    a.local_ctrl  = static_cast<uint64_t*>(x->shared);
+    a.local_inbox = reinterpret_cast<uint32_t*>(static_cast<char*>(x->shared) + x->ctrl_bytes);
+    a.local_out   = x->outbuf;
     for (uint32_t r = 0; r < x->world; r++) {
-        a.peer_ctrl[r] = static_cast<uint64_t*>(x->peer_base[r]);
-        a.peer_out[r]  = reinterpret_cast<uint32_t*>(static_cast<char*>(x->peer_base[r]) + x->ctrl_bytes);
+        a.peer_ctrl[r]  = static_cast<uint64_t*>(x->peer_base[r]);
+        a.peer_inbox[r] = reinterpret_cast<uint32_t*>(static_cast<char*>(x->peer_base[r]) + x->ctrl_bytes);
     }
     a.arrivals = x->arrivals;
     a.result   = x->result;
@@ -246,6 +262,7 @@ void bss_exchange_destroy(bss_exchange* x)
     for (uint32_t r = 0; r < x->world; r++)
         if (x->opened && r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
     if (x->shared) cudaFree(x->shared);
+    if (x->outbuf) cudaFree(x->outbuf);
     if (x->block) cudaFree(x->block);
     if (x->arrivals) cudaFree(x->arrivals);
     if (x->result) cudaFree(x->result);
