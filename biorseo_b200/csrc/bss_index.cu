@@ -133,19 +133,31 @@ __global__ void __launch_bounds__(256) idx_adjacency_kernel(const uint32_t* __re
     for (uint32_t u = blockIdx.x * 8 + warp; u < n; u += gridDim.x * 8) {
         uint32_t* out = partner + pair_begin[u];
         uint32_t  pos = 0;
-        for (uint32_t v0 = 0; v0 < u; v0 += 32) {
-            const uint32_t v   = v0 + lane;
-            const bool     on  = v < u && ((mask[(uint64_t)v * Wm + (u >> 5)] >> (u & 31)) & 1u);
-            const uint32_t all = __ballot_sync(0xFFFFFFFFu, on);
-            if (on) out[pos + __popc(all & lt)] = v;
-            pos += __popc(all);
+        for (uint32_t v0 = 0; v0 < u; v0 += 128) {   // column u above the diagonal: four independent loads per lane, then four ballots
+            bool on[4];
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                const uint32_t v = v0 + 32 * i + lane;
+                on[i] = v < u && ((mask[(uint64_t)v * Wm + (u >> 5)] >> (u & 31)) & 1u);
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                const uint32_t all = __ballot_sync(0xFFFFFFFFu, on[i]);
+                if (on[i]) out[pos + __popc(all & lt)] = v0 + 32 * i + lane;
+                pos += __popc(all);
+            }
         }
-        for (uint32_t w = u >> 5; w < Wm; w++) {
-            const uint32_t v   = (w << 5) + lane;
-            const bool     on  = v > u && v < n && ((mask[(uint64_t)u * Wm + w] >> lane) & 1u);
-            const uint32_t all = __ballot_sync(0xFFFFFFFFu, on);
-            if (on) out[pos + __popc(all & lt)] = v;
-            pos += __popc(all);
+        for (uint32_t w0 = u >> 5; w0 < Wm; w0 += 32) {   // row u: 32 words per coalesced load, handed round by shuffles
+            const uint32_t word = w0 + lane < Wm ? mask[(uint64_t)u * Wm + w0 + lane] : 0u;
+            const uint32_t cnt  = min(32u, Wm - w0);
+            for (uint32_t i = 0; i < cnt; i++) {
+                const uint32_t bits = __shfl_sync(0xFFFFFFFFu, word, i);
+                const uint32_t v    = ((w0 + i) << 5) + lane;
+                const bool     set  = v > u && v < n && ((bits >> lane) & 1u);
+                const uint32_t all  = __ballot_sync(0xFFFFFFFFu, set);
+                if (set) out[pos + __popc(all & lt)] = v;
+                pos += __popc(all);
+            }
         }
     }
 }
@@ -257,33 +269,45 @@ __global__ void __launch_bounds__(32) idx_overlap_hist_kernel(const uint32_t* __
     }
 }
 
-// Pass 2: per nucleotide, exclusive scan over the CTAs' counts (in place) and the nucleotide's total. One warp per
-// nucleotide, lanes over the CTAs; the 8 warps of a CTA take 8 neighbouring nucleotides, i.e. the same 32-byte sectors.
+// Pass 2: per nucleotide, exclusive scan over the slices' counts (in place) and the nucleotide's total. A CTA takes 8
+// neighbouring nucleotides (one 32-byte sector per slice row): thread = (nucleotide, one of 32 runs of consecutive
+// slices). Every thread sums its run (independent loads), the 32 run sums of a nucleotide are scanned in shared
+// memory, and a second sweep over the run (now cached) writes the exclusive prefixes.
 __global__ void __launch_bounds__(256) idx_overlap_colscan_kernel(uint32_t* __restrict__ hist, uint32_t n_blocks, uint32_t n, uint32_t* __restrict__ total)
 {
-    const uint32_t lane = threadIdx.x & 31, u = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (u >= n) return;
-    uint32_t carry = 0;
-    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 128) {   // four independent loads in flight per lane
-        uint32_t t[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t b = b0 + 32 * i + lane;
-            t[i] = b < n_blocks ? hist[(uint64_t)b * n + u] : 0u;
+    __shared__ uint32_t run_sum[32][8];
+    const uint32_t j = threadIdx.x & 7, r = threadIdx.x >> 3, u = blockIdx.x * 8 + j;
+    const uint32_t per = (n_blocks + 31) / 32, b0 = min(n_blocks, r * per), b1 = min(n_blocks, b0 + per);
+    uint32_t       sum = 0;
+    if (u < n) {
+#pragma unroll 8
+        for (uint32_t b = b0; b < b1; b++) sum += hist[(uint64_t)b * n + u];
+    }
+    run_sum[r][j] = sum;
+    __syncthreads();
+    if (threadIdx.x < 8) {   // exclusive scan of the 32 run sums of nucleotide j
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < 32; i++) {
+            const uint32_t v = run_sum[i][threadIdx.x];
+            run_sum[i][threadIdx.x] = acc;
+            acc += v;
         }
+        if (blockIdx.x * 8 + threadIdx.x < n) total[blockIdx.x * 8 + threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (u < n) {
+        uint32_t run = run_sum[r][j];
+        for (uint32_t b = b0; b < b1; b += 4) {   // four loads in flight, then the four stores
+            uint32_t t[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t b = b0 + 32 * i + lane;
-            uint32_t       x = t[i];
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-                if ((int)lane >= d) x += y;
+            for (uint32_t i = 0; i < 4; i++) t[i] = b + i < b1 ? hist[(uint64_t)(b + i) * n + u] : 0u;
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                if (b + i < b1) hist[(uint64_t)(b + i) * n + u] = run;
+                run += t[i];
             }
-            if (b < n_blocks) hist[(uint64_t)b * n + u] = carry + x - t[i];
-            carry += __shfl_sync(0xFFFFFFFFu, x, 31);
         }
     }
-    if (lane == 0) total[u] = carry;
 }
 
 __global__ void __launch_bounds__(kScanThreads) idx_overlap_scan_kernel(const uint32_t* __restrict__ total, uint32_t n, uint32_t* __restrict__ overlap_begin,
@@ -309,15 +333,23 @@ __global__ void __launch_bounds__(32) idx_overlap_fill_kernel(const uint32_t* __
     for (uint32_t u = lane; u < n; u += 32) cursor[u] = overlap_begin[u] + hist[(uint64_t)b * n + u];
     __syncwarp();
     const uint32_t v0 = b * per, v1 = min(n_vars, v0 + per);
-    for (uint32_t base = v0; base < v1; base += 32) {
-        const uint32_t mine = base + lane;
-        uint32_t       f = 0, k = 0;
+    // this lane's variable of a batch: first nucleotide and length (0 past the end of the slice); the next batch is
+    // loaded while the current one is walked
+    auto fetch = [&](uint32_t mine, uint32_t& f, uint32_t& k) {
+        f = 0;
+        k = 0;
         if (mine < v1) {
             f = var_first[mine];
             k = var_second[mine] - f + 1u;
             if (f >= n) k = 0;
             k = min(k, n - min(f, n));
         }
+    };
+    uint32_t nf, nk;
+    fetch(v0 + lane, nf, nk);
+    for (uint32_t base = v0; base < v1; base += 32) {
+        const uint32_t f = nf, k = nk;
+        fetch(base + 32 + lane, nf, nk);
         const uint32_t cnt = min(32u, v1 - base), kmax = __reduce_max_sync(0xFFFFFFFFu, k);
         if (kmax == 0) continue;
         if (kmax <= 32) {
