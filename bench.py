@@ -19,6 +19,7 @@ Workloads (BASELINE.json configs):
   c3        10 000 x 120-nt queries x 1 000-motif JSON library (batch mode)
   c2        230-nt query x 400 synthetic CaRNAval RINs
   c1        73-nt example query x 1 000-motif JSON library
+  c4_desc   2000-nt query x 5 000 synthetic .desc modules (wildcards, widened strands, delay 5, gates)
 value     = motif x position placements tested per second, inputs resident in HBM, device time
             (CUDA events on the launching stream), max over ranks.
 e2e       = the same through the host-buffer C ABI call (bss_search*): upload of sequence + mask
@@ -70,6 +71,12 @@ def make_workload(name, rank):
         w["source"] = "rinfolder"
         w["rin"] = (400, 102)
         w["describe"] = "230-nt query x 400 synthetic CaRNAval RINs"
+    elif name == "c4_desc":
+        seq = synth.sequence(2000, 4)
+        w["seqs"], w["masks"] = [seq], [synth.mask_canonical(seq, seed=204, keep=0.3, span=100)]
+        w["source"] = "descfolder"
+        w["desc"] = (5000, 11)
+        w["describe"] = "2000-nt query x 5000 synthetic .desc modules (wildcards from gap-fill, widened short strands, delay 5, regex gates)"
     elif name == "c1":
         seq = "GGGGUAUCGCCAAGCGGUAAGGCACCGGAUUCUGAUUCCGGAGGUCGAGGUUCGAAUCCUCGUACCCCAGCCA"   # data/fasta/example.fa
         w["seqs"], w["masks"] = [seq], [synth.mask_canonical(seq, seed=201, keep=0.3)]
@@ -87,6 +94,10 @@ def host_library(w, tmp):
         n, seed = w["rin"]
         path = synth.write_rin_folder(os.path.join(tmp, "rin"), n, seed, invalid_fraction=0.0, max_components=4, min_len=2)
         return b.HostLibrary.load("rinfolder", path), path
+    if w["source"] == "descfolder":
+        n, seed = w["desc"]
+        path = synth.write_desc_folder(os.path.join(tmp, "desc"), n, seed)
+        return b.HostLibrary.load("descfolder", path), path
     return b.HostLibrary.from_json_modules(w["modules"]), None
 
 
@@ -190,6 +201,10 @@ def cpu_search(w, sample_modules, repeat, threads=None):
             n, seed = w["rin"]
             lib = synth.write_rin_folder(os.path.join(tmp, "rin"), min(n, sample_modules), seed, invalid_fraction=0.0, max_components=4, min_len=2)
             n_modules = min(n, sample_modules)
+        elif w["source"] == "descfolder":
+            n, seed = w["desc"]
+            lib = synth.write_desc_folder(os.path.join(tmp, "desc"), min(n, sample_modules), seed)
+            n_modules = min(n, sample_modules)
         else:
             mods = w["modules"][:sample_modules]
             lib = synth.write_json(os.path.join(tmp, "lib.json"), mods)
@@ -217,7 +232,7 @@ def cpu_search(w, sample_modules, repeat, threads=None):
 
 def sample_size(name):
     # bounded samples: about 1.5 s of Pool-threaded CPU search per pass on a 16-core host
-    return {"c4": 15000, "c4a": 50000, "c4b": 8000, "c4b_all": 800, "c3": 1000, "c2": 400, "c1": 1000}[name]
+    return {"c4": 15000, "c4a": 50000, "c4b": 8000, "c4b_all": 800, "c3": 1000, "c2": 400, "c1": 1000, "c4_desc": 5000}[name]
 
 
 # ----------------------------------------------------------------------------------------
@@ -523,7 +538,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_extra:
         also = {}
-        for name in ("c4b_all", "c3", "c2"):
+        for name in ("c4b_all", "c3", "c2", "c4_desc"):
             if name == args.workload:
                 continue
             try:
@@ -629,6 +644,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_search(w, sample_size(args.workload), repeat=3)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "sites_per_s")} if cb else None
+        # the same search on ONE thread (SURVEY 8d asks for both), on a smaller sample of the library
+        c1t = cpu_search(w, max(1, sample_size(args.workload) // 10), repeat=1, threads=1)
+        line["cpu_baseline_single_thread"] = {k: c1t[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "sites_per_s")} if c1t else None
 
     if rank == 0:
         print(json.dumps(line))
