@@ -172,6 +172,19 @@ class HostLibrary:
         return DeviceLibrary(h, self)
 
 
+def read_fasta(path):
+    """Records of a (multi-record) FASTA file as (name, sequence, structure) tuples: the C++ reader of the batch
+    front-end (biorseo_b200/host/fasta.h), same rules as the reference's Fasta::load."""
+    lib = capi.load()
+    text, length = C.c_void_p(), C.c_uint64()
+    _check(lib.bsh_fasta_text(str(path).encode(), C.byref(text), C.byref(length)), host=True)
+    try:
+        s = C.string_at(text, length.value).decode("utf-8", "replace")
+    finally:
+        lib.bsh_text_free(text)
+    return [tuple(line.split("\t")) for line in s.split("\n")[:-1]]
+
+
 class Query:
     """Sequences + pair masks resident in device memory."""
 

@@ -101,6 +101,7 @@ SIGNATURES = {
     "bsh_device_library": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "bsh_records_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p]),
     "bsh_text_free": (None, [C.c_void_p]),
+    "bsh_fasta_text": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p), u64p]),
 }
 
 _lib = None

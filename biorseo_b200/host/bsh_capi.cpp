@@ -3,7 +3,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
+#include "fasta.h"
 #include "module_library.h"
 
 struct bsh_library {
@@ -18,6 +20,20 @@ int host_fail(const std::string& what) { g_host_error = what; return -1; }
 extern "C" {
 
 const char* bsh_last_error(void) { return g_host_error.c_str(); }
+
+int bsh_fasta_text(const char* path, char** text, uint64_t* len)
+{
+    if (!path || !text || !len) return host_fail("bad argument");
+    std::vector<bsh::FastaRecord> records;
+    std::string                   err, out;
+    if (!bsh::load_fasta(path, records, err)) return host_fail(err);
+    for (const bsh::FastaRecord& r : records) out += r.name + "\t" + r.seq + "\t" + r.str + "\n";
+    *text = static_cast<char*>(std::malloc(out.size() + 1));
+    if (!*text) return host_fail("out of memory");
+    std::memcpy(*text, out.c_str(), out.size() + 1);
+    *len = out.size();
+    return 0;
+}
 
 int bsh_library_load(int kind, const char* path, bsh_library** out)
 {

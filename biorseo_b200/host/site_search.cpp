@@ -74,6 +74,37 @@ bool InsertionSiteSearch::run(const std::string& seq, const std::vector<uint32_t
     return true;
 }
 
+bool InsertionSiteSearch::run_batch(const std::vector<std::string>& seqs, const std::vector<std::vector<uint32_t>>& masks,
+                                    std::vector<std::vector<Motif>>& sites, std::string& err)
+{
+    if (!device_library_) { err = "no library open"; return false; }
+    if (masks.size() != seqs.size()) { err = "one pair mask per sequence is needed"; return false; }
+    std::string           all;
+    std::vector<uint32_t> all_masks;
+    std::vector<uint64_t> seq_begin(1, 0), mask_begin(1, 0);
+    for (size_t q = 0; q < seqs.size(); q++) {
+        const size_t n = seqs[q].size();
+        if (masks[q].size() != n * ((n + 31) / 32)) { err = "pair mask " + std::to_string(q) + " has the wrong size"; return false; }
+        all += seqs[q];
+        all_masks.insert(all_masks.end(), masks[q].begin(), masks[q].end());
+        seq_begin.push_back(all.size());
+        mask_begin.push_back(all_masks.size());
+    }
+    all_masks.push_back(0u);   // never read: keeps data() valid for an all-empty batch
+    bss_sites* found = nullptr;
+    if (bss_search_batch(device_library_, (uint32_t)seqs.size(), all.c_str(), seq_begin.data(), all_masks.data(), mask_begin.data(), &found) != BSS_OK) {
+        err = bss_last_error();
+        return false;
+    }
+    const uint32_t* rec   = bss_sites_records(found);
+    const uint64_t* begin = bss_sites_seq_word_begin(found);
+    sites.assign(seqs.size(), std::vector<Motif>());
+    for (size_t q = 0; q < seqs.size(); q++)
+        for (uint64_t at = begin[q]; at < begin[q + 1]; at += library_.record_words(rec[at])) sites[q].push_back(library_.rebuild(rec + at));
+    bss_sites_free(found);
+    return true;
+}
+
 namespace {
 
 // std::stoi as the reference uses it: optional blanks and sign, digits, trailing garbage ignored;

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "Motif.h"
+#include "fasta.h"
 #include "module_library.h"
 
 namespace bsh {
@@ -54,6 +55,12 @@ class InsertionSiteSearch
     {
         return run(seq, build_pair_mask(seq.size(), allowed), sites, err);
     }
+
+    // Batch mode (BASELINE config "10k sequences x JSON library"): every sequence of `seqs` (e.g. the records of a
+    // multi-record FASTA file, fasta.h) searched in one call; sites[q] receives the sites of sequence q in canonical
+    // order. masks[q] is the packed allowed_basepair mask of sequence q (build_pair_mask).
+    bool run_batch(const std::vector<std::string>& seqs, const std::vector<std::vector<uint32_t>>& masks, std::vector<std::vector<Motif>>& sites,
+                   std::string& err);
 
     // The `--pre-placed` CSV source (cppsrc/MOIP.cpp:114-145, cppsrc/Motif.cpp:17-47): motifs already
     // placed by BayesPairing, one per line after a header ("id,score,start,end,start,end,..."); no

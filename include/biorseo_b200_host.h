@@ -54,6 +54,10 @@ int bsh_device_library(const bsh_library* lib, int device, bss_library** out);
 int  bsh_records_text(const bsh_library* lib, const uint32_t* records, uint64_t n_words, char** text, uint64_t* len);
 void bsh_text_free(char* text);
 
+/* Multi-record FASTA reader of the batch front-end (biorseo_b200/host/fasta.h; record and line rules of the
+ * reference's Fasta::load, cppsrc/fa.cpp:22-60). One line per record: name \t sequence \t structure. */
+int  bsh_fasta_text(const char* path, char** text, uint64_t* len);
+
 const char* bsh_last_error(void);
 
 #ifdef __cplusplus

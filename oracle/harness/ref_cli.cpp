@@ -19,6 +19,8 @@
 //       cppsrc/MOIP.cpp:146-296 does, and dumps insertion_sites_.
 //   biorseo_ref fno   <delay> <seq> <component>...
 //       the placement enumerator find_next_ones_in (cppsrc/Motif.cpp:432-494) alone.
+//   biorseo_ref fasta <file>
+//       the reference's FASTA loader Fasta::load (cppsrc/fa.cpp:22-60): one line per record, name \t seq \t str.
 //   biorseo_ref bench <source> <library> <seqfile> <maskfile> <threads> <repeat> [max_modules]
 //       as `jobs`, timed from the first Pool::push to the last join (validation, JSON parse
 //       and directory walk excluded), prints one JSON line.
@@ -50,6 +52,7 @@
 #include "MOIP.h"
 #undef private
 #include "Pool.h"
+#include "fa.h"
 
 using std::string;
 using std::vector;
@@ -209,6 +212,12 @@ static int run_pairmask(int argc, char** argv)
 
 int main(int argc, char** argv)
 {
+    if (argc >= 3 && string(argv[1]) == "fasta") {
+        std::list<Fasta> records;
+        Fasta::load(records, argv[2]);
+        for (const Fasta& r : records) std::printf("%s\t%s\t%s\n", r.name().c_str(), r.seq().c_str(), r.str().c_str());
+        return 0;
+    }
     if (argc >= 5 && string(argv[1]) == "fno") return run_fno(argc, argv);
     if (argc >= 6 && string(argv[1]) == "pairmask") return run_pairmask(argc, argv);
     if (argc < 6) {

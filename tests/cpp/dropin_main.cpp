@@ -9,6 +9,12 @@
 // loops over insertion_sites_ (cppsrc/MOIP.cpp:302-328, 507-586): one "V x j first second c3terms" line per
 // C_{x,i,p} variable and one "O u v v ..." line per nucleotide covered by more than one variable (the c4 rows).
 //
+//   dropin <source> <library path> <file.fa> - batch
+//
+// Batch mode: every record of a (multi-record) FASTA file (bsh::load_fasta) searched in ONE call
+// (bsh::InsertionSiteSearch::run_batch -> bss_search_batch); the pair mask of each record is the canonical one
+// (AU / GC / GU pairs, 4 <= v - u < 100, u < n - 6). Output lines: record name \t site.
+//
 // Exit codes: 0 ok, 3 search failed (e.g. no GPU: there is no CPU fallback), 2 usage / input.
 #include <cstdint>
 #include <cstdio>
@@ -20,9 +26,63 @@
 
 #include "site_search.h"
 
+static void print_site(const Motif& m)
+{
+    std::cout << m.get_identifier() << '\t';
+    for (size_t j = 0; j < m.comp.size(); j++) std::cout << (j ? " " : "") << m.comp[j].pos.first << '-' << m.comp[j].pos.second;
+    std::cout << '\t';
+    for (size_t j = 0; j < m.links_.size(); j++) std::cout << (j ? " " : "") << m.links_[j].nts.first << '-' << m.links_[j].nts.second;
+    std::cout << '\n';
+}
+
+static int run_batch_mode(char** argv)
+{
+    std::string                   err;
+    std::vector<bsh::FastaRecord> records;
+    if (!bsh::load_fasta(argv[3], records, err)) {
+        std::cerr << "ERR: " << err << "\n";
+        return 2;
+    }
+    std::vector<std::string>           seqs;
+    std::vector<std::vector<uint32_t>> masks;
+    for (const bsh::FastaRecord& r : records) {
+        const std::string& s = r.seq;
+        const size_t       n = s.size();
+        auto canonical = [&](size_t u, size_t v) {
+            if (v < u + 4 || v - u >= 100 || u + 6 >= n) return false;
+            const char a = s[u], c = s[v];
+            return (a == 'A' && c == 'U') || (a == 'U' && c == 'A') || (a == 'G' && c == 'C') || (a == 'C' && c == 'G') || (a == 'G' && c == 'U') ||
+                   (a == 'U' && c == 'G');
+        };
+        seqs.push_back(s);
+        masks.push_back(bsh::build_pair_mask(n, canonical));
+    }
+    bsh::InsertionSiteSearch search;
+    if (!search.open(argv[1], argv[2], -1, err)) {
+        std::cerr << "ERR: " << err << "\n";
+        return 3;
+    }
+    std::vector<std::vector<Motif>> sites;
+    if (!search.run_batch(seqs, masks, sites, err)) {
+        std::cerr << "ERR: " << err << "\n";
+        return 3;
+    }
+    size_t total = 0;
+    for (size_t q = 0; q < sites.size(); q++) {
+        total += sites[q].size();
+        for (const Motif& m : sites[q]) {
+            std::cout << records[q].name << '\t';
+            print_site(m);
+        }
+    }
+    std::cerr << total << " candidate motifs over " << records.size() << " sequences\n";
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     const bool with_index = argc == 6 && std::string(argv[5]) == "index";
+    if (argc == 6 && std::string(argv[5]) == "batch") return run_batch_mode(argv);
     if (argc != 5 && !with_index) {
         std::cerr << "usage: dropin <source> <library> <seq.txt> <mask.bin>\n";
         return 2;

@@ -18,8 +18,8 @@ ROOT = util.ROOT
 BIN = os.path.join(ROOT, "tests", "cpp", "_build", "dropin")
 
 
-@pytest.fixture(scope="module")
-def dropin():
+def build_dropin():
+    """Compiles tests/cpp/dropin_main.cpp against libbiorseo_b200.so (as a patched MOIP.cpp would be) when it is stale."""
     src = os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp")
     os.makedirs(os.path.dirname(BIN), exist_ok=True)
     if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(src), os.path.getmtime(build.LIB_PATH)):
@@ -27,6 +27,11 @@ def dropin():
         subprocess.run(["g++", "-std=c++17", "-O1", src, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "biorseo_b200", "host"),
                         "-L", lib_dir, "-lbiorseo_b200", f"-Wl,-rpath,{lib_dir}", "-o", BIN], check=True)
     return BIN
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    return build_dropin()
 
 
 def _run(binary, source, library, seq, mask, tmp, *extra):
