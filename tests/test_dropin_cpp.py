@@ -146,3 +146,26 @@ def test_variable_index_through_the_cpp_dropin(dropin, name, tmp_path):
     ob, ov = want["overlap_begin"], want["overlap_vars"]
     exp_o = [(u, *[int(v) for v in ov[int(ob[u]):int(ob[u + 1])]]) for u in range(len(seq)) if int(ob[u + 1]) - int(ob[u]) > 1]
     assert got_o == exp_o
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["A2_json", "A4_rin_renumber", "A4_rin_canonical", "A5_desc", "seed11_rin", "seed12_json"])
+def test_constraints_through_the_cpp_dropin(dropin, name, tmp_path):
+    """The C++ consumer of the variable index (tests/cpp/dropin_main.cpp, `constraints`): c3 / c4 / c5 / c6 built from the
+    index instead of the reference's loops must be the reference's own constraints (committed fixture, written from
+    `biorseo_ref model`; and the live reference where it is present)."""
+    import json
+    import index_ref
+    case = next(c for c in cases.CASES if c["name"] == name)
+    lib = cases.materialise(case, tmp_path)
+    seq, mask = case["seq"], cases.mask_of(case["mask"], case["seq"])
+    res = _run(dropin, case["source"], lib, seq, mask, tmp_path, "constraints")
+    assert res.returncode == 0, res.stderr
+    sites, mine = index_ref.parse_model_dump(res.stdout)
+    with open(os.path.join(util.GOLDEN, "site_index.json")) as f:
+        entry = next(e for e in json.load(f) if e["name"] == name)
+    assert sorted(sites) == entry["sites"]
+    assert mine == sorted((op, rhs, tuple((n_, c_) for n_, c_ in terms)) for op, rhs, terms in entry["constraints"])
+    if util.have_ref():
+        import test_site_index
+        assert mine == test_site_index.run_model(case["source"], lib, seq, mask)[1]

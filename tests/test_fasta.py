@@ -89,3 +89,25 @@ def test_batch_over_a_fasta_file_through_the_cpp_dropin(tmp_path):
         assert got.get(f"seq{i}", []) == host.records_text(one.records()), i
         one.close()
     dev.close()
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(not util.have_ref(), reason="needs oracle/_ref")
+def test_reader_equals_reference_on_random_files(tmp_path):
+    """Differential fuzz: random line soups over the characters the loader distinguishes; where the reference aborts
+    (its assertion on a record closed by another header) the reader must refuse the file, elsewhere the records agree."""
+    import random
+    rng = random.Random(20240607)
+    pieces = ["ACGU", "acgu", "N", ">", ">id", "(", ")", ".", "[", "]", "?", "x", "l", "e", " ", "\r", "-", "1", "*", "\t", "GG", "((..))", "leu"]
+    for i in range(150):
+        lines = ["".join(rng.choice(pieces) for _ in range(rng.randint(0, 5))) for _ in range(rng.randint(0, 9))]
+        path = tmp_path / f"f{i}.fa"
+        path.write_bytes(("\n".join(lines) + ("\n" if rng.random() < 0.7 else "")).encode())
+        ref = subprocess.run([util.REF_BIN, "fasta", str(path)], capture_output=True)
+        if ref.returncode != 0:
+            with pytest.raises(b.SearchError):
+                b.read_fasta(path)
+            continue
+        want = [tuple(line.split("\t")) for line in ref.stdout.decode().split("\n")[:-1]]
+        got = b.read_fasta(path)
+        assert got == want, (i, lines)
