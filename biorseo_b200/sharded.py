@@ -23,6 +23,48 @@ def shard_range(n_modules, world_size, rank):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def module_costs(table, n, alphabet=4):
+    """Search-cost estimate per module of a flat component table (HostLibrary.table()) on a query of n nucleotides:
+    the match phase (one shift-AND step per pattern byte per 32-position word) plus the expected number of
+    placements before the pair checks (product over the components of the expected matches n / alphabet^literals),
+    summed over the module's units. Only the ratios between modules matter."""
+    import numpy as np
+    n_units = int(table["n_units"])
+    ucb = table["unit_comp_begin"].astype(np.int64)
+    cpb = table["comp_pat_begin"].astype(np.int64)
+    pattern = np.asarray(table["pattern"])
+    words = (n + 31) // 32
+    costs = np.zeros(int(table["n_modules"]), dtype=np.float64)
+    for u in range(n_units):
+        match, placements = 0.0, 1.0
+        for c in range(int(ucb[u]), int(ucb[u + 1])):
+            p = pattern[int(cpb[c]):int(cpb[c + 1])]
+            literals = int((p != 0x2E).sum())
+            match += 2.0 * len(p) * words
+            placements *= min(float(n), n / float(alphabet) ** literals)
+        costs[int(table["unit_module"][u])] += match + 2.0 * min(placements, 1e9)
+    return costs
+
+
+def shard_ranges_by_cost(costs, world_size):
+    """Contiguous module ranges [begin, end) per rank, in canonical module order, whose summed costs are as even as a
+    contiguous cut allows: rank r ends at the first module where the running cost reaches (r + 1) / world of the total."""
+    import numpy as np
+    costs = np.asarray(costs, dtype=np.float64)
+    m = costs.size
+    prefix = np.concatenate([[0.0], np.cumsum(costs)])
+    total = float(prefix[-1])
+    cuts = [0]
+    for r in range(1, world_size):
+        at = int(np.searchsorted(prefix, total * r / world_size, side="left")) if total > 0 else (m * r) // world_size
+        # the cut goes before or after module at-1, whichever lands closer to the target
+        if total > 0 and at > 0 and at <= m and abs(prefix[at - 1] - total * r / world_size) <= abs(prefix[min(at, m)] - total * r / world_size):
+            at -= 1
+        cuts.append(min(m, max(cuts[-1], at)))
+    cuts.append(m)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
 def allgatherv(local, group=None, counts_out=None):
     """Concatenates the ranks' 1-D tensors in rank order on every rank.
 

@@ -88,3 +88,26 @@ def test_shard_ranges_partition_the_library():
             assert all(a[1] == b_[0] for a, b_ in zip(ranges, ranges[1:]))
             sizes = [e - s for s, e in ranges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_cost_balanced_ranges_partition_the_library_and_beat_equal_counts():
+    """Library shards balanced by a search-cost estimate instead of by module count: contiguous, complete,
+    and on a library whose expensive modules sit at one end, far more even than the equal-count cut."""
+    cheap = synth.json_modules(300, 7, "c4a")      # long strands: few expected placements
+    heavy = synth.json_modules(100, 8, "c4b")      # three short strands: thousands of expected placements
+    modules = sorted(cheap + [("z" + k, s, t) for k, s, t in heavy])      # the heavy ones last in canonical order
+    host = b.HostLibrary.from_json_modules(modules)
+    costs = sharded.module_costs(host.table(), 2000)
+    assert costs.size == host.n_modules and (costs > 0).all()
+    for world in (1, 2, 4, 8):
+        ranges = sharded.shard_ranges_by_cost(costs, world)
+        assert ranges[0][0] == 0 and ranges[-1][1] == costs.size
+        assert all(a[1] == b_[0] and a[0] <= a[1] for a, b_ in zip(ranges, ranges[1:]))
+        by_cost = max(costs[s:e].sum() for s, e in ranges)
+        by_count = max(costs[s:e].sum() for s, e in (sharded.shard_range(costs.size, world, r) for r in range(world)))
+        assert by_cost <= by_count + 1e-9
+        assert by_cost <= costs.sum() / world + costs.max() + 1e-9
+    assert max(costs[s:e].sum() for s, e in sharded.shard_ranges_by_cost(costs, 4)) < 0.6 * max(
+        costs[s:e].sum() for s, e in (sharded.shard_range(costs.size, 4, r) for r in range(4)))
+    assert sharded.shard_ranges_by_cost(np.zeros(0), 3) == [(0, 0), (0, 0), (0, 0)]
+    assert sharded.shard_ranges_by_cost(np.zeros(5), 2) == [(0, 2), (2, 5)]
