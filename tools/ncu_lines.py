@@ -9,7 +9,7 @@ def flush():
         tot = sum(v[0] for v in acc.values()); tots = sum(v[1] for v in acc.values())
         print(f"== {func[:100]}  inst={tot:.3g} samples={tots}")
         for ln, (ins, smp, src) in sorted(acc.items(), key=lambda kv: -kv[1][0])[:top]:
-            print(f"  L{ln:>4} {100*ins/tot:5.1f}% inst {100*smp/max(tots,1):5.1f}% smp  {src.strip()[:110]}")
+            print(f"  L{ln:>4} {100*ins/max(tot,1):5.1f}% inst {100*smp/max(tots,1):5.1f}% smp  {src.strip()[:110]}")
 for r in rows:
     if not r: continue
     if r[0] == "Function Name":
