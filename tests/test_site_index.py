@@ -67,6 +67,45 @@ def test_restatement_equals_reference_constraints(case, tmp_path):
     assert mine == ref_constraints
 
 
+@pytest.mark.ref
+@pytest.mark.skipif(not util.have_ref(), reason="needs oracle/_ref")
+@pytest.mark.parametrize("source", ["jsonfolder", "rinfolder", "descfolder"])
+@pytest.mark.parametrize("seed,n", [(21, 60), (22, 90), (23, 120)])
+def test_restatement_equals_reference_on_seeded_libraries(tmp_path, source, seed, n):
+    """Wider pinning of the restatement (the GPU tests compare the device arrays with it at sizes the reference cannot
+    reach): seeded libraries and dense RANDOM pair masks (not only canonical ones), constraints against the reference's.
+    The JSON modules are cut out of the query itself, so that they do have placements."""
+    import numpy as np
+    seq = synth.sequence(n, 500 + seed)
+    mask = synth.mask_random(n, seed, density=0.6) if seed % 2 else synth.mask_all(n)
+    if source == "jsonfolder":
+        rng = np.random.default_rng(seed)
+        mods = []
+        for i in range(25):
+            lengths = [int(x) for x in rng.integers(2, 6, int(rng.integers(1, 4)))]
+            if sum(lengths) < 4:
+                lengths[0] += 4
+            at, strands = int(rng.integers(0, 8)), []
+            for k in lengths:
+                strands.append(seq[at:at + k])
+                at += k + int(rng.integers(1, 9))
+            if at >= n or any(len(x) < 2 for x in strands):
+                continue
+            mods.append((f"m{i:02d}", "&".join(strands), synth._strand_struct([len(x) for x in strands])))
+        path = synth.write_json(str(tmp_path / "lib.json"), mods)
+    elif source == "rinfolder":
+        path = synth.write_rin_folder(str(tmp_path / "rin"), 60, seed, max_components=3, min_len=1)
+    else:
+        path = synth.write_desc_folder(str(tmp_path / "desc"), 150, seed)
+    ref_sites, ref_constraints = run_model(source, path, seq, mask)
+    host = b.HostLibrary.load(source, path)
+    lines = canonical_sites(host, source, path, seq, mask)
+    assert len(lines) >= 2 and sorted(lines) == sorted(ref_sites)
+    rule = RULE[source]
+    index = index_ref.build(lines, n, mask, rule)
+    assert index_ref.constraints_from_index(index, lines, n, mask, rule) == ref_constraints
+
+
 def _fixture():
     with open(FIXTURE) as f:
         return json.load(f)
