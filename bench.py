@@ -232,7 +232,7 @@ def cpu_search(w, sample_modules, repeat, threads=None):
 
 def sample_size(name):
     # bounded samples: about 1.5 s of Pool-threaded CPU search per pass on a 16-core host
-    return {"c4": 15000, "c4a": 50000, "c4b": 8000, "c4b_all": 800, "c3": 1000, "c2": 400, "c1": 1000, "c4_desc": 5000}[name]
+    return {"c4": 15000, "c4a": 50000, "c4b": 8000, "c4b_all": 800, "c3": 1000, "c2": 400, "c1": 1000, "c4_desc": 500}[name]
 
 
 # ----------------------------------------------------------------------------------------
