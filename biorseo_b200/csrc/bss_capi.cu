@@ -1002,8 +1002,11 @@ int bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, con
     uint32_t* overlap_total   = pair_begin_tmp + n1;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    BSS_CUDA(cudaEventCreate(&ev0));
-    BSS_CUDA(cudaEventCreate(&ev1));
+    if (cudaError_t ee = cudaEventCreate(&ev0); ee != cudaSuccess) return cuda_fail(ee, "cudaEventCreate");
+    if (cudaError_t ee = cudaEventCreate(&ev1); ee != cudaSuccess) {
+        cudaEventDestroy(ev0);
+        return cuda_fail(ee, "cudaEventCreate");
+    }
     bss_site_index* x = new bss_site_index();
     x->lib = lib;
     x->n   = n;

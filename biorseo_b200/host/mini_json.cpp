@@ -70,10 +70,10 @@ struct Cursor {
             case 'r': out += '\r'; break;
             case 't': out += '\t'; break;
             case 'u': {
-                uint32_t cp;
+                uint32_t cp = 0;
                 if (!hex4(cp)) return false;
                 if (cp >= 0xD800 && cp <= 0xDBFF) {
-                    uint32_t lo;
+                    uint32_t lo = 0;
                     if (i + 2 > s.size() || s[i] != '\\' || s[i + 1] != 'u') return fail("lone surrogate");
                     i += 2;
                     if (!hex4(lo)) return false;
