@@ -33,7 +33,7 @@ def test_interpreter_enumerator_golden(entry):
 
 
 @pytest.mark.skipif(not (util.have_ref() or util.have_port()), reason="no oracle binary")
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", range(10))
 def test_loaders_match_oracle_on_random_libraries(seed, tmp_path):
     n = 60 + 31 * seed
     seq = synth.sequence(n, 900 + seed)
