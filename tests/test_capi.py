@@ -56,3 +56,24 @@ def test_product_sources_do_not_touch_the_oracle():
                 if name.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                     text = open(os.path.join(dirpath, name)).read()
                     assert "oracle/" not in text.replace("oracle/Makefile", "") or name == "build.py", os.path.join(dirpath, name)
+
+
+def test_new_entry_points_validate_their_arguments_before_touching_a_device():
+    """Index build, exchange and probe: malformed calls are refused with a status code and a message (no crash, no CUDA)."""
+    lib = capi.load()
+    out = C.c_void_p()
+    assert lib.bss_site_index_build(None, None, 0, None, 0, 1, C.byref(out)) == capi.BSS_ERR_INVALID and not out.value
+    assert lib.bss_site_index_count(None, 0) == 0 and not lib.bss_site_index_host(None, 0) and not lib.bss_site_index_device(None, 0)
+    lib.bss_site_index_free(None)
+    v = C.c_double()
+    assert lib.bss_measure_int_issue(None, C.byref(v)) == capi.BSS_ERR_INVALID
+    for world, rank, cap, header in ((0, 0, 64, 4), (17, 0, 64, 4), (2, 2, 64, 4), (2, 0, 64, 3), (2, 0, 64, 0), (2, 0, 1 << 41, 4)):
+        rc = lib.bss_exchange_create(0, world, rank, cap, header, C.byref(out))
+        assert rc in (capi.BSS_ERR_INVALID, capi.BSS_ERR_LIMIT) and not out.value, (world, rank, cap, header)
+        assert lib.bss_last_error()
+    assert lib.bss_exchange_run_async(None, None, None, None) == capi.BSS_ERR_INVALID
+    assert lib.bss_exchange_handle(None, None) == capi.BSS_ERR_INVALID and lib.bss_exchange_open(None, None) == capi.BSS_ERR_INVALID
+    assert not lib.bss_exchange_block(None) and lib.bss_exchange_capacity(None) == 0
+    lib.bss_exchange_destroy(None)
+    text, length = C.c_void_p(), C.c_uint64()
+    assert lib.bsh_fasta_text(None, C.byref(text), C.byref(length)) != 0
