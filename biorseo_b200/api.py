@@ -248,9 +248,10 @@ class HostBatch:
 
 
 class Sites:
-    def __init__(self, handle, n_seqs):
+    def __init__(self, handle, n_seqs, owner=None):
         self._lib = capi.load()
         self._h = handle
+        self._owner = owner   # keeps the DeviceLibrary alive while its result is
         self.n_sites = int(self._lib.bss_sites_count(handle))
         self.n_words = int(self._lib.bss_sites_words(handle))
         self.n_seqs = n_seqs
@@ -284,9 +285,10 @@ class SiteIndex:
     """Insertion-variable index of one searched sequence (bss_site_index_build): the C_{x,i,p} variables,
     the c3 term counts, the per-nucleotide overlap lists (c4) and the pair adjacency, as u32 arrays."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, owner=None):
         self._lib = capi.load()
         self._h = handle
+        self._owner = owner
         self.build_ms = float(self._lib.bss_site_index_ms(handle))
         self.kernel_launches = int(self._lib.bss_site_index_launches(handle))
 
@@ -323,6 +325,11 @@ class SiteIndex:
             pass
 
 
+# Developer knobs applied to every DeviceLibrary created while it is non-empty (tests force rarely taken paths
+# on small inputs this way: {"heavy_ranks": 64}, {"list_cap": 40}, {"window": 0} ...; see bss_library_set_tuning).
+DEFAULT_TUNING = {}
+
+
 class DeviceLibrary:
     """Flat component table resident on one GPU + the search entry points."""
 
@@ -330,6 +337,23 @@ class DeviceLibrary:
         self._lib = capi.load()
         self._h = handle
         self.host = host
+        for knob, value in DEFAULT_TUNING.items():
+            self.set_tuning(knob, value)
+
+    def set_tuning(self, knob, value):
+        """knob: one of capi.TUNE; value < 0 returns it to automatic."""
+        _check(self._lib.bss_library_set_tuning(self._h, capi.TUNE[knob], int(value)))
+
+    @property
+    def n_window_units(self):
+        return self._lib.bss_library_window_units(self._h)
+
+    def placements_enumerated(self, query=None):
+        """Exact number of placements the reference's enumerator materialises before its filters, over the whole
+        query (None: the query of the last host-buffer search). A diagnostic kernel of its own."""
+        v = C.c_uint64()
+        _check(self._lib.bss_placements_enumerated(self._h, query._h if query is not None else None, C.byref(v)))
+        return v.value
 
     @classmethod
     def from_table(cls, table, device=-1):
@@ -403,7 +427,7 @@ class DeviceLibrary:
     def search_query(self, query, fetch=True):
         h = C.c_void_p()
         _check(self._lib.bss_search_query(self._h, query._h, 1 if fetch else 0, C.byref(h)))
-        return Sites(h, query.n_seqs)
+        return Sites(h, query.n_seqs, self)
 
     def search_query_into(self, query, device_ptr, capacity_words, seq_begin_ptr=None):
         """Returns (rc, n_words, n_sites); rc == BSS_ERR_OVERFLOW leaves the buffer untouched."""
@@ -434,7 +458,7 @@ class DeviceLibrary:
         buf = np.frombuffer(seq + b"\0", dtype=np.uint8)
         h = C.c_void_p()
         _check(self._lib.bss_search(self._h, buf.ctypes.data_as(C.c_void_p), len(seq), mask.ctypes.data_as(C.c_void_p), C.byref(h)))
-        return Sites(h, 1)
+        return Sites(h, 1, self)
 
     def search_batch(self, seqs, masks):
         if len(seqs) == 1:   # no concatenation of the (possibly large) mask
@@ -448,14 +472,14 @@ class DeviceLibrary:
         h = C.c_void_p()
         _check(self._lib.bss_search_batch(self._h, len(seqs), blob.ctypes.data_as(C.c_void_p), seq_begin.ctypes.data_as(capi.u64p),
                                           allm.ctypes.data_as(C.c_void_p), mask_begin.ctypes.data_as(capi.u64p), C.byref(h)))
-        return Sites(h, len(seqs))
+        return Sites(h, len(seqs), self)
 
     def search_host(self, batch):
         """One-shot on a HostBatch: upload, search, download (bss_search_batch)."""
         h = C.c_void_p()
         _check(self._lib.bss_search_batch(self._h, batch.n_seqs, batch.seqs.ctypes.data_as(C.c_void_p), batch.seq_begin.ctypes.data_as(capi.u64p),
                                           batch.masks.ctypes.data_as(C.c_void_p), batch.mask_begin.ctypes.data_as(capi.u64p), C.byref(h)))
-        return Sites(h, batch.n_seqs)
+        return Sites(h, batch.n_seqs, self)
 
     def site_index(self, query, records_ptr, seq=0, c3_rule=None, fetch=True):
         """Index of the sites of sequence `seq` of the LAST search on this library (made with `query`;
@@ -466,7 +490,7 @@ class DeviceLibrary:
         h = C.c_void_p()
         _check(self._lib.bss_site_index_build(self._h, query._h if query is not None else None, int(seq),
                                               C.c_void_p(records_ptr) if records_ptr else None, int(c3_rule), 1 if fetch else 0, C.byref(h)))
-        return SiteIndex(h)
+        return SiteIndex(h, self)
 
     def gather_cut(self, blocks_ptr, world, block_words, header_words, out_ptr, counts_ptr, overflow_ptr, cuda_stream=None):
         _check(self._lib.bss_gather_cut(self._h, C.c_void_p(blocks_ptr), world, block_words, header_words, C.c_void_p(out_ptr), C.c_void_p(counts_ptr),

@@ -11,11 +11,12 @@ LIB_PATH = os.path.join(HERE, "lib", "libbiorseo_b200.so")
 
 BSS_OK = 0
 BSS_ERR_INVALID, BSS_ERR_NO_DEVICE, BSS_ERR_CUDA, BSS_ERR_LIMIT = -1, -2, -3, -4
-BSS_ERR_BAD_SEQUENCE, BSS_ERR_OVERFLOW, BSS_ERR_COUNT = -5, -6, -7
+BSS_ERR_BAD_SEQUENCE, BSS_ERR_OVERFLOW, BSS_ERR_COUNT, BSS_ERR_NOMEM, BSS_ERR_INTERNAL = -5, -6, -7, -8, -9
 KIND_JSON, KIND_RIN, KIND_DESC = 0, 1, 2
 C3_COMPONENT_LESS_LINKS, C3_INTERIOR = 0, 1
 IDX_SECTIONS = ("var_begin", "var_first", "var_second", "var_c3_terms", "overlap_begin", "overlap_vars", "pair_begin", "pair_partner",
                 "row_first_pair")
+TUNE = {"group": 0, "units_per_chunk": 1, "heavy_ranks": 2, "list_cap": 3, "window": 4, "window_stage": 5}
 KIND_OF_SOURCE = {"jsonfolder": KIND_JSON, "rinfolder": KIND_RIN, "descfolder": KIND_DESC}
 
 u32p = C.POINTER(C.c_uint32)
@@ -32,7 +33,9 @@ class BssTable(C.Structure):
 class BssStats(C.Structure):
     _fields_ = [("placements_tested", C.c_uint64), ("n_sites", C.c_uint64), ("n_words", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
-                ("count_ms", C.c_float), ("scan_ms", C.c_float), ("emit_ms", C.c_float), ("total_ms", C.c_float)]
+                ("count_ms", C.c_float), ("scan_ms", C.c_float), ("emit_ms", C.c_float), ("total_ms", C.c_float),
+                ("window_items", C.c_uint64), ("ordinary_items", C.c_uint64), ("heavy_items", C.c_uint64),
+                ("placements_enumerated", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/*.h
@@ -44,7 +47,10 @@ SIGNATURES = {
     "bss_library_destroy": (None, [C.c_void_p]),
     "bss_library_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bss_library_set_module_base": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "bss_library_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "bss_library_units": (C.c_uint32, [C.c_void_p]),
+    "bss_library_window_units": (C.c_uint32, [C.c_void_p]),
+    "bss_placements_enumerated": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
     "bss_library_modules": (C.c_uint32, [C.c_void_p]),
     "bss_library_module_components": (C.c_uint32, [C.c_void_p, C.c_uint32]),
     "bss_query_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, u64p, C.c_void_p, u64p, C.POINTER(C.c_void_p)]),

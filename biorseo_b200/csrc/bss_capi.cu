@@ -4,6 +4,7 @@
 #include "biorseo_b200.h"
 
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -14,6 +15,7 @@
 namespace {
 
 thread_local std::string g_error;
+using bss::guarded;
 
 int fail(int code, const std::string& what)
 {
@@ -78,20 +80,6 @@ struct PinnedBuffer {
     }
 };
 
-bool compatible(uint8_t a, uint8_t b) { return a == '.' || b == '.' || a == b; }
-
-// Can two matches of this pattern overlap, i.e. is the pattern compatible with itself at
-// some shift 1..k-1 ?
-bool can_self_overlap(const uint8_t* p, uint32_t k)
-{
-    for (uint32_t s = 1; s < k; s++) {
-        bool ok = true;
-        for (uint32_t j = 0; ok && j + s < k; j++) ok = compatible(p[j], p[j + s]);
-        if (ok) return true;
-    }
-    return false;
-}
-
 }   // namespace
 
 int bss::set_error(int code, const std::string& what) { return fail(code, what); }
@@ -107,6 +95,8 @@ struct bss_query {
     uint64_t      total_len = 0;
     uint64_t      h2d_bytes = 0;
     std::vector<uint64_t> h_seq_begin, h_mask_begin;   // host copies of the offsets (relative to the first sequence)
+    int           known_band = INT32_MIN;   // widest band over the sequences, when it has been read back (resident queries)
+    bss_library*  owner = nullptr;          // the library it was created on (null for the library's own one-shot query)
 };
 
 struct bss_library {
@@ -115,17 +105,20 @@ struct bss_library {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t  ev[4]      = {nullptr, nullptr, nullptr, nullptr};
     bss::DevLibrary       dev{};
-    DeviceBuffer          d_blob, d_unit_off, d_unit_rlen, d_unit_probe, d_prefilter;
-    uint32_t              n_modules = 0, n_units = 0;
+    DeviceBuffer          d_blob, d_unit_off, d_unit_rlen, d_unit_probe, d_unit_flags, d_prefilter;
+    uint32_t              n_modules = 0, n_units = 0, n_window_units = 0;
+    bss::Tuning           tuning;
     std::vector<uint32_t> module_components;
     // work buffers, reused across searches
-    DeviceBuffer d_counts, d_chunk_sites, d_chunk_words, d_totals, d_seq_word_begin, d_alive, d_lane_counts, d_heavy;
-    uint32_t     n_alive = 0, n_heavy = 0;   // items with sites / parked heavy items of the last count pass
+    DeviceBuffer d_counts, d_chunks, d_totals, d_seq_word_begin, d_alive, d_lane_counts, d_heavy, d_wlist, d_alive_w, d_lane_counts_w;
+    uint32_t     n_alive = 0, n_heavy = 0, n_alive_w = 0;   // items with sites / parked heavy items / window items with sites of the last count pass
+    DeviceBuffer d_placements;               // scratch of bss_placements_enumerated
     // bss_search_query_into replays its launch sequence as a CUDA graph while its arguments stay the same
     struct GraphKey {
         uint64_t query_serial = 0, capacity = 0, dev_serial = 0;
         const void *records = nullptr, *seq_out = nullptr, *stream = nullptr, *counts = nullptr, *alive = nullptr, *lanes = nullptr, *heavy = nullptr,
-                   *chunk_sites = nullptr, *chunk_words = nullptr, *seq_begin = nullptr, *prefilter = nullptr;
+                   *chunk_sites = nullptr, *chunk_words = nullptr, *seq_begin = nullptr, *prefilter = nullptr, *wlist = nullptr, *alive_w = nullptr,
+                   *lanes_w = nullptr;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof *this) == 0; }
     } graph_key;
     cudaGraphExec_t graph_exec = nullptr;
@@ -136,9 +129,14 @@ struct bss_library {
         bss::Plan       plan{};
         uint64_t        capacity = 0;
         uint64_t*       seq_out = nullptr;
+        bool            ordinary = true;
     } pending;
+    // result handles and queries created on this library and still alive: bss_library_destroy detaches them
+    std::vector<bss_sites*>      live_sites;
+    std::vector<bss_site_index*> live_indexes;
+    std::vector<bss_query*>      live_queries;
     bool            graphs_ok  = true;
-    uint64_t        dev_serial = 1;   // bumped when launch parameters held by value change (module base)
+    uint64_t        dev_serial = 1;   // bumped when launch parameters held by value change (module base, tuning)
     bss_query    oneshot;       // storage of the host-buffer entry points (bss_search, bss_search_batch), reused across calls
     PinnedBuffer h_totals;
     // one spare set of result buffers, recycled by bss_sites_free
@@ -160,6 +158,36 @@ struct bss_sites {
     std::vector<uint64_t> seq_word_begin;
 };
 
+struct bss_site_index {
+    bss_library* lib = nullptr;
+    uint32_t     n = 0, launches = 0;
+    float        ms = 0.0f;
+    bool         fetched = false;
+    DeviceBuffer d_main, d_overlap;
+    PinnedBuffer h_main, h_overlap;
+    uint64_t     offset[BSS_IDX_SECTIONS] = {}, count[BSS_IDX_SECTIONS] = {};   // in u32 elements; OVERLAP_VARS lives in its own buffer
+};
+
+namespace {
+
+template <typename T>
+void forget(std::vector<T*>& v, T* x)
+{
+    v.erase(std::remove(v.begin(), v.end(), x), v.end());
+}
+
+void detach_children(bss_library* lib)
+{
+    for (bss_sites* s : lib->live_sites) s->lib = nullptr;
+    for (bss_site_index* x : lib->live_indexes) x->lib = nullptr;
+    for (bss_query* q : lib->live_queries) q->owner = nullptr;
+    lib->live_sites.clear();
+    lib->live_indexes.clear();
+    lib->live_queries.clear();
+}
+
+}   // namespace
+
 extern "C" {
 
 int bss_abi_version(void) { return BSS_ABI_VERSION; }
@@ -168,6 +196,7 @@ const char* bss_last_error(void) { return g_error.c_str(); }
 
 int bss_device_count(void)
 {
+    return guarded([&]() -> int {
     int         n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) {
@@ -175,163 +204,20 @@ int bss_device_count(void)
         return 0;
     }
     return n;
+    });
 }
 
 int bss_library_create(const bss_table* t, int device, bss_library** out)
 {
+    return guarded([&]() -> int {
     if (!t || !out) return fail(BSS_ERR_INVALID, "null argument");
     *out = nullptr;
-    const uint32_t n_all = t->n_units + t->n_gates;
-    if (n_all && (!t->unit_module || !t->unit_delay || !t->unit_comp_begin || !t->comp_pat_begin || !t->unit_check_begin))
-        return fail(BSS_ERR_INVALID, "null table array");
-    if (t->n_units && !t->unit_gate) return fail(BSS_ERR_INVALID, "null unit_gate");
-
-    // alphabet: distinct literal pattern bytes
-    int code_of[256];
-    std::fill(code_of, code_of + 256, -1);
-    std::vector<uint8_t> alphabet;
-    const uint32_t n_comps = n_all ? t->unit_comp_begin[n_all] : 0;
-    const uint32_t n_pat   = n_comps ? t->comp_pat_begin[n_comps] : 0;
-    if (n_pat && !t->pattern) return fail(BSS_ERR_INVALID, "null pattern array");
-    for (uint32_t i = 0; i < n_pat; i++) {
-        const uint8_t b = t->pattern[i];
-        if (b == '.' || code_of[b] >= 0) continue;
-        if (b == '\n' || b == '\r') return fail(BSS_ERR_INVALID, "pattern contains a line terminator");
-        code_of[b] = (int)alphabet.size();
-        alphabet.push_back(b);
+    bss::BuiltLibrary built;
+    {
+        std::string why;
+        const int   rc = bss::build_library(t, built, why);
+        if (rc != BSS_OK) return fail(rc, why);
     }
-    if (alphabet.size() > BSS_MAX_ALPHABET) return fail(BSS_ERR_LIMIT, "more than BSS_MAX_ALPHABET distinct pattern bytes");
-
-    // unit descriptors
-    std::vector<uint32_t> blob, unit_off(n_all + 1, 0);
-    std::vector<uint32_t> module_components(t->n_modules, 0);
-    std::vector<float>    density;   // per searched unit: expected matches per nucleotide, all components
-    std::vector<uint16_t> unit_probe(4 * (size_t)std::max<uint32_t>(1, t->n_units), 0xFFFFu);   // k-mer probes of up to four components
-    uint32_t              cmax = 1;
-    for (uint32_t u = 0; u < n_all; u++) {
-        unit_off[u] = (uint32_t)blob.size();
-        const uint32_t c0 = t->unit_comp_begin[u], c1 = t->unit_comp_begin[u + 1];
-        const uint32_t k0 = t->unit_check_begin[u], k1 = t->unit_check_begin[u + 1];
-        if (c1 < c0 || k1 < k0) return fail(BSS_ERR_INVALID, "non-monotonic table offsets");
-        const uint32_t C = c1 - c0, NK = k1 - k0;
-        if (C < 1 || C > BSS_MAX_COMPONENTS) return fail(BSS_ERR_LIMIT, "unit with 0 or more than BSS_MAX_COMPONENTS components");
-        if (NK > BSS_MAX_CHECKS) return fail(BSS_ERR_LIMIT, "unit with more than BSS_MAX_CHECKS checks");
-        if (NK && !t->checks) return fail(BSS_ERR_INVALID, "null checks array");
-        if (t->unit_delay[u] > 0xFFFFu) return fail(BSS_ERR_LIMIT, "delay above 65535");
-        if (t->unit_module[u] >= t->n_modules) return fail(BSS_ERR_INVALID, "unit_module out of range");
-        uint32_t gate = bss::kNoGate;
-        if (u < t->n_units) {
-            gate = t->unit_gate[u];
-            if (gate != bss::kNoGate && (gate < t->n_units || gate >= n_all)) return fail(BSS_ERR_INVALID, "unit_gate out of range");
-            uint32_t& mc = module_components[t->unit_module[u]];
-            if (mc != 0 && mc != C) return fail(BSS_ERR_INVALID, "units of one module disagree on the component count");
-            mc = C;
-        }
-        cmax = std::max(cmax, C);
-
-        // order checks by the level at which both ends are known
-        std::vector<uint32_t> order(NK);
-        std::vector<int>      level(NK);
-        for (uint32_t i = 0; i < NK; i++) {
-            const int16_t* c = t->checks + 4 * (size_t)(k0 + i);
-            if (c[0] < -1 || c[0] >= (int)C || c[2] < -1 || c[2] >= (int)C) return fail(BSS_ERR_INVALID, "check anchor out of range");
-            level[i] = std::max(0, std::max((int)c[0], (int)c[2]));
-            order[i] = i;
-        }
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return level[a] < level[b]; });
-
-        // match programs: one (occurrence row, shift) step per literal symbol, or per pair of
-        // adjacent literal symbols when the alphabet is small enough for pair rows
-        const bool     pairs = alphabet.size() <= bss::kPairAlphabet;
-        const uint32_t ns    = (uint32_t)alphabet.size();
-        std::vector<uint16_t>              program;
-        std::vector<std::pair<uint32_t, uint32_t>> prog_range(C);   // first step, number of steps
-        for (uint32_t c = c0; c < c1; c++) {
-            const uint32_t pb = t->comp_pat_begin[c], k = t->comp_pat_begin[c + 1] - pb;
-            if (t->comp_pat_begin[c + 1] < pb || k > BSS_MAX_PATTERN) return fail(BSS_ERR_LIMIT, "component pattern longer than BSS_MAX_PATTERN");
-            const uint8_t* p = t->pattern + pb;
-            const uint32_t first_step = (uint32_t)program.size();
-            for (uint32_t j = 0; j < k;) {
-                if (p[j] == '.') { j++; continue; }
-                uint32_t row = (uint32_t)code_of[p[j]], shift = j;
-                if (pairs && j + 1 < k && p[j + 1] != '.') {
-                    row = ns + row * ns + (uint32_t)code_of[p[j + 1]];
-                    j += 2;
-                } else {
-                    j += 1;
-                }
-                program.push_back((uint16_t)(row | ((shift & 31u) << 7) | ((shift >> 5) << 12)));
-            }
-            prog_range[c - c0] = {first_step, (uint32_t)program.size() - first_step};
-        }
-        if (u < t->n_units) {   // uniform symbols: a pattern with l literal symbols matches one position in |alphabet|^l
-            double d = 0.0;
-            for (uint32_t c = c0; c < c1; c++) {
-                const uint32_t pb = t->comp_pat_begin[c], k = t->comp_pat_begin[c + 1] - pb;
-                double         f  = 1.0;
-                for (uint32_t j = 0; j < k; j++)
-                    if (t->pattern[pb + j] != '.') f /= std::max<double>(2.0, (double)alphabet.size());
-                d += f;
-            }
-            density.push_back((float)d);
-        }
-        if (u < t->n_units && alphabet.size() <= 4) {   // longest window (4..6) of consecutive literal symbols of the (up to four) probed patterns
-            uint32_t slot = 0;
-            for (uint32_t c = c0; c < c1 && slot < 4; c++) {
-                const uint32_t pb = t->comp_pat_begin[c], k = t->comp_pat_begin[c + 1] - pb;
-                uint32_t       run = 0, best = 0, best_end = 0;
-                for (uint32_t j = 0; j < k && best < bss::kKmerMax; j++) {
-                    run = t->pattern[pb + j] == '.' ? 0 : run + 1;
-                    if (std::min(run, bss::kKmerMax) > best) { best = std::min(run, bss::kKmerMax); best_end = j + 1; }
-                }
-                if (best < bss::kKmerMin) continue;
-                uint32_t code = 0;
-                for (uint32_t i = 0; i < best; i++) code |= (uint32_t)code_of[t->pattern[pb + best_end - best + i]] << (2 * i);
-                unit_probe[4 * (size_t)u + slot++] = (uint16_t)(code | ((best - bss::kKmerMin) << 12));
-            }
-        }
-        const uint32_t pat_words = ((uint32_t)program.size() + 1) / 2;
-        const uint32_t head      = 4 + 2 * C;
-        const size_t   base      = blob.size();
-        blob.resize(base + head + pat_words + 2 * (size_t)NK, 0);
-        uint32_t* b  = blob.data() + base;
-        b[0] = t->unit_module[u];
-        b[1] = C | (NK << 8) | (t->unit_delay[u] << 16);
-        b[2] = gate;
-        b[3] = (head + pat_words) << 16;
-        if (!program.empty()) std::memcpy(b + head, program.data(), program.size() * sizeof(uint16_t));
-        uint32_t next_check = 0;
-        for (uint32_t c = 0; c < C; c++) {
-            const uint32_t pb = t->comp_pat_begin[c0 + c], k = t->comp_pat_begin[c0 + c + 1] - pb;
-            b[4 + 2 * c] = k | ((head * 2 + prog_range[c].first) << 8) | (can_self_overlap(t->pattern + pb, k) ? bss::kCompOverlap : 0u);
-            const uint32_t begin = next_check;
-            while (next_check < NK && level[order[next_check]] == (int)c) next_check++;
-            b[5 + 2 * c] = begin | (next_check << 8) | (prog_range[c].second << 16);
-        }
-        uint32_t* chk = b + head + pat_words;
-        for (uint32_t i = 0; i < NK; i++) {
-            const int16_t* c = t->checks + 4 * (size_t)(k0 + order[i]);
-            const int      lv = level[order[i]];
-            // word 0: the end known before level lv is entered; word 1: the end on component lv
-            const bool a_on = c[0] == lv, b_on = c[2] == lv;
-            const int16_t *first = c, *second = c + 2;
-            uint32_t       flags = 0;
-            if (a_on != b_on) {
-                if (a_on) std::swap(first, second);
-            } else {
-                flags = bss::kCheckFixed;
-            }
-            if (!flags && first[0] >= 0 && first[0] < second[0] && t->unit_delay[u] >= 1) {
-                const uint32_t ka = t->comp_pat_begin[c0 + first[0] + 1] - t->comp_pat_begin[c0 + first[0]];
-                const uint32_t kb = t->comp_pat_begin[c0 + second[0] + 1] - t->comp_pat_begin[c0 + second[0]];
-                if (first[1] >= 0 && (uint32_t)first[1] < ka && second[1] >= 0 && (uint32_t)second[1] < kb) flags |= bss::kCheckOrdered;
-            }
-            chk[2 * i]     = ((uint32_t)(uint8_t)(int8_t)first[0]) | (((uint32_t)(uint16_t)first[1]) << 8) | flags;
-            chk[2 * i + 1] = ((uint32_t)(uint8_t)(int8_t)second[0]) | (((uint32_t)(uint16_t)second[1]) << 8);
-        }
-        if (blob.size() > 0x7FFFFFFFu) return fail(BSS_ERR_LIMIT, "library too large");
-    }
-    unit_off[n_all] = (uint32_t)blob.size();
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -347,7 +233,8 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     lib->device      = device;
     lib->n_modules   = t->n_modules;
     lib->n_units     = t->n_units;
-    lib->module_components = module_components;
+    lib->n_window_units    = built.n_window_units;
+    lib->module_components = built.module_components;
     auto bail = [&](int code) { bss_library_destroy(lib); return code; };
 #define BSS_CUDA_LIB(call)                                                   \
     do {                                                                     \
@@ -358,41 +245,34 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     BSS_CUDA_LIB(cudaStreamCreateWithFlags(&lib->own_stream, cudaStreamNonBlocking));
     lib->stream = lib->own_stream;
     for (auto& ev : lib->ev) BSS_CUDA_LIB(cudaEventCreate(&ev));
-    BSS_CUDA_LIB(lib->d_blob.reserve(std::max<size_t>(4, blob.size() * 4)));
-    BSS_CUDA_LIB(lib->d_unit_off.reserve(unit_off.size() * 4));
-    if (!blob.empty()) BSS_CUDA_LIB(cudaMemcpy(lib->d_blob.ptr, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
-    BSS_CUDA_LIB(cudaMemcpy(lib->d_unit_off.ptr, unit_off.data(), unit_off.size() * 4, cudaMemcpyHostToDevice));
-    {
-        std::vector<uint8_t> rlen(std::max<uint32_t>(1, t->n_units), 0);
-        for (uint32_t u = 0; u < t->n_units; u++) rlen[u] = (uint8_t)(t->unit_comp_begin[u + 1] - t->unit_comp_begin[u] + 1);
-        BSS_CUDA_LIB(lib->d_unit_rlen.reserve(rlen.size()));
-        BSS_CUDA_LIB(cudaMemcpy(lib->d_unit_rlen.ptr, rlen.data(), rlen.size(), cudaMemcpyHostToDevice));
-        BSS_CUDA_LIB(lib->d_unit_probe.reserve(unit_probe.size() * 2));
-        BSS_CUDA_LIB(cudaMemcpy(lib->d_unit_probe.ptr, unit_probe.data(), unit_probe.size() * 2, cudaMemcpyHostToDevice));
-    }
-    BSS_CUDA_LIB(lib->h_totals.reserve(64));
-    BSS_CUDA_LIB(lib->d_totals.reserve(64));
+    auto upload = [&](DeviceBuffer& d, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e_ = d.reserve(std::max<size_t>(4, bytes));
+        if (e_ == cudaSuccess && bytes) e_ = cudaMemcpy(d.ptr, src, bytes, cudaMemcpyHostToDevice);
+        return e_;
+    };
+    BSS_CUDA_LIB(upload(lib->d_blob, built.blob.data(), built.blob.size() * 4));
+    BSS_CUDA_LIB(upload(lib->d_unit_off, built.unit_off.data(), built.unit_off.size() * 4));
+    BSS_CUDA_LIB(upload(lib->d_unit_rlen, built.unit_rlen.data(), built.unit_rlen.size()));
+    BSS_CUDA_LIB(upload(lib->d_unit_flags, built.unit_flags.data(), built.unit_flags.size()));
+    BSS_CUDA_LIB(upload(lib->d_unit_probe, built.unit_probe.data(), built.unit_probe.size() * 2));
+    BSS_CUDA_LIB(lib->h_totals.reserve(8 * bss::kTotalsWords));
+    BSS_CUDA_LIB(lib->d_totals.reserve(8 * bss::kTotalsWords));
 #undef BSS_CUDA_LIB
-    lib->dev.blob      = static_cast<const uint32_t*>(lib->d_blob.ptr);
-    lib->dev.unit_off  = static_cast<const uint32_t*>(lib->d_unit_off.ptr);
-    lib->dev.unit_rlen = static_cast<const uint8_t*>(lib->d_unit_rlen.ptr);
-    lib->dev.unit_probe = nullptr;
-    for (uint16_t p : unit_probe)
-        if (p != 0xFFFFu) { lib->dev.unit_probe = static_cast<const uint16_t*>(lib->d_unit_probe.ptr); break; }
-    lib->dev.n_units   = t->n_units;
-    lib->dev.n_symbols = (uint32_t)alphabet.size();
-    lib->dev.cmax      = cmax;
-    lib->dev.pair_rows = alphabet.size() <= bss::kPairAlphabet ? 1u : 0u;
-    lib->dev.list_density = 0.f;
-    if (!density.empty()) {
-        const size_t at = (density.size() - 1) * 98 / 100;
-        std::nth_element(density.begin(), density.begin() + at, density.end());
-        lib->dev.list_density = density[at];
-    }
+    lib->dev.blob       = static_cast<const uint32_t*>(lib->d_blob.ptr);
+    lib->dev.unit_off   = static_cast<const uint32_t*>(lib->d_unit_off.ptr);
+    lib->dev.unit_rlen  = static_cast<const uint8_t*>(lib->d_unit_rlen.ptr);
+    lib->dev.unit_flags = static_cast<const uint8_t*>(lib->d_unit_flags.ptr);
+    lib->dev.unit_probe = built.has_probes ? static_cast<const uint16_t*>(lib->d_unit_probe.ptr) : nullptr;
+    lib->dev.n_units    = t->n_units;
+    lib->dev.n_symbols  = (uint32_t)built.alphabet.size();
+    lib->dev.cmax       = built.cmax;
+    lib->dev.pair_rows  = built.alphabet.size() <= bss::kPairAlphabet ? 1u : 0u;
+    lib->dev.list_density = built.list_density;
     std::memset(lib->dev.alphabet, 0, sizeof lib->dev.alphabet);
-    std::copy(alphabet.begin(), alphabet.end(), lib->dev.alphabet);
+    std::copy(built.alphabet.begin(), built.alphabet.end(), lib->dev.alphabet);
     *out = lib;
     return BSS_OK;
+    });
 }
 
 void bss_library_destroy(bss_library* lib)
@@ -400,33 +280,73 @@ void bss_library_destroy(bss_library* lib)
     if (!lib) return;
     cudaSetDevice(lib->device);
     if (lib->own_stream) cudaStreamSynchronize(lib->own_stream);
+    // Result handles and queries that outlive the library keep their own buffers but lose their way back to it
+    // (their free functions then release instead of recycling).
+    detach_children(lib);
     if (lib->graph_exec) cudaGraphExecDestroy(lib->graph_exec);
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
-    lib->oneshot.storage.release(); lib->d_blob.release(); lib->d_unit_off.release(); lib->d_unit_rlen.release(); lib->d_unit_probe.release(); lib->d_prefilter.release(); lib->d_alive.release(); lib->d_lane_counts.release(); lib->d_heavy.release(); lib->d_counts.release(); lib->d_chunk_sites.release();
-    lib->d_idx_work.release(); lib->d_idx_hist.release(); lib->spare_idx_main.release(); lib->spare_idx_overlap.release();
-    lib->spare_idx_host_main.release(); lib->spare_idx_host_overlap.release(); lib->h_idx_totals.release();
-    lib->d_chunk_words.release(); lib->d_totals.release(); lib->d_seq_word_begin.release(); lib->h_totals.release();
-    lib->spare_records.release(); lib->spare_host.release();
+    for (DeviceBuffer* b : {&lib->oneshot.storage, &lib->d_blob, &lib->d_unit_off, &lib->d_unit_rlen, &lib->d_unit_probe, &lib->d_unit_flags, &lib->d_prefilter,
+                            &lib->d_alive, &lib->d_lane_counts, &lib->d_heavy, &lib->d_counts, &lib->d_chunks, &lib->d_wlist, &lib->d_alive_w,
+                            &lib->d_lane_counts_w, &lib->d_placements, &lib->d_idx_work, &lib->d_idx_hist, &lib->spare_idx_main, &lib->spare_idx_overlap,
+                            &lib->d_totals, &lib->d_seq_word_begin, &lib->spare_records})
+        b->release();
+    for (PinnedBuffer* b : {&lib->spare_idx_host_main, &lib->spare_idx_host_overlap, &lib->h_idx_totals, &lib->h_totals, &lib->spare_host}) b->release();
     if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
     delete lib;
 }
 
 int bss_library_set_stream(bss_library* lib, void* cuda_stream)
 {
+    return guarded([&]() -> int {
     if (!lib) return fail(BSS_ERR_INVALID, "null library");
     lib->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : lib->own_stream;
     return BSS_OK;
+    });
 }
 
 int bss_library_set_module_base(bss_library* lib, uint32_t base)
 {
+    return guarded([&]() -> int {
     if (!lib) return fail(BSS_ERR_INVALID, "null library");
     lib->dev.module_base = base;
     lib->dev_serial++;
     return BSS_OK;
+    });
 }
 
+int bss_library_set_tuning(bss_library* lib, int knob, int64_t value)
+{
+    return guarded([&]() -> int {
+    if (!lib) return fail(BSS_ERR_INVALID, "null library");
+    bss::Tuning& t = lib->tuning;
+    switch (knob) {
+    case BSS_TUNE_GROUP:
+        if (value >= 0 && value != 4 && value != 8 && value != 16 && value != 32) return fail(BSS_ERR_INVALID, "group must be 4, 8, 16 or 32");
+        t.group = value;
+        break;
+    case BSS_TUNE_UNITS_PER_CHUNK:
+        if (value == 0) return fail(BSS_ERR_INVALID, "units per chunk must be at least 1");
+        t.units_per_chunk = value;
+        break;
+    case BSS_TUNE_HEAVY_RANKS:
+        if (value == 0 || value > 0xFFFFFFFFll) return fail(BSS_ERR_INVALID, "heavy-item threshold out of range");
+        t.heavy_ranks = value;
+        break;
+    case BSS_TUNE_LIST_CAP:
+        if (value > 4096) return fail(BSS_ERR_INVALID, "list capacity above 4096");
+        t.list_cap = value;
+        break;
+    case BSS_TUNE_WINDOW: t.window = value; break;
+    case BSS_TUNE_WINDOW_STAGE: t.window_stage = value; break;
+    default: return fail(BSS_ERR_INVALID, "unknown tuning knob");
+    }
+    lib->dev_serial++;   // a cached launch graph was built for the old plan
+    return BSS_OK;
+    });
+}
+
+uint32_t bss_library_window_units(const bss_library* lib) { return lib ? lib->n_window_units : 0; }
 uint32_t bss_library_units(const bss_library* lib) { return lib ? lib->n_units : 0; }
 uint32_t bss_library_modules(const bss_library* lib) { return lib ? lib->n_modules : 0; }
 uint32_t bss_library_module_components(const bss_library* lib, uint32_t module)
@@ -437,6 +357,22 @@ uint32_t bss_library_module_components(const bss_library* lib, uint32_t module)
 }   // extern "C"
 
 namespace {
+
+// Resident queries: the host learns the widest band of the query (it waits for the upload anyway), so that a search
+// can leave out the passes no item will take and size the window kernel's shared memory.
+cudaError_t read_back_band(bss_library* lib, bss_query* q)
+{
+    std::vector<int32_t> band(q->dev.n_seqs);
+    cudaError_t          e = cudaSuccess;
+    if (!band.empty()) e = cudaMemcpyAsync(band.data(), q->dev.band, 4 * band.size(), cudaMemcpyDeviceToHost, lib->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(lib->stream);
+    if (e == cudaSuccess) {
+        int widest = -1;
+        for (int32_t b : band) widest = std::max(widest, (int)b);
+        q->known_band = widest;
+    }
+    return e;
+}
 
 // Validates the host buffers, (re)uses q's device storage and queues upload + occurrence
 // table + band on the library's stream. With `wait` the call returns once the query is resident.
@@ -461,14 +397,18 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     static uint64_t next_serial = 0;
     q->serial    = ++next_serial;
     q->device    = lib->device;
-    // one allocation: [seq_begin | mask_begin | band | occurrence table | masks | seqs]
+    // one allocation: [seq_begin | mask_begin | band | occurrence table | banded masks | masks | seqs]
     const uint32_t ns = lib->dev.n_symbols, occ_rows = ns + (lib->dev.pair_rows ? ns * ns : 0u);
     const uint32_t occ_stride = (max_len + 32) / 32 + bss::kOccPad;
     const bool     with_kmers = lib->dev.unit_probe != nullptr;
     const size_t   occ_words  = (size_t)n_seqs * occ_rows * occ_stride + (with_kmers ? (size_t)n_seqs * bss::kKmerWords : 0);
-    const size_t off_sb = 0, off_mb = off_sb + 8 * (size_t)(n_seqs + 1), off_band = off_mb + 8 * (size_t)(n_seqs + 1),
-                 off_occ = off_band + 4 * (((size_t)n_seqs + 3) & ~(size_t)3), off_mask = off_occ + 4 * ((occ_words + 3) & ~(size_t)3),
-                 off_seq = off_mask + 4 * total_mask, bytes = off_seq + total_len + 16;
+    // banded masks for the window walk: only where whole warps work on an item (make_plan's rule for 32-lane groups)
+    const uint64_t n_items_q   = (uint64_t)n_seqs * lib->n_units;
+    const bool     with_bmask  = lib->n_window_units > 0 && ((max_len + 32) / 32 > 16 || n_items_q <= (1u << 17));
+    const size_t   bmask_words = with_bmask ? (size_t)bss::kBandWordsMax * total_len : 0;
+    const size_t   off_sb = 0, off_mb = off_sb + 8 * (size_t)(n_seqs + 1), off_band = off_mb + 8 * (size_t)(n_seqs + 1),
+                 off_occ = off_band + 4 * (((size_t)n_seqs + 3) & ~(size_t)3), off_bmask = off_occ + 4 * ((occ_words + 3) & ~(size_t)3),
+                 off_mask = off_bmask + 4 * ((bmask_words + 3) & ~(size_t)3), off_seq = off_mask + 4 * total_mask, bytes = off_seq + total_len + 16;
     cudaError_t e = q->storage.reserve(bytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(query)");
     char* d = static_cast<char*>(q->storage.ptr);
@@ -486,6 +426,7 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     q->dev.seqs       = reinterpret_cast<const uint8_t*>(d + off_seq);
     q->dev.occ        = reinterpret_cast<const uint32_t*>(d + off_occ);
     q->dev.kmers      = with_kmers ? q->dev.occ + (size_t)n_seqs * occ_rows * occ_stride : nullptr;
+    q->dev.bmask      = with_bmask ? reinterpret_cast<const uint32_t*>(d + off_bmask) : nullptr;
     q->dev.occ_rows   = occ_rows;
     q->dev.occ_stride = occ_stride;
     q->dev.n_seqs     = n_seqs;
@@ -496,9 +437,11 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     // per-symbol (and per-symbol-pair) occurrence bit rows of every sequence, matched against by every unit
     if (e == cudaSuccess) e = bss::launch_occ(lib->dev, q->dev, reinterpret_cast<uint32_t*>(d + off_occ), const_cast<uint32_t*>(q->dev.kmers), st);
     // widest pair the mask allows, per sequence: bounds the window a tied component is searched in
-    if (e == cudaSuccess && !device_mask) e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), st);   // (a device-built mask gets its band afterwards)
+    if (e == cudaSuccess && !device_mask) e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), const_cast<uint32_t*>(q->dev.bmask), st);   // (a device-built mask gets its band afterwards)
     // (copies from pageable host memory are staged before cudaMemcpyAsync returns: sb / mb may go out of scope)
-    if (e == cudaSuccess && wait) e = cudaStreamSynchronize(st);
+    q->known_band = INT32_MIN;
+    if (e == cudaSuccess && wait && !device_mask) e = read_back_band(lib, q);
+    else if (e == cudaSuccess && wait) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "query upload");
     q->total_len      = total_len;
     q->h2d_bytes      = 16 * (uint64_t)(n_seqs + 1) + 4 * total_mask + total_len;
@@ -529,6 +472,7 @@ uint64_t pij_extent(uint32_t n, uint64_t row_stride, uint64_t col_stride) { retu
 int bss_pair_mask_device(bss_library* lib, const float* d_pij, uint32_t n, uint64_t row_stride, uint64_t col_stride, float theta,
                          uint32_t* d_mask, void* cuda_stream)
 {
+    return guarded([&]() -> int {
     int rc = check_pij_args(lib, d_pij, n, row_stride, col_stride);
     if (rc != BSS_OK) return rc;
     if (n && !d_mask) return fail(BSS_ERR_INVALID, "null argument");
@@ -536,10 +480,12 @@ int bss_pair_mask_device(bss_library* lib, const float* d_pij, uint32_t n, uint6
     BSS_CUDA(bss::launch_pair_mask(d_pij, n, row_stride, col_stride, theta, d_mask, lib->sm_count,
                                    cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : lib->stream));
     return BSS_OK;
+    });
 }
 
 int bss_pair_mask(bss_library* lib, const float* pij, uint32_t n, uint64_t row_stride, uint64_t col_stride, float theta, uint32_t* mask)
 {
+    return guarded([&]() -> int {
     int rc = check_pij_args(lib, pij, n, row_stride, col_stride);
     if (rc != BSS_OK) return rc;
     if (n == 0) return BSS_OK;
@@ -557,11 +503,13 @@ int bss_pair_mask(bss_library* lib, const float* pij, uint32_t n, uint64_t row_s
     d_mask.release();
     if (e != cudaSuccess) return cuda_fail(e, "bss_pair_mask");
     return BSS_OK;
+    });
 }
 
 int bss_query_create_pij(bss_library* lib, const char* seq, uint32_t n, const float* pij, uint64_t row_stride, uint64_t col_stride, float theta,
                          bss_query** out)
 {
+    return guarded([&]() -> int {
     if (!out) return fail(BSS_ERR_INVALID, "null argument");
     *out   = nullptr;
     int rc = check_pij_args(lib, pij, n, row_stride, col_stride);
@@ -579,8 +527,8 @@ int bss_query_create_pij(bss_library* lib, const char* seq, uint32_t n, const fl
         cudaError_t    e = d_pij.reserve(extent * 4);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_pij.ptr, pij, extent * 4, cudaMemcpyHostToDevice, lib->stream);
         if (e == cudaSuccess) e = bss::launch_pair_mask(static_cast<const float*>(d_pij.ptr), n, row_stride, col_stride, theta, const_cast<uint32_t*>(q->dev.masks), lib->sm_count, lib->stream);
-        if (e == cudaSuccess) e = bss::launch_band(q->dev, const_cast<int32_t*>(q->dev.band), lib->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(lib->stream);
+        if (e == cudaSuccess) e = bss::launch_band(q->dev, const_cast<int32_t*>(q->dev.band), const_cast<uint32_t*>(q->dev.bmask), lib->stream);
+        if (e == cudaSuccess) e = read_back_band(lib, q);
         d_pij.release();
         if (e != cudaSuccess) rc = cuda_fail(e, "bss_query_create_pij");
         q->h2d_bytes = 16 * 2 + extent * 4 + n;
@@ -590,13 +538,17 @@ int bss_query_create_pij(bss_library* lib, const char* seq, uint32_t n, const fl
         delete q;
         return rc;
     }
+    q->owner = lib;
+    lib->live_queries.push_back(q);
     *out = q;
     return BSS_OK;
+    });
 }
 
 int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
                      const uint64_t* mask_begin, bss_query** out)
 {
+    return guarded([&]() -> int {
     if (!out) return fail(BSS_ERR_INVALID, "null argument");
     *out         = nullptr;
     bss_query* q = new bss_query();
@@ -606,14 +558,31 @@ int bss_query_create(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
         delete q;
         return rc;
     }
+    q->owner = lib;
+    lib->live_queries.push_back(q);
     *out = q;
     return BSS_OK;
+    });
 }
 
 void bss_query_destroy(bss_query* q)
 {
     if (!q) return;
     cudaSetDevice(q->device);
+    if (q->owner) {
+        bss_library* lib = q->owner;
+        forget(lib->live_queries, q);
+        if (lib->pending.q == q) {   // a search of this query may still be running: let it end before its inputs go
+            cudaStreamSynchronize(lib->stream);
+            lib->pending.active = false;
+            lib->pending.q      = nullptr;
+        }
+        if (lib->graph_key.query_serial == q->serial && lib->graph_exec) {
+            cudaStreamSynchronize(lib->stream);
+            cudaGraphExecDestroy(lib->graph_exec);
+            lib->graph_exec = nullptr;
+        }
+    }
     q->storage.release();
     delete q;
 }
@@ -625,13 +594,16 @@ namespace {
 // count + scan, then the totals come back to the host. On success `plan` and `work` describe
 // the pending emit.
 // Validation, work decomposition and (grow-only) work buffers of a search: no stream operation.
-int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work)
+int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::Work& work, bool& ordinary)
 {
     if (q->n_symbols != lib->dev.n_symbols || q->pair_rows != lib->dev.pair_rows || std::memcmp(q->alphabet, lib->dev.alphabet, sizeof q->alphabet))
         return fail(BSS_ERR_INVALID, "the query was created for a library with a different pattern alphabet");
     BSS_CUDA(cudaSetDevice(lib->device));
-    plan = bss::make_plan(lib->dev, q->dev.n_seqs, q->dev.max_len, lib->sm_count);
+    plan = bss::make_plan(lib->dev, q->dev, lib->sm_count, lib->tuning, lib->n_window_units, q->known_band);
     if (plan.smem_bytes_emit > 200 * 1024) return fail(BSS_ERR_LIMIT, "query too long for the shared-memory working set");
+    // The ordinary passes can be left out when the host knows that every item takes the window walk (or ends in the
+    // route kernel): a library of window-walk units on a query whose widest band it has read back.
+    ordinary = !(plan.window && lib->n_window_units == lib->n_units && q->known_band != INT32_MIN && q->known_band <= bss::kWindowBandMax);
     const uint64_t n_items = (uint64_t)q->dev.n_seqs * lib->n_units;
     if (n_items >= 0xFFFFFFFFull) return fail(BSS_ERR_LIMIT, "more than 2^32 (sequence, unit) items in one search: split the batch");
     BSS_CUDA(lib->d_counts.reserve(std::max<uint64_t>(4, n_items * 4)));
@@ -649,17 +621,26 @@ int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::W
     work.heavy_ranks      = work.heavy_items + 1024;
     work.task_sites       = work.heavy_ranks + 1024;
     work.task_lane_counts = work.task_sites + 1024 * 256;
-    BSS_CUDA(lib->d_chunk_sites.reserve(8 * (size_t)(plan.n_chunks + 1)));
-    BSS_CUDA(lib->d_chunk_words.reserve(8 * (size_t)(plan.n_chunks + 1)));
+    // chunk totals: [sites | words], zeroed per search (the passes add to them)
+    BSS_CUDA(lib->d_chunks.reserve(16 * (size_t)(plan.n_chunks + 1)));
     BSS_CUDA(lib->d_seq_word_begin.reserve(8 * (size_t)(q->dev.n_seqs + 1)));
     work.prefilter = nullptr;
-    if (lib->dev.unit_probe && q->dev.kmers) {
+    if (plan.window || (lib->dev.unit_probe && q->dev.kmers)) {
         BSS_CUDA(lib->d_prefilter.reserve(4 * ((n_items + 31) / 32) + 4));
         work.prefilter = static_cast<uint32_t*>(lib->d_prefilter.ptr);
     }
+    work.wlist = work.alive_w = work.lane_counts_w = nullptr;
+    if (plan.window) {
+        BSS_CUDA(lib->d_wlist.reserve(std::max<uint64_t>(4, n_items * 4)));
+        BSS_CUDA(lib->d_alive_w.reserve(std::max<uint64_t>(4, n_items * 4)));
+        BSS_CUDA(lib->d_lane_counts_w.reserve(std::max<uint64_t>(4, n_items * 128)));
+        work.wlist         = static_cast<uint32_t*>(lib->d_wlist.ptr);
+        work.alive_w       = static_cast<uint32_t*>(lib->d_alive_w.ptr);
+        work.lane_counts_w = static_cast<uint32_t*>(lib->d_lane_counts_w.ptr);
+    }
     work.counts         = static_cast<uint32_t*>(lib->d_counts.ptr);
-    work.chunk_sites    = static_cast<uint64_t*>(lib->d_chunk_sites.ptr);
-    work.chunk_words    = static_cast<uint64_t*>(lib->d_chunk_words.ptr);
+    work.chunk_sites    = static_cast<uint64_t*>(lib->d_chunks.ptr);
+    work.chunk_words    = work.chunk_sites + plan.n_chunks + 1;
     work.totals         = static_cast<uint64_t*>(lib->d_totals.ptr);
     work.seq_word_begin = static_cast<uint64_t*>(lib->d_seq_word_begin.ptr);
     lib->stats          = bss_stats{};
@@ -674,13 +655,14 @@ cudaError_t record_event(bss_library* lib, int i, bool capturing)
 }
 
 // Queues the count pass (+ heavy count) and the scan.
-int enqueue_count(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, bool capturing = false)
+int enqueue_count(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, bool ordinary, bool capturing = false)
 {
     cudaStream_t st = lib->stream;
-    BSS_CUDA(cudaMemsetAsync(work.totals, 0, 48, st));
+    BSS_CUDA(cudaMemsetAsync(work.totals, 0, 8 * bss::kTotalsWords, st));
+    BSS_CUDA(cudaMemsetAsync(work.chunk_sites, 0, 16 * (size_t)(plan.n_chunks + 1), st));
     BSS_CUDA(cudaMemsetAsync(work.seq_word_begin, 0, 8 * (size_t)(q->dev.n_seqs + 1), st));
     BSS_CUDA(record_event(lib, 0, capturing));
-    BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, lib->sm_count, st));
+    BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, ordinary, lib->sm_count, st));
     BSS_CUDA(record_event(lib, 1, capturing));
     BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));
     BSS_CUDA(record_event(lib, 2, capturing));
@@ -688,31 +670,55 @@ int enqueue_count(bss_library* lib, const bss_query* q, const bss::Plan& plan, c
 }
 
 // What the count pass found, once the copy queued by enqueue_totals has landed.
-int parse_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, uint64_t& n_words, uint64_t& n_sites)
+constexpr size_t kTotalsFetch = 64;   // bytes of the totals the host reads: [0] .. [7]
+
+// kernels of the count side of a search: route / prefilter, ordinary count, heavy count, window count, scan
+uint32_t count_launches(const bss_library* lib, const bss_query* q, const bss::Plan& plan, bool ordinary)
+{
+    if (!plan.n_chunks) return 1u;   // the scan alone
+    uint32_t n = 1u;
+    if (plan.window || (lib->dev.unit_probe && q->dev.kmers)) n++;
+    if (ordinary) n += 1u + (plan.group == 32 && plan.list_cap ? 1u : 0u);
+    if (plan.window) n++;
+    return n;
+}
+
+// emit, heavy emit, window emit when they are queued without knowing the sizes
+uint32_t blind_emit_launches(const bss::Plan& plan, bool ordinary)
+{
+    return (ordinary ? 1u + (plan.group == 32 && plan.list_cap ? 1u : 0u) : 0u) + (plan.window ? 1u : 0u);
+}
+
+int parse_totals(bss_library* lib, const bss_query* q, const bss::Plan& plan, bool ordinary, uint64_t& n_words, uint64_t& n_sites)
 {
     const uint64_t* tot = static_cast<const uint64_t*>(lib->h_totals.ptr);
     n_words             = tot[0];
     n_sites             = tot[1];
     lib->n_alive        = (uint32_t)tot[3];
     lib->n_heavy        = (uint32_t)std::min<uint64_t>(tot[4], 1024);
-    // prefilter (when the library has k-mer probes), count, heavy count (32-lane groups), scan
-    lib->stats.kernel_launches   = (plan.n_chunks ? 1u : 0u) + 1u + (plan.group == 32 && plan.list_cap && plan.n_chunks ? 1u : 0u) +
-                                 (lib->dev.unit_probe && q->dev.kmers && plan.n_chunks ? 1u : 0u);
+    lib->n_alive_w      = (uint32_t)tot[5];
+    lib->stats.kernel_launches   = count_launches(lib, q, plan, ordinary);
     lib->stats.placements_tested = q->total_len * lib->n_units;
     lib->stats.n_sites           = n_sites;
     lib->stats.n_words           = n_words;
-    lib->stats.d2h_bytes         = 40;
+    lib->stats.d2h_bytes         = kTotalsFetch;
+    lib->stats.window_items      = tot[6];
+    lib->stats.ordinary_items    = plan.window ? tot[7] : (uint64_t)q->dev.n_seqs * lib->n_units;
+    lib->stats.heavy_items       = tot[4];
     if (tot[2] & 1) return fail(BSS_ERR_COUNT, "a unit has 2^32 or more sites on one sequence");
     return BSS_OK;
 }
 
-int run_emit(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, uint32_t* d_records, uint64_t n_words)
+int run_emit(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, bool ordinary, uint32_t* d_records, uint64_t n_words)
 {
     cudaStream_t st = lib->stream;
     if (n_words && plan.n_chunks) {
-        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, lib->n_alive, lib->n_heavy, ~0ull, lib->sm_count, st));
-        if (lib->n_heavy) lib->stats.kernel_launches++;
-        lib->stats.kernel_launches++;
+        // sizes known on the host: only the passes that have something to write
+        bss::Plan p = plan;
+        if (!lib->n_alive_w) p.window = 0;
+        const bool ord = ordinary && (lib->n_alive || lib->n_heavy);
+        BSS_CUDA(bss::launch_emit(lib->dev, q->dev, p, work, d_records, lib->n_alive, lib->n_heavy, ~0ull, ord, lib->sm_count, st));
+        lib->stats.kernel_launches += (ord ? 1u + (lib->n_heavy ? 1u : 0u) : 0u) + (p.window ? 1u : 0u);
     }
     BSS_CUDA(cudaEventRecord(lib->ev[3], st));
     return BSS_OK;
@@ -734,17 +740,20 @@ extern "C" {
 
 int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites** out)
 {
+    return guarded([&]() -> int {
     if (!lib || !q || !out) return fail(BSS_ERR_INVALID, "null argument");
     *out = nullptr;
     if (q->device != lib->device) return fail(BSS_ERR_INVALID, "query and library live on different devices");
     bss::Plan plan;
     bss::Work work;
     uint64_t  n_words = 0, n_sites = 0;
-    int       rc = prepare_search(lib, q, plan, work);
+    bool      ordinary = true;
+    int       rc = prepare_search(lib, q, plan, work, ordinary);
     if (rc != BSS_OK) return rc;
 
     bss_sites* s = new bss_sites();
     s->lib       = lib;
+    lib->live_sites.push_back(s);
     std::swap(s->d_records, lib->spare_records);
     std::swap(s->h_records, lib->spare_host);
     auto bail = [&](int code) { bss_sites_free(s); return code; };
@@ -755,27 +764,27 @@ int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites*
     // take their sizes from device memory), so the host's wait for the totals overlaps them.
     const uint64_t guess_words = s->d_records.cap / 4;
     bool           emitted     = false;
-    rc = enqueue_count(lib, q, plan, work);
+    rc = enqueue_count(lib, q, plan, work, ordinary);
     if (rc != BSS_OK) return bail(rc);
     if (guess_words >= 16 && plan.n_chunks) {
-        e = bss::launch_emit(lib->dev, q->dev, plan, work, static_cast<uint32_t*>(s->d_records.ptr), 0xFFFFFFFFu, 0, guess_words, lib->sm_count, st);
+        e = bss::launch_emit(lib->dev, q->dev, plan, work, static_cast<uint32_t*>(s->d_records.ptr), 0xFFFFFFFFu, 0, guess_words, ordinary, lib->sm_count, st);
         if (e == cudaSuccess) e = cudaEventRecord(lib->ev[3], st);
         if (e != cudaSuccess) return bail(cuda_fail(e, "emit launch"));
         emitted = true;
     }
-    e = cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 40, cudaMemcpyDeviceToHost, st);
+    e = cudaMemcpyAsync(lib->h_totals.ptr, work.totals, kTotalsFetch, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return bail(cuda_fail(e, "count pass"));
-    rc = parse_totals(lib, q, plan, n_words, n_sites);
+    rc = parse_totals(lib, q, plan, ordinary, n_words, n_sites);
     if (rc != BSS_OK) return bail(rc);
     s->n_words = n_words;
     s->n_sites = n_sites;
     if (emitted && n_words <= guess_words) {
-        lib->stats.kernel_launches += 1 + (plan.group == 32 && plan.list_cap ? 1 : 0);   // emit, heavy emit (queued blind)
+        lib->stats.kernel_launches += blind_emit_launches(plan, ordinary);   // emit, heavy emit, window emit (queued blind)
     } else {   // first search of this size: allocate, then emit with the sizes now known on the host
         e = s->d_records.reserve(std::max<uint64_t>(16, n_words * 4));
         if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(records)"));
-        rc = run_emit(lib, q, plan, work, static_cast<uint32_t*>(s->d_records.ptr), n_words);
+        rc = run_emit(lib, q, plan, work, ordinary, static_cast<uint32_t*>(s->d_records.ptr), n_words);
         if (rc != BSS_OK) return bail(rc);
     }
     s->seq_word_begin.assign(q->dev.n_seqs + 1, 0);
@@ -795,19 +804,23 @@ int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites*
     if (rc != BSS_OK) return bail(rc);
     *out = s;
     return BSS_OK;
+    });
 }
 
 int bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_records, uint64_t capacity_words,
                           uint64_t* d_seq_word_begin, uint64_t* n_words_out, uint64_t* n_sites_out)
 {
+    return guarded([&]() -> int {
     if (!n_words_out || !n_sites_out) return fail(BSS_ERR_INVALID, "null argument");
     const int rc = bss_search_query_into_async(lib, q, d_records, capacity_words, d_seq_word_begin);
     if (rc != BSS_OK) return rc;
     return bss_search_wait(lib, n_words_out, n_sites_out);
+    });
 }
 
 int bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* d_records, uint64_t capacity_words, uint64_t* d_seq_word_begin)
 {
+    return guarded([&]() -> int {
     if (!lib || !q) return fail(BSS_ERR_INVALID, "null argument");
     if (q->device != lib->device) return fail(BSS_ERR_INVALID, "query and library live on different devices");
     bss::Plan plan;
@@ -817,19 +830,21 @@ int bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* 
     // would not fit `capacity_words`. While the arguments stay the same (a query stream searched
     // into the same buffer, as in a benchmark loop or a sharded exchange) the whole sequence is
     // replayed as one CUDA graph: one launch call instead of a dozen.
-    int rc = prepare_search(lib, q, plan, work);
+    bool ordinary = true;
+    int  rc = prepare_search(lib, q, plan, work, ordinary);
     if (rc != BSS_OK) return rc;
     cudaStream_t st      = lib->stream;
     const bool   emitting = plan.n_chunks && d_records && capacity_words;
     auto enqueue = [&](bool capturing) -> int {
-        int r = enqueue_count(lib, q, plan, work, capturing);
+        int r = enqueue_count(lib, q, plan, work, ordinary, capturing);
         if (r != BSS_OK) return r;
-        if (emitting) {
-            BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, 0xFFFFFFFFu, 0, capacity_words, lib->sm_count, st));
-            if (d_seq_word_begin) BSS_CUDA(bss::launch_guarded_copy(work, capacity_words, d_seq_word_begin, q->dev.n_seqs + 1, st));
-        }
+        if (emitting) BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, 0xFFFFFFFFu, 0, capacity_words, ordinary, lib->sm_count, st));
+        // The per-sequence offsets (their last entry is the number of record words) always reach the caller's header,
+        // also when the records did not fit: a sharded exchange behind this search then sees the true count on every
+        // rank and raises its overflow flag instead of forwarding a stale one.
+        if (d_seq_word_begin && plan.n_chunks) BSS_CUDA(bss::launch_offsets_copy(work, d_seq_word_begin, q->dev.n_seqs + 1, st));
         BSS_CUDA(record_event(lib, 3, capturing));
-        BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, 40, cudaMemcpyDeviceToHost, st));
+        BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, kTotalsFetch, cudaMemcpyDeviceToHost, st));
         return BSS_OK;
     };
     bool launched = false;
@@ -838,7 +853,8 @@ int bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* 
         key.query_serial = q->serial; key.capacity = capacity_words; key.dev_serial = lib->dev_serial;
         key.records = d_records; key.seq_out = d_seq_word_begin; key.stream = st; key.counts = work.counts; key.alive = work.alive;
         key.lanes = work.lane_counts; key.heavy = work.heavy_items; key.chunk_sites = work.chunk_sites; key.chunk_words = work.chunk_words;
-        key.seq_begin = work.seq_word_begin; key.prefilter = work.prefilter;
+        key.seq_begin = work.seq_word_begin; key.prefilter = work.prefilter; key.wlist = work.wlist; key.alive_w = work.alive_w;
+        key.lanes_w = work.lane_counts_w;
         if (!lib->graph_exec || !(key == lib->graph_key)) {
             if (lib->graph_exec) { cudaGraphExecDestroy(lib->graph_exec); lib->graph_exec = nullptr; }
             cudaGraph_t graph = nullptr;
@@ -874,11 +890,14 @@ int bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* 
     lib->pending.plan        = plan;
     lib->pending.capacity    = capacity_words;
     lib->pending.seq_out     = d_seq_word_begin;
+    lib->pending.ordinary    = ordinary;
     return BSS_OK;
+    });
 }
 
 int bss_search_wait(bss_library* lib, uint64_t* n_words_out, uint64_t* n_sites_out)
 {
+    return guarded([&]() -> int {
     if (!lib) return fail(BSS_ERR_INVALID, "null argument");
     if (!lib->pending.active) return fail(BSS_ERR_INVALID, "no search is pending on this library");
     lib->pending.active = false;
@@ -887,33 +906,39 @@ int bss_search_wait(bss_library* lib, uint64_t* n_words_out, uint64_t* n_sites_o
     uint64_t                    n_words = 0, n_sites = 0;
     BSS_CUDA(cudaSetDevice(lib->device));
     BSS_CUDA(cudaStreamSynchronize(st));
-    int rc = parse_totals(lib, p.q, p.plan, n_words, n_sites);
+    int rc = parse_totals(lib, p.q, p.plan, p.ordinary, n_words, n_sites);
     if (n_words_out) *n_words_out = n_words;
     if (n_sites_out) *n_sites_out = n_sites;
     if (rc != BSS_OK) return rc;
     if (n_words > p.capacity || (n_words && !p.has_records)) return fail(BSS_ERR_OVERFLOW, "output buffer too small");
-    if (p.seq_out && !p.emitting) {   // nothing was queued for the output: the offsets are all zero
+    if (p.seq_out && !p.plan.n_chunks) {   // an empty library or query: nothing was queued, the offsets are all zero
         BSS_CUDA(cudaMemsetAsync(p.seq_out, 0, 8 * (size_t)(p.q->dev.n_seqs + 1), st));
         BSS_CUDA(cudaStreamSynchronize(st));
     }
-    if (p.emitting) lib->stats.kernel_launches += 1 + (p.plan.group == 32 && p.plan.list_cap ? 1 : 0) + (p.seq_out ? 1 : 0);   // emit, heavy emit, offsets copy
+    if (p.emitting) lib->stats.kernel_launches += blind_emit_launches(p.plan, p.ordinary);   // emit, heavy emit, window emit
+    if (p.seq_out && p.plan.n_chunks) lib->stats.kernel_launches++;                          // offsets copy
     return finish_stats(lib);
+    });
 }
 
 int bss_gather_cut(bss_library* lib, const uint32_t* d_blocks, uint32_t world, uint64_t block_words, uint32_t header_words, uint32_t* d_out,
                    uint64_t* d_counts, uint32_t* d_overflow, void* cuda_stream)
 {
+    return guarded([&]() -> int {
     if (!lib || !d_blocks || !d_out || !d_counts || !d_overflow) return fail(BSS_ERR_INVALID, "null argument");
-    if (header_words < 2 || (header_words & 1) || block_words < header_words) return fail(BSS_ERR_INVALID, "bad block layout");
+    if (header_words < 2 || (header_words & 1) || (block_words & 1) || block_words < header_words)
+        return fail(BSS_ERR_INVALID, "bad block layout (header and block sizes must be even: the counts are 8-byte words)");
     BSS_CUDA(cudaSetDevice(lib->device));
     BSS_CUDA(bss::launch_gather_cut(d_blocks, world, block_words, header_words, d_out, d_counts, d_overflow,
                                     cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : lib->stream));
     return BSS_OK;
+    });
 }
 
 int bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
                      const uint64_t* mask_begin, bss_sites** out)
 {
+    return guarded([&]() -> int {
     if (!out) return fail(BSS_ERR_INVALID, "null argument");
     *out = nullptr;
     if (!lib) return fail(BSS_ERR_INVALID, "null argument");
@@ -923,13 +948,16 @@ int bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const 
     rc = bss_search_query(lib, q, 1, out);
     if (rc == BSS_OK) lib->stats.h2d_bytes = q->h2d_bytes;
     return rc;
+    });
 }
 
 int bss_search(bss_library* lib, const char* seq, uint32_t n, const uint32_t* mask, bss_sites** out)
 {
+    return guarded([&]() -> int {
     const uint64_t seq_begin[2]  = {0, n};
     const uint64_t mask_begin[2] = {0, (uint64_t)n * ((n + 31) / 32)};
     return bss_search_batch(lib, 1, seq, seq_begin, mask, mask_begin, out);
+    });
 }
 
 uint64_t        bss_sites_count(const bss_sites* s) { return s ? s->n_sites : 0; }
@@ -941,8 +969,9 @@ const uint64_t* bss_sites_seq_word_begin(const bss_sites* s) { return s ? s->seq
 void bss_sites_free(bss_sites* s)
 {
     if (!s) return;
-    if (s->lib) {
+    if (s->lib) {   // (null once the library has been destroyed: the handle then only releases its own buffers)
         cudaSetDevice(s->lib->device);
+        forget(s->lib->live_sites, s);
         // keep the largest buffers around for the next search
         if (s->d_records.cap > s->lib->spare_records.cap) std::swap(s->d_records, s->lib->spare_records);
         if (s->h_records.cap > s->lib->spare_host.cap) std::swap(s->h_records, s->lib->spare_host);
@@ -952,23 +981,10 @@ void bss_sites_free(bss_sites* s)
     delete s;
 }
 
-}   // extern "C"
-
-struct bss_site_index {
-    bss_library* lib = nullptr;
-    uint32_t     n = 0, launches = 0;
-    float        ms = 0.0f;
-    bool         fetched = false;
-    DeviceBuffer d_main, d_overlap;
-    PinnedBuffer h_main, h_overlap;
-    uint64_t     offset[BSS_IDX_SECTIONS] = {}, count[BSS_IDX_SECTIONS] = {};   // in u32 elements; OVERLAP_VARS lives in its own buffer
-};
-
-extern "C" {
-
 int bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, const uint32_t* d_records, int c3_rule, int fetch,
                          bss_site_index** out)
 {
+    return guarded([&]() -> int {
     if (!lib || !out) return fail(BSS_ERR_INVALID, "null argument");
     *out = nullptr;
     if (!q) q = &lib->oneshot;   // the query of the host-buffer entry points (bss_search, bss_search_batch)
@@ -1009,6 +1025,7 @@ int bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, con
     }
     bss_site_index* x = new bss_site_index();
     x->lib = lib;
+    lib->live_indexes.push_back(x);
     x->n   = n;
     std::swap(x->d_main, lib->spare_idx_main);
     std::swap(x->d_overlap, lib->spare_idx_overlap);
@@ -1094,6 +1111,7 @@ int bss_site_index_build(bss_library* lib, const bss_query* q, uint32_t seq, con
     cudaEventDestroy(ev1);
     *out = x;
     return BSS_OK;
+    });
 }
 
 uint64_t bss_site_index_count(const bss_site_index* x, int section)
@@ -1121,8 +1139,9 @@ uint32_t bss_site_index_launches(const bss_site_index* x) { return x ? x->launch
 void bss_site_index_free(bss_site_index* x)
 {
     if (!x) return;
-    if (x->lib) {
+    if (x->lib) {   // (null once the library has been destroyed)
         cudaSetDevice(x->lib->device);
+        forget(x->lib->live_indexes, x);
         // keep the largest buffers around for the next build
         if (x->d_main.cap > x->lib->spare_idx_main.cap) std::swap(x->d_main, x->lib->spare_idx_main);
         if (x->d_overlap.cap > x->lib->spare_idx_overlap.cap) std::swap(x->d_overlap, x->lib->spare_idx_overlap);
@@ -1136,8 +1155,39 @@ void bss_site_index_free(bss_site_index* x)
     delete x;
 }
 
+int bss_placements_enumerated(bss_library* lib, const bss_query* q, uint64_t* placements)
+{
+    return guarded([&]() -> int {
+    if (!lib || !placements) return fail(BSS_ERR_INVALID, "null argument");
+    if (!q) q = &lib->oneshot;
+    if (q->device != lib->device) return fail(BSS_ERR_INVALID, "query and library live on different devices");
+    if (q->n_symbols != lib->dev.n_symbols || q->pair_rows != lib->dev.pair_rows || std::memcmp(q->alphabet, lib->dev.alphabet, sizeof q->alphabet))
+        return fail(BSS_ERR_INVALID, "the query was created for a library with a different pattern alphabet");
+    if (lib->pending.active) return fail(BSS_ERR_INVALID, "a search is pending on this library: call bss_search_wait first");
+    BSS_CUDA(cudaSetDevice(lib->device));
+    *placements = 0;
+    const bss::Plan plan = bss::make_plan(lib->dev, q->dev, lib->sm_count, lib->tuning, 0, INT32_MIN);
+    if (4u * (bss::kThreads / 32) * (bss::kBlobStage + 2 * lib->dev.cmax * (plan.W + plan.WS)) > 200u * 1024u)
+        return fail(BSS_ERR_LIMIT, "query too long for the shared-memory working set");
+    // per-warp scratch in global memory: as many warps as 256 MB allow, at most 8 per SM
+    const size_t per_warp = bss::placements_words_per_warp(q->dev.max_len);
+    uint32_t     ctas     = (uint32_t)lib->sm_count * 2u;
+    while (ctas > 1 && (size_t)ctas * (bss::kThreads / 32) * per_warp * 8 > ((size_t)256 << 20)) ctas /= 2;
+    BSS_CUDA(lib->d_placements.reserve(8 + (size_t)ctas * (bss::kThreads / 32) * per_warp * 8));
+    unsigned long long* total   = static_cast<unsigned long long*>(lib->d_placements.ptr);
+    uint64_t*           scratch = static_cast<uint64_t*>(lib->d_placements.ptr) + 1;
+    BSS_CUDA(cudaMemsetAsync(total, 0, 8, lib->stream));
+    BSS_CUDA(bss::launch_placements(lib->dev, q->dev, plan, scratch, per_warp, ctas, total, lib->stream));
+    BSS_CUDA(cudaMemcpyAsync(placements, total, 8, cudaMemcpyDeviceToHost, lib->stream));
+    BSS_CUDA(cudaStreamSynchronize(lib->stream));
+    lib->stats.placements_enumerated = *placements;
+    return BSS_OK;
+    });
+}
+
 int bss_measure_int_issue(bss_library* lib, double* thread_ops_per_s)
 {
+    return guarded([&]() -> int {
     if (!lib || !thread_ops_per_s) return fail(BSS_ERR_INVALID, "null argument");
     BSS_CUDA(cudaSetDevice(lib->device));
     BSS_CUDA(lib->d_idx_work.reserve(64));
@@ -1164,13 +1214,16 @@ int bss_measure_int_issue(bss_library* lib, double* thread_ops_per_s)
     cudaEventDestroy(e1);
     *thread_ops_per_s = best;
     return BSS_OK;
+    });
 }
 
 int bss_last_stats(const bss_library* lib, bss_stats* out)
 {
+    return guarded([&]() -> int {
     if (!lib || !out) return fail(BSS_ERR_INVALID, "null argument");
     *out = lib->stats;
     return BSS_OK;
+    });
 }
 
 }   // extern "C"

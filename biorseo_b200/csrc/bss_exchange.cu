@@ -160,6 +160,7 @@ extern "C" {
 
 int bss_exchange_create(int device, uint32_t world, uint32_t rank, uint64_t capacity_words, uint32_t header_words, bss_exchange** out)
 {
+    return bss::guarded([&]() -> int {
     if (!out) return bss::set_error(BSS_ERR_INVALID, "null argument");
     *out = nullptr;
     if (world < 1 || world > 16 || rank >= world || header_words < 2 || (header_words & 1)) return bss::set_error(BSS_ERR_INVALID, "bad exchange geometry");
@@ -187,10 +188,12 @@ int bss_exchange_create(int device, uint32_t world, uint32_t rank, uint64_t capa
     }
     *out = x;
     return BSS_OK;
+    });
 }
 
 int bss_exchange_handle(const bss_exchange* x, void* handle64)
 {
+    return bss::guarded([&]() -> int {
     if (!x || !handle64) return bss::set_error(BSS_ERR_INVALID, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
@@ -199,10 +202,12 @@ int bss_exchange_handle(const bss_exchange* x, void* handle64)
     if (e != cudaSuccess) return bss::set_error(BSS_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
     std::memcpy(handle64, &h, 64);
     return BSS_OK;
+    });
 }
 
 int bss_exchange_open(bss_exchange* x, const void* handles)
 {
+    return bss::guarded([&]() -> int {
     if (!x || !handles) return bss::set_error(BSS_ERR_INVALID, "null argument");
     if (x->opened) return bss::set_error(BSS_ERR_INVALID, "exchange already opened");
     cudaError_t e = cudaSetDevice(x->device);
@@ -223,6 +228,7 @@ int bss_exchange_open(bss_exchange* x, const void* handles)
     }
     x->opened = true;
     return BSS_OK;
+    });
 }
 
 uint32_t* bss_exchange_block(const bss_exchange* x) { return x ? x->block : nullptr; }
@@ -230,6 +236,7 @@ uint64_t  bss_exchange_capacity(const bss_exchange* x) { return x ? x->capacity 
 
 int bss_exchange_run_async(bss_exchange* x, void* cuda_stream, const uint32_t** d_out, const uint64_t** d_result)
 {
+    return bss::guarded([&]() -> int {
     if (!x) return bss::set_error(BSS_ERR_INVALID, "null argument");
     if (!x->opened) return bss::set_error(BSS_ERR_INVALID, "exchange not opened");
     cudaError_t e = cudaSetDevice(x->device);
@@ -252,6 +259,7 @@ int bss_exchange_run_async(bss_exchange* x, void* cuda_stream, const uint32_t** 
     if (d_out) *d_out = a.local_out + (x->epoch & 1) * (uint64_t)x->world * x->capacity;
     if (d_result) *d_result = x->result;
     return BSS_OK;
+    });
 }
 
 void bss_exchange_destroy(bss_exchange* x)

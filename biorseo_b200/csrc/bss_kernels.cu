@@ -32,8 +32,10 @@
 //                (item, block of ranks) tasks spread over a GPU-wide grid, with subtree pruning.
 // Not a contraction: integer/bit work only, no tensor cores.
 #include "bss_device.cuh"
+#include "bss_window_walk.h"
 
-#include <cstdlib>
+#include <algorithm>
+
 
 #ifndef BSS_MIN_CTAS
 #define BSS_MIN_CTAS 8   // resident CTAs per SM the register allocation is held to
@@ -1021,6 +1023,8 @@ __device__ __forceinline__ SeqCtx load_seq(const DevLibrary& lib, const DevQuery
     return sq;
 }
 
+#include "bss_window.cuh"
+
 // Count pass (EMIT = false): one CTA per chunk = (sequence, contiguous unit range); the groups
 // of the CTA draw units from the chunk's counter, write the site count of every item, add the
 // items that have sites to the alive list, and the CTA leaves the chunk's totals behind.
@@ -1047,6 +1051,7 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
 {
     constexpr bool EMIT = (MODE & 1) != 0, HEAVY = MODE >= 2;
     if (HEAVY && work.totals[4] == 0) return;   // the usual case: nothing was parked
+    if (MODE == kModeCount && plan.window && work.totals[7] == 0) return;   // every item went to the window pass or ended in route_kernel
     if (EMIT) {
         // Emit passes queued behind the count pass without a host round trip: the sizes come from
         // device memory, and nothing is written when the records would not fit the caller's buffer.
@@ -1346,9 +1351,10 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
             atomicAdd(&cta_words, (unsigned long long)my_words);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            work.chunk_sites[chunk] = cta_sites;
-            work.chunk_words[chunk] = cta_words;
+        // (added, not stored: the window pass and the heavy passes account for their items in the same totals, zeroed per search)
+        if (threadIdx.x == 0 && cta_sites) {
+            atomicAdd((unsigned long long*)&work.chunk_sites[chunk], cta_sites);
+            atomicAdd((unsigned long long*)&work.chunk_words[chunk], cta_words);
         }
     }
 }
@@ -1553,19 +1559,20 @@ cudaError_t launch_search(const DevLibrary& lib, const DevQuery& q, const Plan& 
 
 }   // namespace
 
-Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_count)
+Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tuning& tuning, uint32_t n_window_units, int known_band)
 {
+    const uint32_t n_seqs = q.n_seqs, max_len = q.max_len;
     Plan p{};
     p.W  = (max_len + 32) / 32;
     p.WS = (p.W + 31) / 32;
     // Lanes per item. Short sequences in large batches: narrow groups, several items per warp (most
     // items end in the match phase). Otherwise a whole warp per item, which also enables the
-    // rank-space walk.
+    // rank-space walk and the window walk.
     const uint64_t n_items = (uint64_t)n_seqs * lib.n_units;
     p.group = (p.W > 16 || n_items <= (1u << 17)) ? 32 : p.W <= 4 ? 4 : p.W <= 8 ? 8 : 16;
-    // (BSS_DEBUG_* environment variables: developer knobs for experiments and for tests that force the rarely
-    //  taken paths — narrow groups, tiny list capacity, heavy-item blocks — on small inputs; not a tuning interface)
-    if (const char* dbg = getenv("BSS_DEBUG_GROUP")) p.group = (uint32_t)atoi(dbg);
+    // (tuning: developer knobs for experiments and for tests that force the rarely taken paths — narrow groups,
+    //  tiny list capacity, heavy-item blocks — on small inputs; bss_library_set_tuning validates them)
+    if (tuning.group > 0) p.group = (uint32_t)tuning.group;
     const uint32_t groups = kThreads / p.group;
     // Several waves of CTAs, so that the hardware scheduler evens out chunks of unequal cost;
     // a chunk holds at least one item per group.
@@ -1574,7 +1581,7 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
     uint32_t       upc     = (lib.n_units + per_seq - 1) / (per_seq ? per_seq : 1);
     upc                    = ((upc + groups - 1) / groups) * groups;
     if (upc < groups) upc = groups;
-    if (const char* dbg = getenv("BSS_DEBUG_UPC")) upc = (uint32_t)atoi(dbg);
+    if (tuning.units_per_chunk > 0) upc = (uint32_t)tuning.units_per_chunk;
     if (upc > kMaxChunkUnits) upc = kMaxChunkUnits;
     p.units_per_chunk = upc;
     p.chunks_per_seq  = lib.n_units ? (lib.n_units + upc - 1) / upc : 0;
@@ -1588,15 +1595,27 @@ Plan make_plan(const DevLibrary& lib, uint32_t n_seqs, uint32_t max_len, int sm_
         p.list_cap        = want > 1024.0 ? 1024u : want < 64.0 ? 64u : (((uint32_t)want + 31u) & ~31u);
     }
     p.heavy_ranks = 1u << 15;
-    if (const char* dbg = getenv("BSS_DEBUG_HEAVY")) p.heavy_ranks = (uint32_t)atoll(dbg);
+    if (tuning.heavy_ranks > 0) p.heavy_ranks = (uint32_t)tuning.heavy_ranks;
     p.heavy_block = p.heavy_ranks / 4 ? p.heavy_ranks / 4 : 1;
-    if (const char* dbg = getenv("BSS_DEBUG_CAP")) p.list_cap = p.group == 32 ? (uint32_t)atoi(dbg) : 0u;
+    if (tuning.list_cap >= 0) p.list_cap = p.group == 32 ? (uint32_t)tuning.list_cap : 0u;
     p.smem_bytes      = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, false);
     p.smem_bytes_emit = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, true);
+    // Window walk: whole warps only; the query carries banded masks; the working set fits.
+    p.smem_bytes_window = 4u * window_smem_words(lib.cmax, p.W, p.WS);
+    p.window = (p.group == 32 && n_window_units > 0 && q.bmask != nullptr && p.smem_bytes_window <= 160u * 1024u && tuning.window != 0) ? 1u : 0u;
+    p.window_stage = 0;
+    if (p.window && n_seqs == 1 && known_band >= 0 && known_band <= kWindowBandMax && tuning.window_stage > 0) {
+        // occurrence table + banded mask of the one sequence in shared memory, next to the warps' scratch
+        const uint32_t staged = 4u * window_stage_words(q.occ_rows, q.occ_stride, max_len, (uint32_t)band_words(known_band));
+        if (p.smem_bytes_window + staged <= 110u * 1024u) {   // two CTAs per SM at least
+            p.window_stage = 1;
+            p.smem_bytes_window += staged;
+        }
+    }
     return p;
 }
 
-cudaError_t launch_band(const DevQuery& q, int32_t* band, cudaStream_t s)
+cudaError_t launch_band(const DevQuery& q, int32_t* band, uint32_t* bmask, cudaStream_t s)
 {
     if (q.n_seqs == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(band, 0xFF, sizeof(int32_t) * (size_t)q.n_seqs, s);   // -1: no pair allowed
@@ -1606,6 +1625,7 @@ cudaError_t launch_band(const DevQuery& q, int32_t* band, cudaStream_t s)
     slices          = slices < 1 ? 1u : slices > 64 ? 64u : slices;
     dim3 grid(q.n_seqs, slices);
     band_kernel<<<grid, 256, 0, s>>>(q, band);
+    if (bmask) bandmask_kernel<<<grid, 256, 0, s>>>(q, bmask);   // (reads the bands the kernel before it wrote)
     return cudaGetLastError();
 }
 
@@ -1621,12 +1641,47 @@ cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, int sm_count, cudaStream_t s)
+template <bool EMIT>
+cudaError_t launch_window(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records, uint64_t capacity_words,
+                          int sm_count, cudaStream_t s)
 {
-    cudaError_t e = work.prefilter ? launch_prefilter(lib, q, work, sm_count, s) : cudaSuccess;
-    if (e == cudaSuccess) e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, 0, s);
-    // the blocks of the items the count pass parked on the heavy list (returns at once when there are none)
-    if (e == cudaSuccess && plan.group == 32 && plan.list_cap) e = launch_search<kModeHeavyCount>(lib, q, plan, work, nullptr, 0, (uint32_t)sm_count * 4u, 0, s);
+    // persistent warps: the list lengths are read on the device
+    const uint32_t per_sm = plan.smem_bytes_window ? std::min<uint32_t>(8u, (200u * 1024u) / plan.smem_bytes_window) : 8u;
+    const uint32_t grid   = (uint32_t)sm_count * (per_sm ? per_sm : 1u);
+    const uint32_t smem   = plan.smem_bytes_window;
+#define BSS_LAUNCH_WIN(STAGE)                                                                                            \
+    do {                                                                                                                 \
+        auto kernel = window_kernel<EMIT, STAGE>;                                                                        \
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        if (e != cudaSuccess) return e;                                                                                  \
+        kernel<<<grid, kWinThreads, smem, s>>>(lib, q, plan, work, records, capacity_words);                             \
+    } while (0)
+    if (plan.window_stage) BSS_LAUNCH_WIN(true); else BSS_LAUNCH_WIN(false);
+#undef BSS_LAUNCH_WIN
+    return cudaGetLastError();
+}
+
+cudaError_t launch_route(const DevLibrary& lib, const DevQuery& q, const Work& work, int sm_count, cudaStream_t s)
+{
+    const uint64_t n_items = (uint64_t)q.n_seqs * lib.n_units;
+    if (n_items == 0) return cudaSuccess;
+    uint64_t grid = (n_items + 255) / 256;
+    if (grid > (uint64_t)sm_count * 64) grid = (uint64_t)sm_count * 64;
+    route_kernel<<<(uint32_t)grid, 256, 0, s>>>(lib, q, work, n_items);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, bool ordinary, int sm_count, cudaStream_t s)
+{
+    cudaError_t e = cudaSuccess;
+    if (plan.window) e = launch_route(lib, q, work, sm_count, s);
+    else if (work.prefilter) e = launch_prefilter(lib, q, work, sm_count, s);
+    if (ordinary) {
+        if (e == cudaSuccess) e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, 0, s);
+        // the blocks of the items the count pass parked on the heavy list (returns at once when there are none)
+        if (e == cudaSuccess && plan.group == 32 && plan.list_cap) e = launch_search<kModeHeavyCount>(lib, q, plan, work, nullptr, 0, (uint32_t)sm_count * 4u, 0, s);
+    }
+    if (e == cudaSuccess && plan.window && plan.n_chunks) e = launch_window<false>(lib, q, plan, work, nullptr, 0, sm_count, s);
     return e;
 }
 
@@ -1637,29 +1692,45 @@ cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, c
 }
 
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
-                        uint32_t n_alive, uint32_t n_heavy, uint64_t capacity_words, int sm_count, cudaStream_t s)
+                        uint32_t n_alive, uint32_t n_heavy, uint64_t capacity_words, bool ordinary, int sm_count, cudaStream_t s)
 {
     // n_alive == UINT32_MAX: sizes are read on the device (no host round trip after the count pass);
     // the heavy emit is then launched unconditionally (it returns at once without heavy items).
     const bool  blind = n_alive == 0xFFFFFFFFu;
-    cudaError_t e     = launch_search<kModeEmit>(lib, q, plan, work, records, n_alive, (uint32_t)sm_count * 8u, capacity_words, s);   // (blind: 32 CTAs per SM stride over the list)
-    if (e == cudaSuccess && (n_heavy || (blind && plan.group == 32 && plan.list_cap)))
-        e = launch_search<kModeHeavyEmit>(lib, q, plan, work, records, 0, (uint32_t)sm_count * 4u, capacity_words, s);
+    cudaError_t e     = cudaSuccess;
+    if (ordinary) {
+        e = launch_search<kModeEmit>(lib, q, plan, work, records, n_alive, (uint32_t)sm_count * 8u, capacity_words, s);   // (blind: 32 CTAs per SM stride over the list)
+        if (e == cudaSuccess && (n_heavy || (blind && plan.group == 32 && plan.list_cap)))
+            e = launch_search<kModeHeavyEmit>(lib, q, plan, work, records, 0, (uint32_t)sm_count * 4u, capacity_words, s);
+    }
+    if (e == cudaSuccess && plan.window) e = launch_window<true>(lib, q, plan, work, records, capacity_words, sm_count, s);
     return e;
 }
 
-// dst[0..n] = src[0..n] unless the records did not fit (then nothing may be written)
-__global__ void guarded_copy_kernel(const uint64_t* __restrict__ totals, uint64_t capacity_words, const uint64_t* __restrict__ src,
-                                    uint64_t* __restrict__ dst, uint32_t n)
+cudaError_t launch_placements(const DevLibrary& lib, const DevQuery& q, const Plan& plan, uint64_t* scratch, size_t per_warp, uint32_t n_ctas,
+                              unsigned long long* total, cudaStream_t s)
 {
-    if (totals[0] > capacity_words) return;
+    if (q.n_seqs == 0 || lib.n_units == 0) return cudaSuccess;
+    const uint32_t smem = 4u * (kThreads / 32) * (kBlobStage + 2 * lib.cmax * (plan.W + plan.WS));
+    cudaError_t    e    = cudaFuncSetAttribute(placements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    placements_kernel<<<n_ctas, kThreads, smem, s>>>(lib, q, plan, scratch, per_warp, total);
+    return cudaGetLastError();
+}
+
+size_t placements_words_per_warp(uint32_t max_len) { return placements_scratch_words(max_len); }
+
+// The per-sequence word offsets go to the caller's header whether or not the records fitted (its last entry is the
+// number of record words: what an exchange behind the search reads, and what tells every rank about an overflow).
+__global__ void offsets_copy_kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint32_t n)
+{
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
-cudaError_t launch_guarded_copy(const Work& work, uint64_t capacity_words, uint64_t* dst, uint32_t n, cudaStream_t s)
+cudaError_t launch_offsets_copy(const Work& work, uint64_t* dst, uint32_t n, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    guarded_copy_kernel<<<n > 4096 ? 16 : 1, 256, 0, s>>>(work.totals, capacity_words, work.seq_word_begin, dst, n);
+    offsets_copy_kernel<<<n > 4096 ? 16 : 1, 256, 0, s>>>(work.seq_word_begin, dst, n);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,287 @@
+// Window walk: the per-lane placement enumerator of window_kernel (bss_kernels.cu).
+//
+// What it replaces (reference, CPU): the recursion of find_next_ones_in (cppsrc/Motif.cpp:432-494)
+// followed by the pair filters (cppsrc/MOIP.cpp:1072-1079, 1131-1137, 1194-1205), for units in
+// which every component after the first is tied to an earlier one by a "row check" (kCheckRow: a
+// base pair (u, v) with u on an earlier component and v on the component being placed — every JSON
+// loop closing pair, every DESC closing pair, most RIN links).
+//
+// Idea: for a placed upper part, the candidates of the next component that satisfy such a check are
+// exactly the bits of   chain set of the component  AND  (mask row u >> offset)  — a few word-wide
+// ANDs instead of a list walk — and they live in the window (u, u + band], `band` being the widest
+// pair the sequence's mask allows (the reference's masks come from a windowed fold, span <= 100).
+// A lane owns a contiguous range of the first component's candidates and runs a depth-first walk
+// whose every step is "next set bit of an AND of a handful of words": only partial placements whose
+// pairs are all allowed are ever visited, so in the banded regime the walk ends after a few words
+// per candidate. The chain semantics of the reference (leftmost non-overlapping matches of the
+// suffix, sregex_iterator) are kept: for a component whose matches overlap on this sequence the
+// candidates are a few "greedy" matches followed by the thinned set T (see thin_components).
+//
+// Plain C++ in host/device functions: the same source runs in the kernel and, lane by lane, in the
+// CPU emulation the tests compare with the flat-table interpreter (tests/cpp/window_host.cpp).
+#pragma once
+#include <cstdint>
+
+#include "bss_layout.h"
+
+#if defined(__CUDACC__)
+#define BSS_HD __host__ __device__ __forceinline__
+#else
+#define BSS_HD inline
+#endif
+
+namespace bss {
+namespace win {
+
+#if defined(__CUDA_ARCH__)
+BSS_HD int      ffs32(uint32_t x) { return __ffs((int)x); }
+BSS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+#else
+BSS_HD int      ffs32(uint32_t x) { return __builtin_ffs((int)x); }
+BSS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { s &= 31u; return s ? (lo >> s) | (hi << (32u - s)) : lo; }
+#endif
+
+BSS_HD int imax(int a, int b) { return a > b ? a : b; }
+BSS_HD int imin(int a, int b) { return a < b ? a : b; }
+BSS_HD int anchor_of(uint32_t w) { return (int)(int8_t)(w & 0xFFu); }
+BSS_HD int off_of(uint32_t w) { return (int)(int16_t)((w >> 8) & 0xFFFFu); }
+
+struct Ctx {
+    const uint32_t* blob;   // unit descriptor
+    const uint32_t* M;      // [C][W] every match of every component
+    const uint32_t* T;      // [C][W] thinned matches, valid for the components in `ovl`
+    const uint32_t* SM;     // [C][WS] one-bit-per-word summaries of M
+    const uint32_t* ST;     // [C][WS] ... of T
+    const uint32_t* bm;     // banded pair mask of the sequence: row u = K words, the mask words (u >> 5) .. of row u
+    uint32_t*       pos;    // this lane's column (stride cs): position | last position of the level's window << 16
+    uint32_t*       bits;   // this lane's column: candidates left in the word of the current position
+    uint32_t*       grd;    // this lane's column: 1 while the level's chain is still a greedy walk over all matches
+    uint32_t        ovl;    // bit c: matches of component c overlap on this sequence
+    int             W, WS, n, K, C, delay, band, cs;
+};
+
+// First set bit at or after position t (t >= 0) of a bitset with a one-bit-per-word summary, or -1.
+BSS_HD int next_set(const uint32_t* B, const uint32_t* S, int W, int WS, int t)
+{
+    int w = t >> 5;
+    if (w >= W) return -1;
+    uint32_t x = B[w] & (0xFFFFFFFFu << (t & 31));
+    if (x) return (w << 5) + ffs32(x) - 1;
+    if (++w >= W) return -1;
+    int      sw = w >> 5;
+    uint32_t s  = S[sw] & (0xFFFFFFFFu << (w & 31));
+    while (!s) {
+        if (++sw >= WS) return -1;
+        s = S[sw];
+    }
+    w = (sw << 5) + ffs32(s) - 1;
+    return (w << 5) + ffs32(B[w]) - 1;
+}
+
+BSS_HD bool bit_of(const uint32_t* B, int q) { return (B[q >> 5] >> (q & 31)) & 1u; }
+
+BSS_HD int placed(const Ctx& cx, int level) { return (int)(cx.pos[level * cx.cs] & 0xFFFFu); }
+
+// Word w (absolute index into the mask row) of row u of the pair mask; zero outside the band.
+BSS_HD uint32_t row_word(const Ctx& cx, int u, int w)
+{
+    const unsigned j = (unsigned)(w - (u >> 5));
+    return j < (unsigned)cx.K ? cx.bm[u * cx.K + (int)j] : 0u;
+}
+
+BSS_HD bool pair_allowed(const Ctx& cx, int u, int v)
+{
+    const int a = imin(u, v), b = imax(u, v);
+    if (a < 0 || b >= cx.n || a == b) return false;
+    return (row_word(cx, a, b >> 5) >> (b & 31)) & 1u;
+}
+
+// The checks of level `level` that are not row checks, one candidate at a time (rare: pairs inside one
+// strand, absolute positions, ends outside their component).
+BSS_HD bool generic_pass(const Ctx& cx, int level)
+{
+    const uint32_t  range = cx.blob[5 + 2 * level];
+    const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
+    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
+    for (int i = cb; i < ce; i++) {
+        const uint32_t ea = chk[2 * i], eb = chk[2 * i + 1];
+        if (ea & kCheckRow) continue;
+        const int aa = anchor_of(ea), ba = anchor_of(eb);
+        const int u  = (aa < 0 ? 0 : placed(cx, aa)) + off_of(ea);
+        const int v  = (ba < 0 ? 0 : placed(cx, ba)) + off_of(eb);
+        if (!pair_allowed(cx, u, v)) return false;
+    }
+    return true;
+}
+
+// x = bits of word w of the chain set of component c; keeps the positions that satisfy every row check of the level.
+BSS_HD uint32_t row_filter(const Ctx& cx, int c, int w, uint32_t x)
+{
+    const uint32_t  range = cx.blob[5 + 2 * c];
+    const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
+    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
+    for (int i = cb; i < ce && x; i++) {
+        const uint32_t ea = chk[2 * i];
+        if (!(ea & kCheckRow)) continue;
+        const int u = placed(cx, anchor_of(ea)) + off_of(ea);
+        if (u < 0) return 0u;
+        const int ob = off_of(chk[2 * i + 1]);
+        const int ws = w + (ob >> 5);
+        x &= funnel_r(row_word(cx, u, ws), row_word(cx, u, ws + 1), (uint32_t)ob & 31u);   // bit q = row bit q + ob
+    }
+    return x;
+}
+
+BSS_HD bool row_pass(const Ctx& cx, int c, int q)
+{
+    return (row_filter(cx, c, q >> 5, 1u << (q & 31)) >> (q & 31)) & 1u;
+}
+
+// Next candidate of level c at or after `start` (a position of the thinned part of the chain), up to hi.
+BSS_HD int scan_from(const Ctx& cx, int c, int start, int hi)
+{
+    const bool      thinned = (cx.ovl >> c) & 1u;
+    const uint32_t* S  = (thinned ? cx.T : cx.M) + c * cx.W;
+    const uint32_t* SS = (thinned ? cx.ST : cx.SM) + c * cx.WS;
+    int             q  = start;
+    while (q <= hi) {
+        q = next_set(S, SS, cx.W, cx.WS, q);   // skips the empty words through the summary
+        if (q < 0 || q > hi) return -1;
+        const int w = q >> 5;
+        uint32_t  x = row_filter(cx, c, w, S[w] & (0xFFFFFFFFu << (q & 31)));
+        if (x) {
+            const int p = (w << 5) + ffs32(x) - 1;
+            if (p > hi) return -1;
+            cx.bits[c * cx.cs] = x & (x - 1u);
+            cx.pos[c * cx.cs]  = (uint32_t)p | ((uint32_t)hi << 16);
+            return p;
+        }
+        q = (w + 1) << 5;
+    }
+    return -1;
+}
+
+// First candidate of component c below the current placement of components 0 .. c-1, or -1.
+BSS_HD int level_first(const Ctx& cx, int c)
+{
+    const int kprev = (int)(cx.blob[4 + 2 * (c - 1)] & 0xFFu), kc = (int)(cx.blob[4 + 2 * c] & 0xFFu);
+    const int t     = placed(cx, c - 1) + kprev - 1 + cx.delay;   // start of the suffix the component is searched in (inside the sequence)
+    int       hi    = cx.n - kc - (c < cx.C - 1 ? cx.delay : 0);  // the pattern fits and leaves room for the next component
+    if (cx.band < 0) return -1;                                   // no pair at all is allowed: the level's row check cannot hold
+    const uint32_t  range = cx.blob[5 + 2 * c];
+    const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
+    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
+    for (int i = cb; i < ce; i++) {   // v = candidate + ob must lie in (u, u + band] and inside the sequence
+        const uint32_t ea = chk[2 * i];
+        if (!(ea & kCheckRow)) continue;
+        const int u  = placed(cx, anchor_of(ea)) + off_of(ea);
+        const int ob = off_of(chk[2 * i + 1]);
+        if (u < 0) return -1;
+        hi = imin(hi, imin(u + cx.band, cx.n - 1) - ob);
+    }
+    if (t > hi) return -1;
+    cx.grd[c * cx.cs] = 0;
+    if ((cx.ovl >> c) & 1u) {
+        // the reference's iterator restarts at t: greedy walk over all matches until it meets the thinned set
+        const uint32_t *M = cx.M + c * cx.W, *SM = cx.SM + c * cx.WS, *T = cx.T + c * cx.W;
+        const int       ke = imax(1, kc);
+        int             q  = next_set(M, SM, cx.W, cx.WS, t);
+        while (q >= 0 && q <= hi && !bit_of(T, q)) {
+            if (row_pass(cx, c, q)) {
+                cx.grd[c * cx.cs]  = 1;
+                cx.bits[c * cx.cs] = 0;
+                cx.pos[c * cx.cs]  = (uint32_t)q | ((uint32_t)hi << 16);
+                return q;
+            }
+            q = next_set(M, SM, cx.W, cx.WS, q + ke);
+        }
+        if (q < 0 || q > hi) return -1;
+        return scan_from(cx, c, q, hi);
+    }
+    return scan_from(cx, c, t, hi);
+}
+
+// Next candidate of level c after the current one, or -1.
+BSS_HD int level_next(const Ctx& cx, int c)
+{
+    const uint32_t e = cx.pos[c * cx.cs];
+    const int      p = (int)(e & 0xFFFFu), hi = (int)(e >> 16);
+    if (cx.grd[c * cx.cs]) {
+        const uint32_t *M = cx.M + c * cx.W, *SM = cx.SM + c * cx.WS, *T = cx.T + c * cx.W;
+        const int       ke = imax(1, (int)(cx.blob[4 + 2 * c] & 0xFFu));
+        int             q  = next_set(M, SM, cx.W, cx.WS, p + ke);
+        while (q >= 0 && q <= hi && !bit_of(T, q)) {
+            if (row_pass(cx, c, q)) {
+                cx.pos[c * cx.cs] = (uint32_t)q | ((uint32_t)hi << 16);
+                return q;
+            }
+            q = next_set(M, SM, cx.W, cx.WS, q + ke);
+        }
+        if (q < 0 || q > hi) return -1;
+        cx.grd[c * cx.cs] = 0;   // the chain has met the thinned set: it is the thinned set from here on
+        return scan_from(cx, c, q, hi);
+    }
+    const uint32_t x = cx.bits[c * cx.cs];
+    if (x) {
+        const int q = (p & ~31) + ffs32(x) - 1;
+        if (q > hi) return -1;
+        cx.bits[c * cx.cs] = x & (x - 1u);
+        cx.pos[c * cx.cs]  = (uint32_t)q | ((uint32_t)hi << 16);
+        return q;
+    }
+    return scan_from(cx, c, (p | 31) + 1, hi);
+}
+
+// Every site whose first component lies in the words [w0, w1) of its candidate set. Returns their number;
+// when EMIT, writes their records [module, p_0 .. p_{C-1}] from `out` on, in depth-first order.
+template <bool EMIT>
+BSS_HD uint64_t walk_words(const Ctx& cx, int w0, int w1, uint32_t module, uint32_t* out)
+{
+    const int       C = cx.C, R = C + 1;
+    const uint32_t* first = (cx.ovl & 1u) ? cx.T : cx.M;   // the chain from position 0 starts on a run start: it is the thinned set
+    const int       k0  = (int)(cx.blob[4] & 0xFFu);
+    const int       hi0 = cx.n - k0 - (C > 1 ? cx.delay : 0);
+    uint64_t        found = 0;
+    for (int w = w0; w < w1; w++) {
+        for (uint32_t x = first[w]; x; x &= x - 1u) {
+            const int p0 = (w << 5) + ffs32(x) - 1;
+            if (p0 > hi0) return found;   // later candidates leave even less room
+            cx.pos[0] = (uint32_t)p0;
+            if ((cx.blob[4] & kCompGeneric) && !generic_pass(cx, 0)) continue;
+            if (C == 1) {
+                if (EMIT) { out[found * R] = module; out[found * R + 1] = (uint32_t)p0; }
+                found++;
+                continue;
+            }
+            int level = 1;
+            int q     = level_first(cx, 1);
+            for (;;) {
+                if (q < 0) {   // this level is exhausted: on to the next candidate of its parent
+                    if (--level == 0) break;
+                    q = level_next(cx, level);
+                    continue;
+                }
+                if ((cx.blob[4 + 2 * level] & kCompGeneric) && !generic_pass(cx, level)) {
+                    q = level_next(cx, level);
+                    continue;
+                }
+                if (level == C - 1) {
+                    if (EMIT) {
+                        uint32_t* rec = out + found * (uint64_t)R;
+                        rec[0]        = module;
+                        for (int c = 0; c < C; c++) rec[1 + c] = (uint32_t)placed(cx, c);
+                    }
+                    found++;
+                    q = level_next(cx, level);
+                    continue;
+                }
+                level++;
+                q = level_first(cx, level);
+            }
+        }
+    }
+    return found;
+}
+
+}   // namespace win
+}   // namespace bss

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BSS_ABI_VERSION 1
+#define BSS_ABI_VERSION 2
 
 /* ---- status codes (0 = success, negative = failure) ---- */
 #define BSS_OK                 0
@@ -46,6 +46,8 @@ extern "C" {
 #define BSS_ERR_BAD_SEQUENCE (-5)  /* query contains '\n' or '\r' (regex '.' would not match them)     */
 #define BSS_ERR_OVERFLOW     (-6)  /* caller-provided output too small; required size is reported      */
 #define BSS_ERR_COUNT        (-7)  /* one unit has >= 2^32 sites on one sequence                       */
+#define BSS_ERR_NOMEM        (-8)  /* host allocation failed                                           */
+#define BSS_ERR_INTERNAL     (-9)  /* an unexpected C++ exception was caught at the boundary           */
 
 /* ---- documented limits ---- */
 #define BSS_MAX_COMPONENTS   16    /* components per unit                                              */
@@ -93,6 +95,10 @@ typedef struct bss_table {
 /* Opaque handles. A library owns device memory, one CUDA stream and growable work
  * buffers; it is immutable after creation and is used by one host thread at a time
  * (the reference calls this path once, from the main thread: cppsrc/biorseo.cpp:175). */
+/* Lifetime: queries, result handles (bss_sites) and indexes (bss_site_index) may be released before or
+ * after the library they came from; bss_library_destroy detaches the ones still alive (they keep their own
+ * buffers and can still be read and freed), bss_query_destroy waits for a search of that query that is
+ * still queued. A query must outlive every search that uses it. */
 typedef struct bss_library bss_library;
 typedef struct bss_query   bss_query;   /* sequences + pair masks resident in device memory */
 typedef struct bss_sites   bss_sites;   /* one search result                                */
@@ -108,6 +114,10 @@ typedef struct bss_stats {
     float    scan_ms;             /* device time of the offset scan kernel                     */
     float    emit_ms;             /* device time of the emit kernel                            */
     float    total_ms;            /* first launch to last kernel end                           */
+    uint64_t window_items;        /* items that took the window walk (route_kernel's list)     */
+    uint64_t ordinary_items;      /* items left to the ordinary (rank-space / depth-first) passes */
+    uint64_t heavy_items;         /* ordinary items parked and walked block by block           */
+    uint64_t placements_enumerated; /* set by bss_placements_enumerated (0 until it is called)  */
 } bss_stats;
 
 /* ---- library ---- */
@@ -121,7 +131,18 @@ int  bss_library_set_stream(bss_library* lib, void* cuda_stream);
 /* Library shards (one per GPU): `base` is added to every module index written into a record,
  * so that records of different shards can be concatenated in canonical global order. */
 int  bss_library_set_module_base(bss_library* lib, uint32_t base);
+/* Developer knobs: force rarely taken paths on small inputs (tests), compare kernel variants (benchmarks).
+ * value < 0 returns a knob to automatic. Values are validated (BSS_ERR_INVALID). Not a tuning interface
+ * for production callers: the defaults are the measured optimum. */
+#define BSS_TUNE_GROUP            0   /* lanes per (sequence, unit) item: 4, 8, 16 or 32              */
+#define BSS_TUNE_UNITS_PER_CHUNK  1   /* units per count-pass CTA (>= 1)                               */
+#define BSS_TUNE_HEAVY_RANKS      2   /* placements from which an item is walked block by block (>= 1) */
+#define BSS_TUNE_LIST_CAP         3   /* match-list entries per item of the rank-space walk (0: off)   */
+#define BSS_TUNE_WINDOW           4   /* 0: never take the window walk                                 */
+#define BSS_TUNE_WINDOW_STAGE     5   /* 1: window kernel stages occurrence table + banded mask in shared memory (cp.async.bulk) */
+int  bss_library_set_tuning(bss_library* lib, int knob, int64_t value);
 uint32_t bss_library_units(const bss_library* lib);
+uint32_t bss_library_window_units(const bss_library* lib);   /* units every component of which is tied by a pair to an earlier one */
 uint32_t bss_library_modules(const bss_library* lib);
 /* Number of components of the units of `module` (identical for all its units). */
 uint32_t bss_library_module_components(const bss_library* lib, uint32_t module);
@@ -163,8 +184,10 @@ int  bss_query_create_pij(bss_library* lib, const char* seq, uint32_t n, const f
 int  bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites** out);
 
 /* Search a resident query into caller-owned DEVICE memory (e.g. a tensor that will feed an
- * NCCL all-gather). On BSS_ERR_OVERFLOW nothing is written and *n_words holds the size needed.
- * d_seq_word_begin may be NULL, else receives n_seqs + 1 u64 word offsets (device memory). */
+ * NCCL all-gather). On BSS_ERR_OVERFLOW no record is written and *n_words holds the size needed.
+ * d_seq_word_begin may be NULL, else receives n_seqs + 1 u64 word offsets (device memory) — always, also on
+ * overflow: its last entry is the number of record words the search produced, which is what an exchange
+ * queued behind the search reads (a count above the capacity raises the overflow flag on every rank). */
 int  bss_search_query_into(bss_library* lib, const bss_query* q, uint32_t* d_records, uint64_t capacity_words,
                            uint64_t* d_seq_word_begin, uint64_t* n_words, uint64_t* n_sites);
 
@@ -270,6 +293,12 @@ int         bss_last_stats(const bss_library* lib, bss_stats* out);
 const char* bss_last_error(void);   /* thread-local, never NULL */
 int         bss_abi_version(void);
 int         bss_device_count(void);
+/* The reference's real work term ("placements enumerated"): the exact number of placements
+ * find_next_ones_in materialises BEFORE the pair filters (cppsrc/Motif.cpp:466-474), summed over every
+ * (sequence, unit) of the query whose gate is open. A diagnostic kernel of its own (a backward counting
+ * programme per item), not part of a search: the search kernels never visit most of these placements.
+ * q == NULL names the query of the last host-buffer search. Also recorded in bss_stats. */
+int         bss_placements_enumerated(bss_library* lib, const bss_query* q, uint64_t* placements);
 /* Measured integer-issue rate of the device (thread-level 32-bit shift / logic operations per second, all SMs
  * busy with nothing else, at the clocks the GPU runs at): the denominator of the search's integer roofline. */
 int         bss_measure_int_issue(bss_library* lib, double* thread_ops_per_s);

@@ -19,6 +19,10 @@
 //       cppsrc/MOIP.cpp:146-296 does, and dumps insertion_sites_.
 //   biorseo_ref fno   <delay> <seq> <component>...
 //       the placement enumerator find_next_ones_in (cppsrc/Motif.cpp:432-494) alone.
+//   biorseo_ref placements jsonfolder <library> <seqfile> <maskfile>
+//       the reference's real work term: the number of placements find_next_ones_in returns (before the pair
+//       filters), summed over the valid modules of a JSON library — components split the way
+//       MOIP::allowed_motifs_from_json does (cppsrc/MOIP.cpp:1158-1172). Prints one number.
 //   biorseo_ref fasta <file>
 //       the reference's FASTA loader Fasta::load (cppsrc/fa.cpp:22-60): one line per record, name \t seq \t str.
 //   biorseo_ref bench <source> <library> <seqfile> <maskfile> <threads> <repeat> [max_modules]
@@ -292,6 +296,25 @@ int main(int argc, char** argv)
     Dispatch d;
     collect_jobs(moip, source, lib, d, max_modules);
 
+    if (cmd == "placements") {
+        if (source != "jsonfolder") { std::fprintf(stderr, "placements: jsonfolder only\n"); return 2; }
+        unsigned long long total = 0;
+        for (auto it = d.library.begin(); it != d.library.end(); ++it) {
+            if (Motif::is_valid_JSON(it)) continue;
+            string s = it.value()["sequence"];
+            std::transform(s.begin(), s.end(), s.begin(), ::toupper);
+            vector<string> comps;
+            while (s.find("&") != string::npos) {
+                const size_t end = s.find("&");
+                comps.push_back(s.substr(0, end));
+                s = s.substr(end + 1);
+            }
+            if (!s.empty()) comps.push_back(s);
+            total += find_next_ones_in(seq, 0, comps).size();
+        }
+        std::printf("%llu\n", total);
+        return 0;
+    }
     if (cmd == "jobs") {
         run_jobs(d, threads);
         dump_sites(moip.insertion_sites_);

@@ -24,7 +24,7 @@ def test_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared but not exported"
     assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
-    assert lib.bss_abi_version() == 1
+    assert lib.bss_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():

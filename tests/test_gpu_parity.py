@@ -197,50 +197,7 @@ def test_full_size_c4_properties_and_reference_sample(tmp_path, kind, mask_kind)
 # ---------------------------------------------------------------------------------------
 # random flat tables: chains of overlapping matches x band windows x every check shape
 # ---------------------------------------------------------------------------------------
-def _random_table(rng, n_units, alphabet, max_comp, max_len, min_len=1, short_limit=None):
-    """short_limit: units holding a pattern shorter than min_len + 1 get at most that many components
-    (keeps the number of placements the Python interpreter has to enumerate bounded)."""
-    pats, comp_begin, unit_comp_begin, unit_check_begin, checks, delays = [], [0], [0], [0], [], []
-    for _ in range(n_units):
-        C = int(rng.integers(1, max_comp + 1))
-        lens = []
-        for _c in range(C):
-            k = int(rng.integers(0 if rng.random() < 0.05 else min_len, max_len + 1))
-            if short_limit is not None and k <= min_len and _c >= short_limit:
-                k = max_len
-            p = [alphabet[i] for i in rng.integers(0, len(alphabet), k)]
-            p = [0x2E if rng.random() < 0.15 else x for x in p]
-            pats.extend(p)
-            comp_begin.append(len(pats))
-            lens.append(k)
-        unit_comp_begin.append(len(comp_begin) - 1)
-        for _k in range(int(rng.integers(0, 4))):
-            kind = rng.random()
-            a = int(rng.integers(0, C))
-            b = int(rng.integers(0, C))
-            if kind < 0.15:
-                a = -1
-            elif kind < 0.25:
-                b = a
-            ao = int(rng.integers(0, 40)) if a < 0 else int(rng.integers(-2, max(lens[a], 1) + 2))
-            bo = int(rng.integers(0, 40)) if b < 0 else int(rng.integers(-2, max(lens[b], 1) + 2))
-            checks.append((a, ao, b, bo))
-        unit_check_begin.append(len(checks))
-        delays.append(int(rng.integers(0, 6)))
-    return {
-        "n_modules": n_units, "n_units": n_units, "n_gates": 0,
-        "unit_module": np.arange(n_units, dtype=np.uint32), "unit_delay": np.array(delays, np.uint32),
-        "unit_gate": np.full(n_units, 0xFFFFFFFF, np.uint32), "unit_comp_begin": np.array(unit_comp_begin, np.uint32),
-        "comp_pat_begin": np.array(comp_begin, np.uint32), "pattern": np.array(pats, np.uint8) if pats else np.zeros(0, np.uint8),
-        "unit_check_begin": np.array(unit_check_begin, np.uint32),
-        "checks": np.array(checks, np.int16).reshape(-1, 4),
-    }
-
-
-def _banded_random_mask(n, seed, span, density):
-    rng = np.random.default_rng(seed)
-    u, v = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
-    return b.pack_mask((rng.random((n, n)) < density) & (v > u) & (v - u <= span))
+from tables import random_table as _random_table, banded_random_mask as _banded_random_mask  # noqa: E402
 
 
 @pytest.mark.parametrize("seed", range(12))
@@ -298,7 +255,7 @@ def test_random_tables_long_sequences(seed):
 def test_heavy_items_are_walked_block_by_block(seed, threshold, monkeypatch):
     """Items with many placements are parked by the count pass and walked as (item, block-of-ranks)
     tasks by separate passes; with the threshold lowered, ordinary items take that route."""
-    monkeypatch.setenv("BSS_DEBUG_HEAVY", str(threshold))
+    monkeypatch.setattr(b.api, "DEFAULT_TUNING", {"heavy_ranks": threshold, "window": 0})
     test_random_tables_long_sequences(seed)
     test_full_size_like_small(seed)
 
@@ -370,11 +327,12 @@ def test_working_set_limit_is_reported():
     dev.close()
 
 
-@pytest.mark.parametrize("knob,value", [("BSS_DEBUG_CAP", "40"), ("BSS_DEBUG_GROUP", "32"), ("BSS_DEBUG_UPC", "3")])
-def test_rarely_taken_paths_forced_on_small_inputs(knob, value, monkeypatch):
+@pytest.mark.parametrize("tuning", [{"list_cap": 40, "window": 0}, {"group": 32}, {"group": 32, "window": 0}, {"units_per_chunk": 3},
+                                    {"group": 8}, {"window_stage": 1}], ids=str)
+def test_rarely_taken_paths_forced_on_small_inputs(tuning, monkeypatch):
     """Tiny list capacity (items fall back to the depth-first walk inside 32-lane groups), 32-lane groups
-    on short sequences, odd chunk sizes."""
-    monkeypatch.setenv(knob, value)
+    on short sequences (with and without the window walk), odd chunk sizes, narrow groups, staged window tables."""
+    monkeypatch.setattr(b.api, "DEFAULT_TUNING", tuning)
     test_random_tables_long_sequences(2)
     test_random_tables_against_interpreter(4)
     test_full_size_like_small(1)
@@ -410,3 +368,123 @@ def test_full_size_c3_batch_properties_and_reference_sample(tmp_path):
     first.close()
     again.close()
     dev.close()
+
+
+# ---------------------------------------------------------------------------------------
+# window pass (route_kernel + window_kernel): units whose components are tied by row checks, narrow-band masks
+# ---------------------------------------------------------------------------------------
+import tables  # noqa: E402
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_window_tables_against_interpreter(seed):
+    """Random window-walk units (row checks from earlier components, ends outside their component, empty and
+    self-overlapping patterns, extra checks of every shape) on low-complexity queries, banded masks of several
+    widths: window pass == interpreter == ordinary passes; with the tables staged in shared memory too."""
+    rng = np.random.default_rng(5000 + seed)
+    alphabet = [ord(c) for c in ("AG" if seed % 3 == 0 else "ACG" if seed % 3 == 1 else "ACGU")]
+    n = int([37, 64, 97, 130, 200, 33, 700, 1100, 96, 260, 520, 2000][seed])
+    if n >= 500:   # keeps the number of placements the Python interpreter enumerates bounded
+        alphabet = [ord(c) for c in "ACGU"]
+    table = tables.window_table(rng, 60, alphabet, max_comp=4 if n < 300 else 3, max_len=4 if n < 300 else 5, min_len=1 if n < 300 else 3)
+    body = [alphabet[i] for i in rng.integers(0, len(alphabet), n)]
+    for _ in range(6):
+        at, run = int(rng.integers(0, n)), int(rng.integers(3, 14))
+        unit = [alphabet[i] for i in rng.integers(0, len(alphabet), int(rng.integers(1, 3)))]
+        for j in range(run):
+            if at + j < n:
+                body[at + j] = unit[j % len(unit)]
+    seq = bytes(body)
+    span = [12, 30, 5, 60, 255, 31, 32, 33, 100, 64, 20, 99][seed]
+    mask = _banded_random_mask(n, seed, span, [1.0, 0.6, 0.3][seed % 3] if n < 300 else 0.15)
+    expect = flat_interp.search_table(table, seq, mask)
+    for tuning in ({}, {"window": 0}, {"window_stage": 1}):
+        dev = b.DeviceLibrary.from_table(table)
+        for knob, value in tuning.items():
+            dev.set_tuning(knob, value)
+        q = dev.query([seq], [mask])
+        got = dev.search_query(q)
+        st = dev.stats()
+        assert np.array_equal(got.records(), expect), (tuning, got.n_words, expect.size)
+        if tuning.get("window", 1):
+            assert st["window_items"] > 0 and st["window_items"] + st["ordinary_items"] <= 60
+        else:
+            assert st["window_items"] == 0
+        one = dev.search(seq, mask)        # the host-buffer path does not know the band: every pass is queued
+        assert np.array_equal(one.records(), expect), tuning
+        for h in (got, one):
+            h.close()
+        q.close()
+        dev.close()
+
+
+@pytest.mark.parametrize("source", ["jsonfolder", "descfolder"])
+def test_window_and_ordinary_passes_agree_on_libraries(tmp_path, source):
+    """Whole libraries on a 2000-nt query with the banded mask of the headline workload: the window pass takes
+    (nearly) every item; switching it off must not change a word of the output."""
+    n = 2000
+    seq = synth.sequence(n, 4)
+    mask = synth.mask_canonical(seq, seed=204, keep=0.3, span=100)
+    if source == "jsonfolder":
+        host = b.HostLibrary.from_json_modules(synth.json_modules(3000, 104, "mixed"))
+    else:
+        host = b.HostLibrary.load(source, synth.write_desc_folder(str(tmp_path / "desc"), 600, 11))
+    results = {}
+    for name, tuning in (("window", {}), ("ordinary", {"window": 0}), ("staged", {"window_stage": 1})):
+        dev = host.to_device()
+        for knob, value in tuning.items():
+            dev.set_tuning(knob, value)
+        q = dev.query([seq], [mask])
+        s = dev.search_query(q)
+        results[name] = (s.records(), dev.stats())
+        if name == "window":
+            assert dev.n_window_units > 0.7 * dev.n_units
+        s.close()
+        q.close()
+        dev.close()
+    assert results["window"][1]["window_items"] > 0 and results["ordinary"][1]["window_items"] == 0
+    assert np.array_equal(results["window"][0], results["ordinary"][0])
+    assert np.array_equal(results["window"][0], results["staged"][0])
+    assert results["window"][0].size > 0
+
+
+def _placements_python(table, seq):
+    seq = seq.encode() if isinstance(seq, str) else bytes(seq)
+    total = 0
+    for u in range(int(table["n_units"])):
+        gate = int(table["unit_gate"][u])
+        if gate != flat_interp.NO_GATE:
+            gpats, _, gdelay = flat_interp._unit(table, gate)
+            if next(iter(flat_interp._placements(seq, len(seq), gpats, gdelay)), None) is None:
+                continue
+        pats, _, delay = flat_interp._unit(table, u)
+        total += sum(1 for _ in flat_interp._placements(seq, len(seq), pats, delay))
+    return total
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_placements_enumerated_is_the_reference_work_term(seed, tmp_path):
+    """bss_placements_enumerated = the number of tuples find_next_ones_in returns, summed over the library:
+    against the interpreter's enumeration on random tables (overlapping chains, empty patterns, delay 0) and
+    against the reference's own enumerator on a JSON library."""
+    rng = np.random.default_rng(7000 + seed)
+    alphabet = [ord(c) for c in ("AG" if seed % 2 else "ACGU")]
+    n = [60, 90, 150, 33, 200, 64][seed]
+    table = _random_table(rng, 40, alphabet, max_comp=3, max_len=4, short_limit=1 if n > 100 else None)
+    body = [alphabet[i] for i in rng.integers(0, len(alphabet), n)]
+    seq = bytes(body)
+    dev = b.DeviceLibrary.from_table(table)
+    q = dev.query([seq], [synth.mask_all(n)])
+    assert dev.placements_enumerated(q) == _placements_python(table, seq)
+    q.close()
+    dev.close()
+    if seed == 0 and util.have_ref():
+        modules = synth.json_modules(200, 9, "c4b")
+        path = synth.write_json(str(tmp_path / "lib.json"), modules)
+        s = synth.sequence(300, 5)
+        host = b.HostLibrary.load("jsonfolder", path)
+        dev = host.to_device()
+        q = dev.query([s], [synth.mask_all(300)])
+        assert dev.placements_enumerated(q) == util.ref_placements("jsonfolder", path, s, synth.mask_all(300))
+        q.close()
+        dev.close()

@@ -57,8 +57,30 @@ def run_port(source, library, seq, mask):
     return run_oracle(PORT_BIN, "jobs", source, library, seq, mask)
 
 
-def best_oracle(source, library, seq, mask):
-    """The reference binary when present, else the port."""
+_announced = set()
+
+
+def best_oracle(source, library, seq, mask, timeout=120):
+    """The reference's own code (oracle/_ref/biorseo_ref, built from /root/reference by oracle/Makefile and shipped
+    to the GPU box prebuilt). Its absence is an error, not a silent switch to the restatement: set BSS_ALLOW_PORT=1
+    to accept oracle/port instead (a box where the reference could not be built). Which one ran is printed once."""
     if have_ref():
-        return run_ref(source, library, seq, mask)
-    return run_port(source, library, seq, mask)
+        which, binary = "reference (oracle/_ref/biorseo_ref)", REF_BIN
+    elif os.environ.get("BSS_ALLOW_PORT") == "1" and have_port():
+        which, binary = "PORT (oracle/_build/biorseo_port; BSS_ALLOW_PORT=1)", PORT_BIN
+    else:
+        raise RuntimeError(f"{REF_BIN} is missing: build it with `make -C oracle ref` where /root/reference exists "
+                           "(it travels to the GPU box with the snapshot), or set BSS_ALLOW_PORT=1 to check against the C++ restatement instead")
+    if which not in _announced:
+        _announced.add(which)
+        print(f"\n[oracle] parity is checked against the {which}")
+    return run_oracle(binary, "jobs", source, library, seq, mask, timeout=timeout)
+
+
+def ref_placements(source, library, seq, mask):
+    """Number of placements the reference's find_next_ones_in returns over a JSON library (before the pair filters)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        seq_path, mask_path = write_query(tmp, seq, mask)
+        res = subprocess.run([REF_BIN, "placements", source, str(library), seq_path, mask_path], capture_output=True, text=True, timeout=300,
+                             preexec_fn=_bounded, check=True)
+    return int(res.stdout.strip().splitlines()[-1])
