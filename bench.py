@@ -17,9 +17,15 @@ Workloads (BASELINE.json configs):
   c4a / c4b the two halves on their own (search-bound / enumeration-bound)
   c4b_all   c4b with the all-allowed mask: every placement survives, output-bound
   c3        10 000 x 120-nt queries x 1 000-motif JSON library (batch mode)
-  c2        230-nt query x 400 synthetic CaRNAval RINs
+  c2        230-nt query x 400 synthetic CaRNAval RINs at SURVEY 8d's shape (2-6 strands of 1-6 nt)
+  c2_narrow the round-1 variant (2-4 strands of 2-6 nt), kept for comparison
   c1        73-nt example query x 1 000-motif JSON library
+  c4_400k   c4 with a 400 000-module library (strong scaling with enough work per GPU)
   c4_desc   2000-nt query x 5 000 synthetic .desc modules (wildcards, widened strands, delay 5, gates)
+Scaling (--gpus N > 1): "strong" (default) = ONE library, cut into N contiguous module ranges balanced by a
+search-cost estimate (the reference's unit of parallelism is one job per module of one library,
+cppsrc/MOIP.cpp:246-293); "weak" = one library of the named size PER GPU. The strong line carries the weak
+number beside it, and the per-rank search / exchange / skew times.
 value     = motif x position placements tested per second, inputs resident in HBM, device time
             (CUDA events on the launching stream), max over ranks.
 e2e       = the same through the host-buffer C ABI call (bss_search*): upload of sequence + mask
@@ -47,17 +53,18 @@ UNIT = "placements/s"
 # workloads
 # ----------------------------------------------------------------------------------------
 def make_workload(name, rank):
-    """Returns dict(seqs, masks, modules | rin_folder, source, describe). The library shard of
-    `rank` is generated from seed + rank, so the global library is the same for every N."""
+    """Returns dict(seqs, masks, modules | rin | desc, source, describe). `rank` seeds the library (weak scaling:
+    rank r searches its own library of the named size; strong scaling and N = 1: the library of rank 0)."""
     from biorseo_b200 import synth
     w = {"name": name, "source": "jsonfolder"}
-    if name in ("c4", "c4a", "c4b", "c4b_all"):
+    if name in ("c4", "c4a", "c4b", "c4b_all", "c4_400k"):
         seq = synth.sequence(2000, 4)
-        kind = {"c4": "mixed", "c4a": "c4a", "c4b": "c4b", "c4b_all": "c4b"}[name]
+        kind = {"c4": "mixed", "c4a": "c4a", "c4b": "c4b", "c4b_all": "c4b", "c4_400k": "mixed"}[name]
+        size = 400000 if name == "c4_400k" else 50000
         w["seqs"] = [seq]
         w["masks"] = [synth.mask_all(2000) if name == "c4b_all" else synth.mask_canonical(seq, seed=204, keep=0.3, span=100)]
-        w["modules"] = synth.json_modules(50000, 104 + 1000 * rank, kind)
-        w["describe"] = f"2000-nt x 50000 JSON motifs/GPU ({kind}), mask=" + ("all-allowed" if name == "c4b_all" else "banded canonical, Bernoulli 0.3")
+        w["modules"] = synth.json_modules(size, 104 + 1000 * rank, kind)
+        w["describe"] = f"2000-nt x {size} JSON motifs ({kind}), mask=" + ("all-allowed" if name == "c4b_all" else "banded canonical, Bernoulli 0.3")
     elif name == "c3":
         n_seqs = 10000
         w["seqs"] = [synth.sequence(120, 3 + i) for i in range(n_seqs)]
@@ -65,12 +72,15 @@ def make_workload(name, rank):
         w["masks"] = [synth.mask_canonical(s, seed=int(rng.integers(1 << 30)), keep=0.3) for s in w["seqs"]]
         w["modules"] = synth.json_modules(1000, 101, "c1")
         w["describe"] = "10000 x 120-nt queries x 1000 JSON motifs (c1 library), banded canonical masks"
-    elif name == "c2":
+    elif name in ("c2", "c2_narrow"):
         seq = synth.sequence(230, 2)
         w["seqs"], w["masks"] = [seq], [synth.mask_canonical(seq, seed=202, keep=0.3)]
         w["source"] = "rinfolder"
-        w["rin"] = (400, 102)
-        w["describe"] = "230-nt query x 400 synthetic CaRNAval RINs"
+        # (n, seed, max_components, min_len): SURVEY 8d's shape is 2-6 strands of 1-6 nt (scripts/Install_CaRNAval_RINs.py:54-101);
+        # its one-nucleotide strands are where modules with 10^6-10^8 placements before the filters come from
+        w["rin"] = (400, 102, 6, 1) if name == "c2" else (400, 102, 4, 2)
+        w["describe"] = ("230-nt query x 400 synthetic CaRNAval RINs, 2-6 strands of 1-6 nt" if name == "c2" else
+                         "230-nt query x 400 synthetic CaRNAval RINs, narrowed to 2-4 strands of 2-6 nt (round-1 shape)")
     elif name == "c4_desc":
         seq = synth.sequence(2000, 4)
         w["seqs"], w["masks"] = [seq], [synth.mask_canonical(seq, seed=204, keep=0.3, span=100)]
@@ -91,8 +101,8 @@ def host_library(w, tmp):
     import biorseo_b200 as b
     from biorseo_b200 import synth
     if w["source"] == "rinfolder":
-        n, seed = w["rin"]
-        path = synth.write_rin_folder(os.path.join(tmp, "rin"), n, seed, invalid_fraction=0.0, max_components=4, min_len=2)
+        n, seed, max_components, min_len = w["rin"]
+        path = synth.write_rin_folder(os.path.join(tmp, "rin"), n, seed, invalid_fraction=0.0, max_components=max_components, min_len=min_len)
         return b.HostLibrary.load("rinfolder", path), path
     if w["source"] == "descfolder":
         n, seed = w["desc"]

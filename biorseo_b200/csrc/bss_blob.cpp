@@ -201,7 +201,7 @@ int build_library(const bss_table* t, BuiltLibrary& out, std::string& error)
         }
         if (u < t->n_units) {
             // window walk: every component after the first must be tied to an earlier one by a row check
-            bool window = t->unit_delay[u] >= 1;
+            bool window = t->unit_delay[u] >= 1 && head + pat_words + 2 * NK <= kBlobStageWords;
             for (uint32_t c = 1; c < C; c++) window = window && row_checks[c] > 0;
             if (window) {
                 b[3] |= kUnitWindow;

@@ -1185,6 +1185,18 @@ int bss_placements_enumerated(bss_library* lib, const bss_query* q, uint64_t* pl
     });
 }
 
+#ifdef BSS_DEBUG_ASSERT
+// debug build only: the per-item site counts and the first window lane-count rows of the last search
+int bss_debug_counts(bss_library* lib, uint32_t* counts, uint32_t n, uint32_t* lanes_w, uint32_t n_rows, uint32_t* alive_w)
+{
+    cudaStreamSynchronize(lib->stream);
+    if (n && lib->d_counts.ptr) cudaMemcpy(counts, lib->d_counts.ptr, 4ull * n, cudaMemcpyDeviceToHost);
+    if (n_rows && lib->d_lane_counts_w.ptr) cudaMemcpy(lanes_w, lib->d_lane_counts_w.ptr, 128ull * n_rows, cudaMemcpyDeviceToHost);
+    if (n_rows && lib->d_alive_w.ptr) cudaMemcpy(alive_w, lib->d_alive_w.ptr, 4ull * n_rows, cudaMemcpyDeviceToHost);
+    return (int)cudaGetLastError();
+}
+#endif
+
 int bss_measure_int_issue(bss_library* lib, double* thread_ops_per_s)
 {
     return guarded([&]() -> int {

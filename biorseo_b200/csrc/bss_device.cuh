@@ -33,7 +33,7 @@ int guarded(F&& body)
 
 constexpr int      kThreads    = 128;          // threads per CTA (4 warps)
 constexpr int      kOccPad     = 10;           // zero words after each occurrence row (patterns up to 255+32 bytes)
-constexpr int      kBlobStage  = 64;           // unit descriptor words staged in shared memory per group
+constexpr int      kBlobStage  = (int)kBlobStageWords;   // unit descriptor words staged in shared memory per group
 constexpr uint32_t kMaxChunkUnits = 2048;      // units per chunk (bounds the per-CTA offset table)
 __host__ __device__ constexpr uint32_t kmer_table_word(uint32_t table) { return table == 0 ? 0u : table == 1 ? 8u : 40u; }
 constexpr uint32_t kBandWordsMax = (31 + kWindowBandMax) / 32 + 1;   // words per row of the banded pair mask, worst case

@@ -32,6 +32,13 @@
 //                (item, block of ranks) tasks spread over a GPU-wide grid, with subtree pruning.
 // Not a contraction: integer/bit work only, no tensor cores.
 #include "bss_device.cuh"
+
+#ifdef BSS_DEBUG_ASSERT
+namespace bss { __device__ unsigned int g_assert_fail[32]; }
+#ifdef __CUDA_ARCH__
+#define BSS_WIN_CHECK(cond, id) ((cond) ? true : (atomicAdd(&bss::g_assert_fail[id], 1u), false))
+#endif
+#endif
 #include "bss_window_walk.h"
 
 #include <algorithm>
@@ -39,6 +46,17 @@
 
 #ifndef BSS_MIN_CTAS
 #define BSS_MIN_CTAS 8   // resident CTAs per SM the register allocation is held to
+#endif
+
+#ifdef BSS_DEBUG_SYNC
+#include <cstdio>
+#define BSS_SYNC_CHECK(name, stream)                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = cudaStreamSynchronize(stream);                                                \
+        if (e_ != cudaSuccess) { std::fprintf(stderr, "[bss debug] %s: %s\n", name, cudaGetErrorString(e_)); return e_; } \
+    } while (0)
+#else
+#define BSS_SYNC_CHECK(name, stream) do { } while (0)
 #endif
 
 namespace bss {
@@ -63,7 +81,6 @@ __device__ unsigned long long g_phase_cycles[16];
 // available on the GPU pool). Violations are counted per site and read back with
 // bss_debug_assert_counts(); the fuzz tests are run against such a build.
 #ifdef BSS_DEBUG_ASSERT
-__device__ unsigned int g_assert_fail[32];
 #define BSS_ASSERT(cond, id) do { if (!(cond)) atomicAdd(&g_assert_fail[id], 1u); } while (0)
 #else
 #define BSS_ASSERT(cond, id) do { } while (0)
@@ -1542,6 +1559,7 @@ cudaError_t launch_search(const DevLibrary& lib, const DevQuery& q, const Plan& 
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
         if (e != cudaSuccess) return e;                                                                                   \
         kernel<<<grid, kThreads, smem, s>>>(lib, q, plan, work, records, n_alive, capacity_words);                        \
+        BSS_SYNC_CHECK("search_kernel", s);                                                                               \
     } while (0)
     if constexpr (HEAVY) {
         BSS_LAUNCH(32);
@@ -1601,15 +1619,16 @@ Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tun
     p.smem_bytes      = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, false);
     p.smem_bytes_emit = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, true);
     // Window walk: whole warps only; the query carries banded masks; the working set fits.
-    p.smem_bytes_window = 4u * window_smem_words(lib.cmax, p.W, p.WS);
+    p.smem_bytes_window = 4u * window_smem_words(lib.cmax, p.W, p.WS, kWinThreads);
     p.window = (p.group == 32 && n_window_units > 0 && q.bmask != nullptr && p.smem_bytes_window <= 160u * 1024u && tuning.window != 0) ? 1u : 0u;
     p.window_stage = 0;
     if (p.window && n_seqs == 1 && known_band >= 0 && known_band <= kWindowBandMax && tuning.window_stage > 0) {
         // occurrence table + banded mask of the one sequence in shared memory, next to the warps' scratch
-        const uint32_t staged = 4u * window_stage_words(q.occ_rows, q.occ_stride, max_len, (uint32_t)band_words(known_band));
-        if (p.smem_bytes_window + staged <= 110u * 1024u) {   // two CTAs per SM at least
-            p.window_stage = 1;
-            p.smem_bytes_window += staged;
+        const uint32_t staged = 4u * (window_stage_words(q.occ_rows, q.occ_stride, max_len, (uint32_t)band_words(known_band)) +
+                                      window_smem_words(lib.cmax, p.W, p.WS, kWinThreadsStaged));
+        if (staged <= 110u * 1024u) {   // two CTAs of 16 warps per SM
+            p.window_stage      = 1;
+            p.smem_bytes_window = staged;
         }
     }
     return p;
@@ -1625,7 +1644,9 @@ cudaError_t launch_band(const DevQuery& q, int32_t* band, uint32_t* bmask, cudaS
     slices          = slices < 1 ? 1u : slices > 64 ? 64u : slices;
     dim3 grid(q.n_seqs, slices);
     band_kernel<<<grid, 256, 0, s>>>(q, band);
+    BSS_SYNC_CHECK("band_kernel", s);
     if (bmask) bandmask_kernel<<<grid, 256, 0, s>>>(q, bmask);   // (reads the bands the kernel before it wrote)
+    BSS_SYNC_CHECK("bandmask_kernel", s);
     return cudaGetLastError();
 }
 
@@ -1638,23 +1659,34 @@ cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, 
     }
     dim3 grid(q.n_seqs, (q.occ_stride + kOccSliceWords - 1) / kOccSliceWords);
     occ_kernel<<<grid, 128, 0, s>>>(q, lib, occ, kmers);
+    BSS_SYNC_CHECK("occ_kernel", s);
     return cudaGetLastError();
 }
+
+#ifdef BSS_DEBUG_ASSERT
+uint32_t g_dbg_grid = 0, g_dbg_smem_extra = 0;
+#endif
 
 template <bool EMIT>
 cudaError_t launch_window(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records, uint64_t capacity_words,
                           int sm_count, cudaStream_t s)
 {
     // persistent warps: the list lengths are read on the device
-    const uint32_t per_sm = plan.smem_bytes_window ? std::min<uint32_t>(8u, (200u * 1024u) / plan.smem_bytes_window) : 8u;
-    const uint32_t grid   = (uint32_t)sm_count * (per_sm ? per_sm : 1u);
-    const uint32_t smem   = plan.smem_bytes_window;
+    const uint32_t most   = plan.window_stage ? 2u : 8u;
+    const uint32_t per_sm = plan.smem_bytes_window ? std::min<uint32_t>(most, (200u * 1024u) / plan.smem_bytes_window) : most;
+    uint32_t grid = (uint32_t)sm_count * (per_sm ? per_sm : 1u);
+    uint32_t smem = plan.smem_bytes_window;
+#ifdef BSS_DEBUG_ASSERT
+    if (g_dbg_grid) grid = g_dbg_grid;
+    smem += g_dbg_smem_extra;
+#endif
 #define BSS_LAUNCH_WIN(STAGE)                                                                                            \
     do {                                                                                                                 \
         auto kernel = window_kernel<EMIT, STAGE>;                                                                        \
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
         if (e != cudaSuccess) return e;                                                                                  \
-        kernel<<<grid, kWinThreads, smem, s>>>(lib, q, plan, work, records, capacity_words);                             \
+        kernel<<<grid, (STAGE) ? kWinThreadsStaged : kWinThreads, smem, s>>>(lib, q, plan, work, records, capacity_words);  \
+        BSS_SYNC_CHECK(EMIT ? "window_kernel emit" : "window_kernel count", s);                                          \
     } while (0)
     if (plan.window_stage) BSS_LAUNCH_WIN(true); else BSS_LAUNCH_WIN(false);
 #undef BSS_LAUNCH_WIN
@@ -1668,6 +1700,7 @@ cudaError_t launch_route(const DevLibrary& lib, const DevQuery& q, const Work& w
     uint64_t grid = (n_items + 255) / 256;
     if (grid > (uint64_t)sm_count * 64) grid = (uint64_t)sm_count * 64;
     route_kernel<<<(uint32_t)grid, 256, 0, s>>>(lib, q, work, n_items);
+    BSS_SYNC_CHECK("route_kernel", s);
     return cudaGetLastError();
 }
 
@@ -1688,6 +1721,7 @@ cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& p
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s)
 {
     scan_kernel<<<1, 1024, 0, s>>>(plan, work, q.n_seqs);
+    BSS_SYNC_CHECK("scan_kernel", s);
     return cudaGetLastError();
 }
 
@@ -1751,6 +1785,17 @@ extern "C" int bss_debug_phase_cycles(unsigned long long* out, int reset)
 #endif
 
 #ifdef BSS_DEBUG_ASSERT
+extern "C" void bss_debug_set_launch(unsigned grid, unsigned smem_extra)
+{
+    bss::g_dbg_grid       = grid;
+    bss::g_dbg_smem_extra = smem_extra;
+}
+
+extern "C" int bss_debug_set_skip(int mask)
+{
+    return (int)cudaMemcpyToSymbol(bss::g_win_skip, &mask, sizeof mask);
+}
+
 extern "C" int bss_debug_assert_counts(unsigned int* out)
 {
     cudaDeviceSynchronize();

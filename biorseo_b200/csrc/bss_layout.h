@@ -24,7 +24,8 @@ constexpr uint32_t kCheckFixed  = 1u << 24;    // check flag: no end moves at th
 constexpr uint32_t kCheckOrdered = 1u << 25;   // check flag: 0 <= u < v < n holds for every placement (u = word 0's end)
 constexpr uint32_t kCheckRow    = 1u << 26;    // check flag: u < v holds for every placement, u on an earlier component, v = candidate + offset >= candidate:
                                                //             the candidates that pass are the bits of mask row u shifted down by the offset (window walk)
-constexpr uint32_t kUnitWindow  = 1u;          // blob[3] / unit_flags bit: every level >= 1 has a row check (window walk eligible)
+constexpr uint32_t kUnitWindow  = 1u;          // blob[3] / unit_flags bit: every level >= 1 has a row check and the descriptor fits the staging area (window walk eligible)
+constexpr uint32_t kBlobStageWords = 64;       // unit descriptor words staged in shared memory per warp; larger descriptors are read in place
 constexpr int      kWindowBandMax = 255;       // widest pair (v - u) a sequence's mask may allow for the window walk
 
 // Unit descriptor ("blob"), u32 words, one per unit, addressed by unit_off[unit]:

@@ -16,10 +16,13 @@
 #pragma once
 // (bss_window_walk.h is included by bss_kernels.cu at file scope)
 
-constexpr int kWinThreads = 128;   // 4 warps per CTA, one item per warp at a time
-#ifndef BSS_WIN_MIN_CTAS
-#define BSS_WIN_MIN_CTAS 8
+#ifdef BSS_DEBUG_ASSERT
+__device__ int g_win_skip;   // debug build: 1 skip the walk, 2 skip thin + walk, 4 skip match too
 #endif
+
+// One item per warp at a time. 4 warps per CTA, 8 CTAs per SM; with staged tables 16 warps per CTA, 2 CTAs per SM,
+// so that the 46 KB copy of the query's tables is shared by 16 warps and 32 warps stay resident.
+constexpr int kWinThreads = 128, kWinThreadsStaged = 512;
 
 // 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier (sm_90+; UBLKCP in SASS).
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,9 +127,9 @@ __global__ void __launch_bounds__(256) route_kernel(const DevLibrary lib, const 
     }
 }
 
-__host__ __device__ inline uint32_t window_smem_words(uint32_t cmax, uint32_t W, uint32_t WS)
+__host__ __device__ inline uint32_t window_smem_words(uint32_t cmax, uint32_t W, uint32_t WS, uint32_t threads)
 {
-    return (kWinThreads / 32) * (kBlobStage + 2 * cmax * (W + WS)) + 3 * cmax * kWinThreads;
+    return (threads / 32) * (kBlobStage + 2 * cmax * (W + WS)) + 3 * cmax * threads;
 }
 
 // Occurrence table + banded mask of ONE sequence staged in shared memory (words), when the plan asks for it.
@@ -188,16 +191,19 @@ __device__ __forceinline__ bool gate_open_any(const uint32_t* gblob, const uint3
 }
 
 template <bool EMIT, bool STAGE>
-__global__ void __launch_bounds__(kWinThreads, BSS_WIN_MIN_CTAS) window_kernel(const DevLibrary lib, const DevQuery query, const Plan plan,
-                                                                               const Work work, uint32_t* __restrict__ records,
-                                                                               uint64_t capacity_words)
+#ifndef BSS_WIN_MIN_CTAS
+#define BSS_WIN_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE ? 2 : BSS_WIN_MIN_CTAS)
+    window_kernel(const DevLibrary lib, const DevQuery query, const Plan plan, const Work work, uint32_t* __restrict__ records, uint64_t capacity_words)
 {
+    constexpr int THREADS = STAGE ? kWinThreadsStaged : kWinThreads;
     using Gr = Group<32>;
     const uint32_t n_list = (uint32_t)work.totals[EMIT ? 5 : 6];
     if (n_list == 0) return;
     if (EMIT && work.totals[0] > capacity_words) return;   // the records would not fit: nothing is written
     extern __shared__ __align__(16) uint32_t smem_raw[];
-    constexpr uint32_t warps = kWinThreads / 32;
+    constexpr uint32_t warps = THREADS / 32;
     const int          W = (int)plan.W, WS = (int)plan.WS;
     const uint32_t     warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -220,8 +226,8 @@ __global__ void __launch_bounds__(kWinThreads, BSS_WIN_MIN_CTAS) window_kernel(c
             if (b1) bulk_g2s(d_bm, query.bmask, b1, &bar);
         }
         // the tails that are not a multiple of 16 bytes
-        for (uint32_t i = (occ_words & ~3u) + threadIdx.x; i < occ_words; i += kWinThreads) d_occ[i] = query.occ[i];
-        for (uint32_t i = (bm_words & ~3u) + threadIdx.x; i < bm_words; i += kWinThreads) d_bm[i] = query.bmask[i];
+        for (uint32_t i = (occ_words & ~3u) + threadIdx.x; i < occ_words; i += THREADS) d_occ[i] = query.occ[i];
+        for (uint32_t i = (bm_words & ~3u) + threadIdx.x; i < bm_words; i += THREADS) d_bm[i] = query.bmask[i];
         __syncthreads();   // the barrier is initialised before anyone waits on it
         mbar_wait(&bar, 0);
         __syncthreads();
@@ -233,7 +239,15 @@ __global__ void __launch_bounds__(kWinThreads, BSS_WIN_MIN_CTAS) window_kernel(c
     uint32_t* g_T    = base + warp * lib.cmax * W;                     base += warps * lib.cmax * W;
     uint32_t* g_SM   = base + warp * lib.cmax * WS;                    base += warps * lib.cmax * WS;
     uint32_t* g_ST   = base + warp * lib.cmax * WS;                    base += warps * lib.cmax * WS;
-    uint32_t* col    = base + threadIdx.x;   // three columns of cmax entries per thread, stride kWinThreads
+    uint32_t* col    = base + threadIdx.x;   // three columns of cmax entries per thread, stride THREADS
+#ifdef BSS_DEBUG_ASSERT
+    if ((g_win_skip & 64) && blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t dyn;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        printf("[win dbg] EMIT %d dyn smem %u B, plan says %u B, used %u B, cmax %u W %d WS %d n_list %u\n", (int)EMIT, dyn, plan.smem_bytes_window,
+               (uint32_t)((base - smem_raw) + 3 * lib.cmax * THREADS) * 4u, lib.cmax, W, WS, n_list);
+    }
+#endif
 
     unsigned long long* cursor = reinterpret_cast<unsigned long long*>(work.totals + 8);
     uint32_t            slot;
@@ -248,6 +262,7 @@ __global__ void __launch_bounds__(kWinThreads, BSS_WIN_MIN_CTAS) window_kernel(c
         uint32_t next_slot = 0;
         if (!EMIT && lane == 0) next_slot = (uint32_t)atomicAdd(cursor, 1ull);   // drawn ahead: its latency hides behind this item
         const uint32_t item = EMIT ? work.alive_w[slot] : work.wlist[slot];
+        if (!BSS_WIN_CHECK((uint64_t)item < (uint64_t)query.n_seqs * lib.n_units, 21)) break;
         const uint32_t qi   = item / lib.n_units;
         const uint32_t u    = item - qi * lib.n_units;
         const SeqCtx   sq   = load_seq(lib, query, qi);
@@ -266,19 +281,24 @@ __global__ void __launch_bounds__(kWinThreads, BSS_WIN_MIN_CTAS) window_kernel(c
         const uint32_t  boff  = __ldg(lib.unit_off + u);
         const uint32_t  blen  = __ldg(lib.unit_off + u + 1) - boff;
         const uint32_t* gblob = lib.blob + boff;
-        const uint32_t* blob  = gblob;
-        if (blen <= kBlobStage) {
-            for (uint32_t i = lane; i < blen; i += 32) g_blob[i] = __ldg(gblob + i);
-            blob = g_blob;
-            __syncwarp();
-        }
+        if (!BSS_WIN_CHECK(blen >= 6 && blen <= kBlobStage, 22)) break;
+        // (window-walk units always fit the staging area: the library builder only flags those that do, so every
+        //  descriptor read of the walk is a shared-memory load)
+        for (uint32_t i = lane; i < blen; i += 32) g_blob[i] = __ldg(gblob + i);
+        const uint32_t* blob = g_blob;
+        __syncwarp();
         const uint32_t module = blob[0] + lib.module_base;
         const int      C      = (int)(blob[1] & 0xFFu);
         const uint32_t gate   = blob[2];
+        if (!BSS_WIN_CHECK(C >= 1 && C <= (int)lib.cmax && n >= 0 && n <= (int)query.max_len && chunk < plan.n_chunks, 23)) break;
         const uint32_t* occ   = STAGE ? s_occ : sq.occ;
         const int       WP    = (int)query.occ_stride;
 
         bool alive = true;
+#ifdef BSS_DEBUG_ASSERT
+        if (g_win_skip & 4) alive = false;
+        if ((g_win_skip >> 8) && u != (uint32_t)(g_win_skip >> 8) - 1u) alive = false;   // one unit only
+#endif
         if (!EMIT && gate != kNoGate) {   // items on the alive list have passed their gate
             alive = gate_open_any(lib.blob + __ldg(lib.unit_off + gate), occ, WP, g_M, g_SM, W, WS, n);
             __syncwarp();
@@ -286,6 +306,9 @@ __global__ void __launch_bounds__(kWinThreads, BSS_WIN_MIN_CTAS) window_kernel(c
         if (alive) alive = match_components_any(blob, occ, WP, g_M, g_SM, W, WS, n);
 
         uint64_t lane_sites = 0, item_sites = 0;
+#ifdef BSS_DEBUG_ASSERT
+        if (g_win_skip & 2) alive = false;
+#endif
         if (alive) {
             win::Ctx cx;
             cx.blob = blob; cx.M = g_M; cx.T = g_T; cx.SM = g_SM; cx.ST = g_ST;
@@ -293,23 +316,33 @@ __global__ void __launch_bounds__(kWinThreads, BSS_WIN_MIN_CTAS) window_kernel(c
             cx.K    = band_words(sq.band);
             cx.bm   = STAGE ? s_bm : query.bmask + (size_t)kBandWordsMax * query.seq_begin[qi];
             cx.pos  = col;
-            cx.bits = col + lib.cmax * kWinThreads;
-            cx.grd  = col + 2 * lib.cmax * kWinThreads;
+            cx.bits = col + lib.cmax * THREADS;
+            cx.grd  = col + 2 * lib.cmax * THREADS;
             cx.ovl  = thin_components<32>(blob, g_M, g_SM, g_T, g_ST, W, WS);
-            cx.W = W; cx.WS = WS; cx.n = n; cx.C = C; cx.delay = (int)(blob[1] >> 16); cx.cs = kWinThreads;
+            cx.W = W; cx.WS = WS; cx.n = n; cx.C = C; cx.delay = (int)(blob[1] >> 16); cx.cs = THREADS;
             // lane l owns the words [l * per, (l + 1) * per) of the first component's candidates: lane order = position order
             const int per = (sq.Wq + 31) >> 5;
             const int w0 = min(sq.Wq, (int)lane * per), w1 = min(sq.Wq, w0 + per);
+#ifdef BSS_DEBUG_ASSERT
+            if (g_win_skip & 1) { __syncwarp(); goto skip_walk; }
+#endif
             if (EMIT) {
                 const uint64_t mine = work.lane_counts_w[(size_t)slot * 32 + lane];
                 uint64_t       total;
                 const uint64_t ex = Gr::exclusive(mine, total);
-                if (mine) win::walk_words<true>(cx, w0, w1, module, records + out_words + ex * (uint64_t)(C + 1));
+                if (mine && BSS_WIN_CHECK(out_words + (ex + mine) * (uint64_t)(C + 1) <= work.totals[0], 24)) {
+                    const uint64_t wrote = win::walk_words<true>(cx, w0, w1, module, records + out_words + ex * (uint64_t)(C + 1));
+                    (void)BSS_WIN_CHECK(wrote == mine, 25);
+                }
             } else {
                 lane_sites = win::walk_words<false>(cx, w0, w1, module, nullptr);
                 item_sites = Gr::sum(lane_sites);
             }
         }
+#ifdef BSS_DEBUG_ASSERT
+    skip_walk:
+        if (g_win_skip & 8) { item_sites = 0; lane_sites = 0; }   // walk, but drop what it found
+#endif
         __syncwarp();   // the warp's scratch is reused by its next item
         if (!EMIT) {
             uint32_t where = 0;
@@ -325,7 +358,7 @@ __global__ void __launch_bounds__(kWinThreads, BSS_WIN_MIN_CTAS) window_kernel(c
             }
             if (item_sites) {
                 where = Gr::first(where);
-                work.lane_counts_w[(size_t)where * 32 + lane] = (uint32_t)lane_sites;
+                if (BSS_WIN_CHECK((uint64_t)where < (uint64_t)query.n_seqs * lib.n_units, 26)) work.lane_counts_w[(size_t)where * 32 + lane] = (uint32_t)lane_sites;
             }
             slot = Gr::first(next_slot);
         } else {

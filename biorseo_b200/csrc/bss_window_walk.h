@@ -24,10 +24,44 @@
 
 #include "bss_layout.h"
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(BSS_WALK_NOINLINE)
+#define BSS_HD __host__ __device__ __noinline__
+#elif defined(__CUDACC__)
 #define BSS_HD __host__ __device__ __forceinline__
 #else
 #define BSS_HD inline
+#endif
+
+// Optional index checks of the debug build (bss_kernels.cu defines it with -DBSS_DEBUG_ASSERT): a violated
+// condition is counted and the access is skipped.
+#ifndef BSS_WIN_CHECK
+#define BSS_WIN_CHECK(cond, id) true
+#endif
+
+#if defined(__CUDACC__)
+#define BSS_HD_NI __host__ __device__ __noinline__
+#else
+#define BSS_HD_NI inline
+#endif
+#ifdef BSS_NI_ROW
+#define BSS_HD_ROW BSS_HD_NI
+#else
+#define BSS_HD_ROW BSS_HD
+#endif
+#ifdef BSS_NI_LEVEL
+#define BSS_HD_LEVEL BSS_HD_NI
+#else
+#define BSS_HD_LEVEL BSS_HD
+#endif
+#ifdef BSS_NI_WALK
+#define BSS_HD_WALK BSS_HD_NI
+#else
+#define BSS_HD_WALK BSS_HD
+#endif
+#ifdef BSS_NI_MISC
+#define BSS_HD_MISC BSS_HD_NI
+#else
+#define BSS_HD_MISC BSS_HD
 #endif
 
 namespace bss {
@@ -61,8 +95,9 @@ struct Ctx {
 };
 
 // First set bit at or after position t (t >= 0) of a bitset with a one-bit-per-word summary, or -1.
-BSS_HD int next_set(const uint32_t* B, const uint32_t* S, int W, int WS, int t)
+BSS_HD_MISC int next_set(const uint32_t* B, const uint32_t* S, int W, int WS, int t)
 {
+    if (!BSS_WIN_CHECK(t >= 0, 18)) return -1;
     int w = t >> 5;
     if (w >= W) return -1;
     uint32_t x = B[w] & (0xFFFFFFFFu << (t & 31));
@@ -75,17 +110,27 @@ BSS_HD int next_set(const uint32_t* B, const uint32_t* S, int W, int WS, int t)
         s = S[sw];
     }
     w = (sw << 5) + ffs32(s) - 1;
+    if (!BSS_WIN_CHECK(w < W && B[w] != 0, 19)) return -1;
     return (w << 5) + ffs32(B[w]) - 1;
 }
 
-BSS_HD bool bit_of(const uint32_t* B, int q) { return (B[q >> 5] >> (q & 31)) & 1u; }
+BSS_HD bool bit_of(const uint32_t* B, int q)
+{
+    if (!BSS_WIN_CHECK(q >= 0, 20)) return false;
+    return (B[q >> 5] >> (q & 31)) & 1u;
+}
 
-BSS_HD int placed(const Ctx& cx, int level) { return (int)(cx.pos[level * cx.cs] & 0xFFFFu); }
+BSS_HD int placed(const Ctx& cx, int level)
+{
+    if (!BSS_WIN_CHECK(level >= 0 && level < cx.C, 17)) return 0;
+    return (int)(cx.pos[level * cx.cs] & 0xFFFFu);
+}
 
 // Word w (absolute index into the mask row) of row u of the pair mask; zero outside the band.
 BSS_HD uint32_t row_word(const Ctx& cx, int u, int w)
 {
     const unsigned j = (unsigned)(w - (u >> 5));
+    if (!BSS_WIN_CHECK(u >= 0 && u < cx.n, 16)) return 0u;
     return j < (unsigned)cx.K ? cx.bm[u * cx.K + (int)j] : 0u;
 }
 
@@ -98,7 +143,7 @@ BSS_HD bool pair_allowed(const Ctx& cx, int u, int v)
 
 // The checks of level `level` that are not row checks, one candidate at a time (rare: pairs inside one
 // strand, absolute positions, ends outside their component).
-BSS_HD bool generic_pass(const Ctx& cx, int level)
+BSS_HD_MISC bool generic_pass(const Ctx& cx, int level)
 {
     const uint32_t  range = cx.blob[5 + 2 * level];
     const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
@@ -115,7 +160,7 @@ BSS_HD bool generic_pass(const Ctx& cx, int level)
 }
 
 // x = bits of word w of the chain set of component c; keeps the positions that satisfy every row check of the level.
-BSS_HD uint32_t row_filter(const Ctx& cx, int c, int w, uint32_t x)
+BSS_HD_ROW uint32_t row_filter(const Ctx& cx, int c, int w, uint32_t x)
 {
     const uint32_t  range = cx.blob[5 + 2 * c];
     const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
@@ -132,23 +177,80 @@ BSS_HD uint32_t row_filter(const Ctx& cx, int c, int w, uint32_t x)
     return x;
 }
 
-BSS_HD bool row_pass(const Ctx& cx, int c, int q)
+BSS_HD_ROW bool row_pass(const Ctx& cx, int c, int q)
 {
     return (row_filter(cx, c, q >> 5, 1u << (q & 31)) >> (q & 31)) & 1u;
 }
 
-// Next candidate of level c at or after `start` (a position of the thinned part of the chain), up to hi.
-BSS_HD int scan_from(const Ctx& cx, int c, int start, int hi)
+// One step of the walk at level c (>= 1): with `enter`, the first candidate of component c below the current
+// placement of components 0 .. c-1; otherwise the candidate after the current one. Returns its position or -1.
+// A single routine (one copy of the scan loop in the kernel) instead of separate first / next functions.
+BSS_HD_LEVEL int level_step(const Ctx& cx, int c, bool enter)
 {
+    const int       kc = (int)(cx.blob[4 + 2 * c] & 0xFFu), ke = imax(1, kc);
     const bool      thinned = (cx.ovl >> c) & 1u;
-    const uint32_t* S  = (thinned ? cx.T : cx.M) + c * cx.W;
-    const uint32_t* SS = (thinned ? cx.ST : cx.SM) + c * cx.WS;
-    int             q  = start;
+    const uint32_t *M = cx.M + c * cx.W, *SM = cx.SM + c * cx.WS;
+    const uint32_t *S = thinned ? cx.T + c * cx.W : M, *SS = thinned ? cx.ST + c * cx.WS : SM;
+    int             start, hi;
+    bool            greedy;
+    if (enter) {
+        const int kprev = (int)(cx.blob[4 + 2 * (c - 1)] & 0xFFu);
+        start = placed(cx, c - 1) + kprev - 1 + cx.delay;    // start of the suffix the component is searched in (inside the sequence)
+        hi    = cx.n - kc - (c < cx.C - 1 ? cx.delay : 0);   // the pattern fits and leaves room for the next component
+        if (cx.band < 0) return -1;                          // no pair at all is allowed: the level's row check cannot hold
+        const uint32_t  range = cx.blob[5 + 2 * c];
+        const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
+        const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
+        for (int i = cb; i < ce; i++) {   // v = candidate + ob must lie in (u, u + band] and inside the sequence
+            const uint32_t ea = chk[2 * i];
+            if (!(ea & kCheckRow)) continue;
+            const int u  = placed(cx, anchor_of(ea)) + off_of(ea);
+            const int ob = off_of(chk[2 * i + 1]);
+            if (u < 0) return -1;
+            hi = imin(hi, imin(u + cx.band, cx.n - 1) - ob);
+        }
+        if (start > hi) return -1;
+        greedy = thinned;   // the reference's iterator restarts at `start`: a greedy walk over all matches until it meets the thinned set
+    } else {
+        const uint32_t e = cx.pos[c * cx.cs];
+        const int      p = (int)(e & 0xFFFFu);
+        hi     = (int)(e >> 16);
+        greedy = cx.grd[c * cx.cs] != 0;
+        if (greedy) {
+            start = p + ke;
+        } else {
+            const uint32_t x = cx.bits[c * cx.cs];   // candidates left in the word of the current one
+            if (x) {
+                const int q = (p & ~31) + ffs32(x) - 1;
+                if (q > hi) return -1;
+                cx.bits[c * cx.cs] = x & (x - 1u);
+                cx.pos[c * cx.cs]  = (uint32_t)q | ((uint32_t)hi << 16);
+                return q;
+            }
+            start = (p | 31) + 1;
+        }
+    }
+    if (greedy) {
+        int q = next_set(M, SM, cx.W, cx.WS, start);
+        while (q >= 0 && q <= hi && !bit_of(S, q)) {
+            if (row_pass(cx, c, q)) {
+                cx.grd[c * cx.cs]  = 1;
+                cx.bits[c * cx.cs] = 0;
+                cx.pos[c * cx.cs]  = (uint32_t)q | ((uint32_t)hi << 16);
+                return q;
+            }
+            q = next_set(M, SM, cx.W, cx.WS, q + ke);
+        }
+        if (q < 0 || q > hi) return -1;
+        start = q;   // the chain has met the thinned set: it is the thinned set from here on
+    }
+    cx.grd[c * cx.cs] = 0;
+    int q = start;
     while (q <= hi) {
         q = next_set(S, SS, cx.W, cx.WS, q);   // skips the empty words through the summary
         if (q < 0 || q > hi) return -1;
-        const int w = q >> 5;
-        uint32_t  x = row_filter(cx, c, w, S[w] & (0xFFFFFFFFu << (q & 31)));
+        const int      w = q >> 5;
+        const uint32_t x = row_filter(cx, c, w, S[w] & (0xFFFFFFFFu << (q & 31)));
         if (x) {
             const int p = (w << 5) + ffs32(x) - 1;
             if (p > hi) return -1;
@@ -161,81 +263,10 @@ BSS_HD int scan_from(const Ctx& cx, int c, int start, int hi)
     return -1;
 }
 
-// First candidate of component c below the current placement of components 0 .. c-1, or -1.
-BSS_HD int level_first(const Ctx& cx, int c)
-{
-    const int kprev = (int)(cx.blob[4 + 2 * (c - 1)] & 0xFFu), kc = (int)(cx.blob[4 + 2 * c] & 0xFFu);
-    const int t     = placed(cx, c - 1) + kprev - 1 + cx.delay;   // start of the suffix the component is searched in (inside the sequence)
-    int       hi    = cx.n - kc - (c < cx.C - 1 ? cx.delay : 0);  // the pattern fits and leaves room for the next component
-    if (cx.band < 0) return -1;                                   // no pair at all is allowed: the level's row check cannot hold
-    const uint32_t  range = cx.blob[5 + 2 * c];
-    const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
-    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
-    for (int i = cb; i < ce; i++) {   // v = candidate + ob must lie in (u, u + band] and inside the sequence
-        const uint32_t ea = chk[2 * i];
-        if (!(ea & kCheckRow)) continue;
-        const int u  = placed(cx, anchor_of(ea)) + off_of(ea);
-        const int ob = off_of(chk[2 * i + 1]);
-        if (u < 0) return -1;
-        hi = imin(hi, imin(u + cx.band, cx.n - 1) - ob);
-    }
-    if (t > hi) return -1;
-    cx.grd[c * cx.cs] = 0;
-    if ((cx.ovl >> c) & 1u) {
-        // the reference's iterator restarts at t: greedy walk over all matches until it meets the thinned set
-        const uint32_t *M = cx.M + c * cx.W, *SM = cx.SM + c * cx.WS, *T = cx.T + c * cx.W;
-        const int       ke = imax(1, kc);
-        int             q  = next_set(M, SM, cx.W, cx.WS, t);
-        while (q >= 0 && q <= hi && !bit_of(T, q)) {
-            if (row_pass(cx, c, q)) {
-                cx.grd[c * cx.cs]  = 1;
-                cx.bits[c * cx.cs] = 0;
-                cx.pos[c * cx.cs]  = (uint32_t)q | ((uint32_t)hi << 16);
-                return q;
-            }
-            q = next_set(M, SM, cx.W, cx.WS, q + ke);
-        }
-        if (q < 0 || q > hi) return -1;
-        return scan_from(cx, c, q, hi);
-    }
-    return scan_from(cx, c, t, hi);
-}
-
-// Next candidate of level c after the current one, or -1.
-BSS_HD int level_next(const Ctx& cx, int c)
-{
-    const uint32_t e = cx.pos[c * cx.cs];
-    const int      p = (int)(e & 0xFFFFu), hi = (int)(e >> 16);
-    if (cx.grd[c * cx.cs]) {
-        const uint32_t *M = cx.M + c * cx.W, *SM = cx.SM + c * cx.WS, *T = cx.T + c * cx.W;
-        const int       ke = imax(1, (int)(cx.blob[4 + 2 * c] & 0xFFu));
-        int             q  = next_set(M, SM, cx.W, cx.WS, p + ke);
-        while (q >= 0 && q <= hi && !bit_of(T, q)) {
-            if (row_pass(cx, c, q)) {
-                cx.pos[c * cx.cs] = (uint32_t)q | ((uint32_t)hi << 16);
-                return q;
-            }
-            q = next_set(M, SM, cx.W, cx.WS, q + ke);
-        }
-        if (q < 0 || q > hi) return -1;
-        cx.grd[c * cx.cs] = 0;   // the chain has met the thinned set: it is the thinned set from here on
-        return scan_from(cx, c, q, hi);
-    }
-    const uint32_t x = cx.bits[c * cx.cs];
-    if (x) {
-        const int q = (p & ~31) + ffs32(x) - 1;
-        if (q > hi) return -1;
-        cx.bits[c * cx.cs] = x & (x - 1u);
-        cx.pos[c * cx.cs]  = (uint32_t)q | ((uint32_t)hi << 16);
-        return q;
-    }
-    return scan_from(cx, c, (p | 31) + 1, hi);
-}
-
 // Every site whose first component lies in the words [w0, w1) of its candidate set. Returns their number;
 // when EMIT, writes their records [module, p_0 .. p_{C-1}] from `out` on, in depth-first order.
 template <bool EMIT>
-BSS_HD uint64_t walk_words(const Ctx& cx, int w0, int w1, uint32_t module, uint32_t* out)
+BSS_HD_WALK uint64_t walk_words(const Ctx& cx, int w0, int w1, uint32_t module, uint32_t* out)
 {
     const int       C = cx.C, R = C + 1;
     const uint32_t* first = (cx.ovl & 1u) ? cx.T : cx.M;   // the chain from position 0 starts on a run start: it is the thinned set
@@ -253,18 +284,16 @@ BSS_HD uint64_t walk_words(const Ctx& cx, int w0, int w1, uint32_t module, uint3
                 found++;
                 continue;
             }
-            int level = 1;
-            int q     = level_first(cx, 1);
+            int  level = 1;
+            bool enter = true;
             for (;;) {
+                const int q = level_step(cx, level, enter);
+                enter       = false;
                 if (q < 0) {   // this level is exhausted: on to the next candidate of its parent
                     if (--level == 0) break;
-                    q = level_next(cx, level);
                     continue;
                 }
-                if ((cx.blob[4 + 2 * level] & kCompGeneric) && !generic_pass(cx, level)) {
-                    q = level_next(cx, level);
-                    continue;
-                }
+                if ((cx.blob[4 + 2 * level] & kCompGeneric) && !generic_pass(cx, level)) continue;
                 if (level == C - 1) {
                     if (EMIT) {
                         uint32_t* rec = out + found * (uint64_t)R;
@@ -272,11 +301,10 @@ BSS_HD uint64_t walk_words(const Ctx& cx, int w0, int w1, uint32_t module, uint3
                         for (int c = 0; c < C; c++) rec[1 + c] = (uint32_t)placed(cx, c);
                     }
                     found++;
-                    q = level_next(cx, level);
                     continue;
                 }
                 level++;
-                q = level_first(cx, level);
+                enter = true;
             }
         }
     }

@@ -125,7 +125,11 @@ int window_host_search(const bss_table* t, const char* seq_bytes, uint32_t n_u, 
                 bm[(size_t)u * K + j] = x;
             }
     const int cs = 32;   // column stride: 32 emulated lanes
-    std::vector<uint32_t> cols((size_t)3 * lib.cmax * cs);
+    // (the columns start from a poison value taken from the environment: the walk must never read a column entry it
+    //  has not written for the current item, so the result may not depend on it)
+    const char*           poison_env = std::getenv("WINDOW_HOST_POISON");
+    const uint32_t        poison = poison_env ? (uint32_t)std::strtoul(poison_env, nullptr, 0) : 0u;
+    std::vector<uint32_t> cols((size_t)3 * lib.cmax * cs, poison);
     for (uint32_t u = 0; u < t->n_units; u++) {
         unit_window[u] = 0;
         if (!narrow || !(lib.unit_flags[u] & bss::kUnitWindow)) continue;
@@ -148,6 +152,7 @@ int window_host_search(const bss_table* t, const char* seq_bytes, uint32_t n_u, 
         bss::win::Ctx cx;
         cx.blob = blob; cx.M = M.data(); cx.T = T.data(); cx.SM = SM.data(); cx.ST = ST.data(); cx.bm = bm.data();
         cx.ovl = ovl; cx.W = W; cx.WS = WS; cx.n = n; cx.K = K; cx.C = uv.C; cx.delay = uv.delay; cx.band = band; cx.cs = cs;
+        std::fill(cols.begin(), cols.end(), poison);
         const int per = (Wq + 31) >> 5;
         uint64_t  lane_sites[32], total = 0;
         for (int lane = 0; lane < 32; lane++) {
@@ -159,6 +164,7 @@ int window_host_search(const bss_table* t, const char* seq_bytes, uint32_t n_u, 
         const size_t R = (size_t)uv.C + 1, base = out.size();
         out.resize(base + total * R, 0xDEADBEEFu);
         uint64_t before = 0;
+        std::fill(cols.begin(), cols.end(), ~poison);
         for (int lane = 0; lane < 32; lane++) {
             cx.pos = cols.data() + lane; cx.bits = cx.pos + lib.cmax * cs; cx.grd = cx.pos + 2 * lib.cmax * cs;
             const int w0 = std::min(Wq, lane * per), w1 = std::min(Wq, w0 + per);

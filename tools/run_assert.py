@@ -5,7 +5,7 @@ from biorseo_b200 import build, capi
 if len(sys.argv) > 1 and sys.argv[1] == "build":     # here (no GPU needed): python tools/run_assert.py build
     os.makedirs(os.path.join(ROOT, "tools", "_build"), exist_ok=True)
     srcs = [os.path.join(build.HERE, s) for s in build.CUDA_SOURCES + build.HOST_SOURCES]
-    subprocess.run([build._nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-DBSS_DEBUG_ASSERT",
+    subprocess.run([build._nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-DBSS_DEBUG_ASSERT", "-DBSS_DEBUG_SYNC",
                     "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(build.HERE, "host"), "-I", os.path.join(build.HERE, "csrc"),
                     "-o", os.path.join(ROOT, "tools", "_build", "libassert.so")] + srcs, check=True)
     sys.exit(0)
