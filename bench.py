@@ -195,10 +195,45 @@ class ClockSampler(threading.Thread):
 # reference arm / CPU baseline: the reference's own Pool-threaded search (oracle/_ref), or
 # the C++ port of it when the compiled reference is absent
 # ----------------------------------------------------------------------------------------
+def rin_placements_estimate(path, n):
+    """Expected placements of a CaRNAval RIN file before the pair filters on a uniform n-nt query: the reference
+    materialises every one of them (cppsrc/Motif.cpp:466-474), so modules with 10^6 and more cannot be run on the CPU."""
+    with open(path) as f:
+        lines = f.read().split("\n")[3:]
+    est = 1.0
+    for depth, line in enumerate(x for x in lines if x):
+        k = len(line.split(";")[2])
+        est *= max(1.0, n / 4.0 ** k) / (depth + 1)      # ordered placements of the strands
+    return est
+
+
+def write_sample(w, tmp, sample_modules):
+    """The bounded sample of the workload's library the CPU arms run on (the reference's own on-disk formats).
+    Returns (library path, what the sample is)."""
+    from biorseo_b200 import synth
+    if w["source"] == "rinfolder":
+        n, seed, max_components, min_len = w["rin"]
+        lib = synth.write_rin_folder(os.path.join(tmp, "rin"), n, seed, invalid_fraction=0.0, max_components=max_components, min_len=min_len)
+        sub, kept, heavy = os.path.join(lib, "Subfiles"), 0, 0
+        for i in range(n):     # module ids come from the file names: dropping files keeps the others' ids
+            f = os.path.join(sub, f"{i}.txt")
+            if kept >= sample_modules or rin_placements_estimate(f, len(w["seqs"][0])) > 2e5:
+                heavy += kept < sample_modules
+                os.remove(f)
+            else:
+                kept += 1
+        return lib, f"{kept} of the {n} RIN modules (the {heavy} left out are predicted to have more than 2e5 placements before the filters, which the reference materialises)"
+    if w["source"] == "descfolder":
+        n, seed = w["desc"]
+        m = min(n, sample_modules)
+        return synth.write_desc_folder(os.path.join(tmp, "desc"), m, seed), f"first {m} of the {n} .desc modules"
+    mods = w["modules"][:sample_modules]
+    return synth.write_json(os.path.join(tmp, "lib.json"), mods), f"first {len(mods)} of the {len(w['modules'])} JSON modules"
+
+
 def cpu_search(w, sample_modules, repeat, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import util
-    from biorseo_b200 import synth
     kind = "reference" if util.have_ref() else "port"
     binary = util.REF_BIN if kind == "reference" else util.PORT_BIN
     if not os.access(binary, os.X_OK):
@@ -206,19 +241,9 @@ def cpu_search(w, sample_modules, repeat, threads=None):
     cores = os.cpu_count() or 1
     threads = threads or max(1, cores - 1)          # the reference's own choice, cppsrc/MOIP.cpp:250
     seq, mask = w["seqs"][0], w["masks"][0]
+    placements = None
     with tempfile.TemporaryDirectory() as tmp:
-        if w["source"] == "rinfolder":
-            n, seed = w["rin"]
-            lib = synth.write_rin_folder(os.path.join(tmp, "rin"), min(n, sample_modules), seed, invalid_fraction=0.0, max_components=4, min_len=2)
-            n_modules = min(n, sample_modules)
-        elif w["source"] == "descfolder":
-            n, seed = w["desc"]
-            lib = synth.write_desc_folder(os.path.join(tmp, "desc"), min(n, sample_modules), seed)
-            n_modules = min(n, sample_modules)
-        else:
-            mods = w["modules"][:sample_modules]
-            lib = synth.write_json(os.path.join(tmp, "lib.json"), mods)
-            n_modules = len(mods)
+        lib, what = write_sample(w, tmp, sample_modules)
         seq_path, mask_path = util.write_query(tmp, seq, mask)
         t0 = time.perf_counter()
         if kind == "reference":
@@ -226,23 +251,59 @@ def cpu_search(w, sample_modules, repeat, threads=None):
                                  capture_output=True, text=True, check=True).stdout
             res = json.loads(out.strip().splitlines()[-1])
             seconds, sites, n_modules = res["seconds_mean"], res["sites"], res["modules"]
+            if w["source"] == "jsonfolder":   # the reference's real work term on the same sample (its own enumerator, untimed)
+                placements = int(subprocess.run([binary, "placements", w["source"], lib, seq_path, mask_path], capture_output=True, text=True,
+                                                check=True).stdout.strip().splitlines()[-1])
         else:   # single-threaded port, whole process timed
             threads = 1
             t1 = time.perf_counter()
             for _ in range(repeat):
                 out = subprocess.run([binary, "jobs", w["source"], lib, seq_path, mask_path], capture_output=True, text=True, check=True).stdout
             seconds, sites = (time.perf_counter() - t1) / repeat, out.count("\n")
+            n_modules = sample_modules
         wall = time.perf_counter() - t0
     tested = n_modules * len(seq) * 1   # one query of the workload
     return {"value": tested / seconds, "unit": UNIT, "cores": threads, "host_cores": cores, "kind": kind,
-            "sample": f"first {n_modules} modules of the library x query 0 ({len(seq)} nt), {repeat} pass(es), "
+            "sample": f"{what} ({n_modules} valid) x query 0 ({len(seq)} nt), {repeat} pass(es), "
                       f"push->join timed ({seconds:.3f} s/pass, {wall:.1f} s total)",
-            "sites_per_s": sites / seconds, "seconds_per_pass": seconds}
+            "sample_modules": n_modules, "sites_per_s": sites / seconds, "seconds_per_pass": seconds, "placements_enumerated": placements,
+            "placements_enumerated_per_s": placements / seconds if placements else None}
+
+
+def parity_gate(w, sample_modules, device):
+    """before anything is timed, the GPU search of the CPU sample must give the very insertion
+    sites the reference's own matcher gives (multiset of sites; the reference's order is a thread race). A mismatch
+    aborts the benchmark: a number for a wrong answer is not a number."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    import biorseo_b200 as b
+    seq, mask = w["seqs"][0], w["masks"][0]
+    with tempfile.TemporaryDirectory() as tmp:
+        lib, what = write_sample(w, tmp, sample_modules)
+        try:
+            expect = util.best_oracle(w["source"], lib, seq, mask, timeout=900, threads=max(2, (os.cpu_count() or 2) - 1))
+        except RuntimeError as exc:
+            return {"checked_modules": 0, "equal": None, "error": str(exc)[:200]}
+        host = b.HostLibrary.load(w["source"], lib)
+        dev = host.to_device(device)
+        sites = dev.search(seq, mask)
+        mine = sorted(host.records_text(sites.records()))
+        placements = dev.placements_enumerated()
+        res = {"checked_modules": host.n_modules, "sample": what + f", query 0 ({len(seq)} nt)", "sites": len(mine), "equal": mine == expect,
+               "oracle": "reference (oracle/_ref/biorseo_ref: the reference's unmodified sources)" if util.have_ref() else "port (oracle/_build/biorseo_port)",
+               "gpu_placements_enumerated": placements}
+        sites.close()
+        dev.close()
+    if not res["equal"]:
+        sys.stderr.write(f"bench: PARITY FAILURE on {w['name']}: {len(mine)} GPU sites vs {len(expect)} reference sites\n")
+        print(json.dumps({"metric": METRIC, "value": None, "parity": res, "error": "GPU insertion sites differ from the reference's"}))
+        sys.exit(3)
+    return res
 
 
 def sample_size(name):
     # bounded samples: about 1.5 s of Pool-threaded CPU search per pass on a 16-core host
-    return {"c4": 15000, "c4a": 50000, "c4b": 8000, "c4b_all": 800, "c3": 1000, "c2": 400, "c1": 1000, "c4_desc": 500}[name]
+    return {"c4": 15000, "c4_400k": 15000, "c4a": 50000, "c4b": 8000, "c4b_all": 800, "c3": 1000, "c2": 400, "c2_narrow": 400, "c1": 1000, "c4_desc": 500}[name]
 
 
 # ----------------------------------------------------------------------------------------
@@ -253,6 +314,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="N > 1: strong (default for the JSON workloads) = one library cut over the GPUs; weak = one library per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads reported under 'also'")
     args = ap.parse_args()
@@ -262,6 +325,18 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    n_gpus = world if args.impl == "b200" else args.gpus
+    scaling = args.scaling or ("strong" if n_gpus > 1 and args.workload in ("c4", "c4a", "c4b", "c4b_all", "c4_400k", "c3", "c1") else "weak")
+    if n_gpus == 1:
+        scaling = "weak"     # (one GPU: the two coincide; the contract's default label)
+
+    def config_of(w, units_total):
+        """The same keys and values in both arms (the driver compares them); the reference arm adds its sample."""
+        return {"workload": args.workload, "describe": w["describe"], "units_total": int(units_total), "scaling": scaling,
+                "parallelism": (f"library-sharded x{n_gpus}, {'one library cut by search cost' if scaling == 'strong' else 'one library per GPU'}, "
+                                "all-gather-v of site records") if n_gpus > 1 else "single GPU",
+                "l2": "flushed between steps (256 MiB write, outside the timed events)"}
+
     if args.impl == "reference":
         if rank != 0:
             return
@@ -270,13 +345,18 @@ def main():
         if res is None:
             print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/biorseo_ref nor oracle/_build/biorseo_port is built"}))
             return
+        import biorseo_b200 as b
+        with tempfile.TemporaryDirectory() as tmp:     # (the host loaders run without a GPU: the library's unit count for the config keys)
+            units_total = int(host_library(w, tmp)[0].table()["n_units"])
+        if scaling == "weak" and n_gpus > 1:
+            units_total *= n_gpus
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * res["seconds_per_pass"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": 1e3 * res["seconds_per_pass"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic", "impl": "reference",
-                "config": {"workload": args.workload, "describe": w["describe"]},
+                "config": {**config_of(w, units_total), "sample_modules": res["sample_modules"], "reference_threads": res["cores"]},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "sites_per_s": res["sites_per_s"], "gpu_launches": 0}
+                "sites_per_s": res["sites_per_s"], "placements_enumerated_per_s": res["placements_enumerated_per_s"], "gpu_launches": 0}
         print(json.dumps(line))
         return
 
@@ -294,18 +374,30 @@ def main():
 
     exchange_name = {"value": None}
 
-    def run_workload(name, steps, warmup, with_e2e=True, with_collective=True):
-        w = make_workload(name, rank)
+    def run_workload(name, steps, warmup, with_e2e=True, with_collective=True, scaling="weak"):
+        """scaling (world > 1): "weak" = every rank searches its own library of the named size; "strong" = ONE library
+        (rank 0's), cut into contiguous module ranges balanced by the search-cost estimate, one range per rank."""
+        strong = scaling == "strong" and world > 1
+        w = make_workload(name, 0 if strong else rank)
+        if strong and w["source"] != "jsonfolder":
+            raise SystemExit("strong scaling is implemented for the JSON workloads")
         with tempfile.TemporaryDirectory() as tmp:
             host, _ = host_library(w, tmp)
         table = host.table()
+        seq_lens = [len(s) for s in w["seqs"]]
+        units_total, shard = int(table["n_units"]), (0, host.n_modules)
+        if strong:
+            costs = sharded.module_costs(table, max(seq_lens))
+            shard = sharded.shard_ranges_by_cost(costs, world)[rank]
+            host = b.HostLibrary.from_json_modules(w["modules"][shard[0]:shard[1]])
+            table = host.table()
         dev = host.to_device(local_rank)
-        dev.set_module_base(rank * host.n_modules)
+        dev.set_module_base(shard[0] if strong else rank * host.n_modules)
         stream = bench_stream                # a real (non-default) stream: kernels, collectives and the timing events all go there
         dev.set_stream(stream.cuda_stream)
         query = dev.query(w["seqs"], w["masks"])
-        seq_lens = [len(s) for s in w["seqs"]]
-        tested_per_step = sum(seq_lens) * int(table["n_units"])
+        tested_per_step = sum(seq_lens) * int(table["n_units"])        # this rank's share of a step
+        tested_total = sum(seq_lens) * units_total if strong else None  # the whole job of a step (strong: fixed as N grows)
 
         # size the output once (capacity negotiation of the C ABI), then reuse it every step
         rc, n_words, n_sites = dev.search_query_into(query, 0, 0)
@@ -329,7 +421,7 @@ def main():
         exchange_name["value"] = "peer-memory kernel (bss_exchange)" if peer is not None else "NCCL all_gather_into_tensor + cut kernel" if padded else "NCCL grouped send/recv"
 
         gathered = []
-        breakdown = [] if os.environ.get("BSS_BENCH_BREAKDOWN") else None   # debug: event after the search of every step
+        breakdown = []   # one event per step between the search and the exchange: per-rank search / exchange times
 
         def step():
             """Queues one whole step on the stream — search (count -> scan -> emit as one CUDA graph) and, for
@@ -337,9 +429,8 @@ def main():
             if peer is not None:
                 head_ptr, rec_ptr, cap = peer.block_pointers()
                 dev.search_query_into_async(query, rec_ptr, cap, seq_begin_ptr=head_ptr)
-                if breakdown is not None:
-                    breakdown.append(torch.cuda.Event(enable_timing=True))
-                    breakdown[-1].record(stream)
+                breakdown.append(torch.cuda.Event(enable_timing=True))
+                breakdown[-1].record(stream)
                 gathered.append(peer.exchange_async(stream.cuda_stream))
                 if len(gathered) > 2:
                     gathered.pop(0)     # the output is double-buffered: only the last two are valid
@@ -349,12 +440,13 @@ def main():
                 # (the block was sized from the first search; an overflow would show in the flag checked after the loop)
                 head, rec = gatherer.block()
                 dev.search_query_into_async(query, rec.data_ptr(), rec.numel(), seq_begin_ptr=head.data_ptr())
-                if breakdown is not None:
-                    breakdown.append(torch.cuda.Event(enable_timing=True))
-                    breakdown[-1].record(stream)
+                breakdown.append(torch.cuda.Event(enable_timing=True))
+                breakdown[-1].record(stream)
                 gathered.append(gatherer.exchange_async(dev, stream.cuda_stream))
                 return
             dev.search_query_into_async(query, records.data_ptr(), records.numel())
+            breakdown.append(torch.cuda.Event(enable_timing=True))
+            breakdown[-1].record(stream)
             if world > 1 and with_collective:
                 sharded.allgatherv(records[:n_words])
 
@@ -398,19 +490,22 @@ def main():
         # through their exchanges instead of drifting apart by host jitter. Each step is timed by its own pair of events
         # (the flush in between is outside them).
         events = []
+        breakdown.clear()
         for _ in range(steps):
             flush.fill_(1)                      # evict the previous step's lines from L2
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             step()
             e1.record(stream)
-            events.append((e0, e1))
+            events.append((e0, breakdown[-1], e1))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         wall = time.perf_counter() - wall0
         st = finish()                           # sizes of the last search checked (every step runs the same search)
-        step_ms = [a.elapsed_time(z) for a, z in events]
+        step_ms = [a.elapsed_time(z) for a, _, z in events]
+        search_ms = float(np.mean([a.elapsed_time(m) for a, m, _ in events]))      # this rank's search, device time
+        exchange_ms = float(np.mean([m.elapsed_time(z) for _, m, z in events]))    # exchange kernel, waiting for the slowest peer included
         launches = steps * st["kernel_launches"]
         # per-kernel device times (the library's own events belong to the last search queued): a few more steps, one at a time, untimed
         for _ in range(3):
@@ -421,9 +516,6 @@ def main():
             e1.record(stream)
             torch.cuda.synchronize()
             st = finish()
-            if breakdown:
-                sys.stderr.write(f"rank {rank}: search {e0.elapsed_time(breakdown[-1]):.3f} ms, exchange {breakdown[-1].elapsed_time(e1):.3f} ms, "
-                                 f"kernels {st['count_ms'] + st['scan_ms'] + st['emit_ms']:.3f} ms\n")
             for k in kernel_ms:
                 kernel_ms[k].append(st[k])
         if gathered and peer is not None:   # complete and consistent: no overflow, no timeout, every rank's count, canonical order
@@ -448,15 +540,38 @@ def main():
         clocks = sampler.summary()
 
         total_ms = float(sum(step_ms))
+        per_rank, sites_all = None, n_sites * world
         if world > 1:
             t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t.item())
-        res = {"workload": w, "table": table, "value": world * tested_per_step * steps / (total_ms * 1e-3),
+            # per-rank breakdown: units, sites, search time, exchange time (its wait for the slowest peer included), and the
+            # skew = how much earlier than the slowest rank this rank's search ended
+            mine = torch.tensor([int(table["n_units"]), n_sites, n_words, search_ms, exchange_ms, float(sum(step_ms)) / steps], dtype=torch.float64, device="cuda")
+            every = torch.empty(world * mine.numel(), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(every, mine)
+            rows = every.view(world, -1).tolist()
+            slowest = max(r[3] for r in rows)
+            per_rank = [{"rank": i, "units": int(r[0]), "sites": int(r[1]), "words": int(r[2]), "search_ms": r[3], "exchange_ms": r[4],
+                         "skew_ms": slowest - r[3], "step_ms": r[5]} for i, r in enumerate(rows)]
+            sites_all = int(sum(r[1] for r in rows))
+        job_tested = tested_total if strong else world * tested_per_step
+        res = {"workload": w, "table": table, "value": job_tested * steps / (total_ms * 1e-3), "scaling": "strong" if strong else "weak",
                "ms_per_step": total_ms / steps, "sites": n_sites, "words": n_words, "launches": launches, "clocks": clocks,
                "kernel_ms": {k: float(np.mean(v)) for k, v in kernel_ms.items()}, "wall_s": wall, "tested_per_step": tested_per_step,
-               "sites_per_s": world * n_sites * steps / (total_ms * 1e-3), "seq_lens": seq_lens}
+               "sites_per_s": sites_all * steps / (total_ms * 1e-3), "seq_lens": seq_lens, "per_rank": per_rank, "units_total": units_total,
+               "stats": {k: st[k] for k in ("window_items", "ordinary_items", "heavy_items")},
+               "limiter": None}
+        if per_rank:
+            worst = max(per_rank, key=lambda r: r["search_ms"])
+            res["limiter"] = (f"slowest search {worst['search_ms']:.3f} ms on rank {worst['rank']} ({worst['units']} units), mean exchange "
+                              f"{np.mean([r['exchange_ms'] for r in per_rank]):.3f} ms of which skew {np.mean([r['skew_ms'] for r in per_rank]):.3f} ms")
 
+        try:     # the reference's real work term for the whole workload (a diagnostic kernel of its own, outside the timed region)
+            res["placements_enumerated"] = int(dev.placements_enumerated(query))
+            res["placements_enumerated_per_s"] = world * res["placements_enumerated"] * steps / (total_ms * 1e-3) if not strong else None
+        except Exception as exc:
+            res["placements_enumerated"] = f"unavailable: {exc}"
         if with_e2e:
             # end to end through the host-buffer C ABI: pinned host inputs -> device -> pinned host records
             batch = b.HostBatch(w["seqs"], w["masks"], pinned=True)   # packed once, page-locked: the C ABI's input form
@@ -476,7 +591,7 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
             st = dev.stats()
-            res["e2e"] = {"value": world * tested_per_step * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(query.h2d_bytes),
+            res["e2e"] = {"value": job_tested * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(query.h2d_bytes),
                           "d2h_bytes_per_step": int(st["d2h_bytes"]), "ms_per_step": 1e3 * dt / e2e_steps,
                           "path": "bss_search_batch (C ABI): pinned host sequences + masks in, pinned host records out"}
         query.close()
@@ -485,8 +600,18 @@ def main():
             peer.close()
         return res
 
-    main_res = run_workload(args.workload, args.steps, args.warmup)
+    # parity gate: the GPU search of the CPU sample against the reference's own matcher, before timing
+    parity = None
+    if rank == 0:
+        parity = parity_gate(make_workload(args.workload, 0), sample_size(args.workload), local_rank)
+    if world > 1:
+        dist.barrier()
+
+    main_res = run_workload(args.workload, args.steps, args.warmup, scaling=scaling)
     w, table = main_res["workload"], main_res["table"]
+    weak_res = None
+    if world > 1 and scaling == "strong":      # the weak-scaling number beside it (one library of the named size per GPU)
+        weak_res = run_workload(args.workload, max(3, args.steps // 2), args.warmup, with_e2e=False, scaling="weak")
 
     # roofline of the dominant kernel (HBM: this path has no contraction, tensor cores are not used)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -536,24 +661,29 @@ def main():
                 "frac": achieved / peak_g if peak_g else None, "algorithmic_ops_per_step": ops, "kernel_ms": km["count_ms"] + km["emit_ms"],
                 "peak_source": "bss_measure_int_issue: SHF + LOP3 only, 8 independent chains per thread, 8 CTAs x 256 threads per SM, measured in this run"}
 
+    units_total = main_res["units_total"] * (world if scaling == "weak" and world > 1 else 1)
     line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": args.workload, "describe": w["describe"], "units_per_gpu": int(table["n_units"]),
-                       "parallelism": f"library-sharded x{world}, all-gather-v of site records: {exchange_name['value']}" if world > 1 else "single GPU",
-                       "l2": "flushed between steps (256 MiB write, outside the timed events)"},
+            "config": config_of(w, units_total),
+            "exchange": exchange_name["value"] if world > 1 else None, "parity": parity,
+            "per_rank": main_res["per_rank"], "limiter": main_res["limiter"], "routing": main_res["stats"],
+            "weak_scaling": None if weak_res is None else {"value": weak_res["value"], "ms_per_step": weak_res["ms_per_step"], "units_per_gpu": weak_res["units_total"],
+                                                           "sites_per_s": weak_res["sites_per_s"], "per_rank": weak_res["per_rank"], "limiter": weak_res["limiter"]},
             "sites_per_s": main_res["sites_per_s"], "sites_per_step_per_gpu": main_res["sites"],
+            "placements_enumerated_per_step_per_gpu": main_res.get("placements_enumerated"),
             "roofline": roofline(main_res), "roofline_int": roofline_int(main_res) if rank == 0 else None, "clocks": main_res["clocks"], "e2e": main_res.get("e2e"),
             "gpu_launches": main_res["launches"], "wall_s_timed_region": main_res["wall_s"]}
 
     if rank == 0 and world == 1 and not args.no_extra:
         also = {}
-        for name in ("c4b_all", "c3", "c2", "c4_desc"):
+        for name in ("c4b_all", "c3", "c2", "c2_narrow", "c1", "c4_desc"):
             if name == args.workload:
                 continue
             try:
                 r = run_workload(name, max(3, args.steps // 4), 3, with_e2e=True)
-                also[name] = {"describe": r["workload"]["describe"], "value": r["value"], "ms_per_step": r["ms_per_step"],
+                also[name] = {"describe": r["workload"]["describe"], "value": r["value"], "ms_per_step": r["ms_per_step"], "routing": r["stats"],
+                              "placements_enumerated": r.get("placements_enumerated"), "parity": parity_gate(r["workload"], min(sample_size(name), 200), local_rank),
                               "sites_per_s": r["sites_per_s"], "sites_per_step": r["sites"], "e2e": r.get("e2e"), "roofline": roofline(r),
                               "roofline_int": roofline_int(r)}
             except Exception as exc:   # a secondary workload must never take the headline down
@@ -653,7 +783,8 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_search(w, sample_size(args.workload), repeat=3)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "sites_per_s")} if cb else None
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "sites_per_s", "placements_enumerated",
+                                                   "placements_enumerated_per_s")} if cb else None
         # the same search on ONE thread (SURVEY 8d asks for both), on a smaller sample of the library
         c1t = cpu_search(w, max(1, sample_size(args.workload) // 10), repeat=1, threads=1)
         line["cpu_baseline_single_thread"] = {k: c1t[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "sites_per_s")} if c1t else None

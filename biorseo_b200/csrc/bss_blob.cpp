@@ -101,7 +101,21 @@ int build_library(const bss_table* t, BuiltLibrary& out, std::string& error)
             level[i] = std::max(0, std::max((int)c[0], (int)c[2]));
             order[i] = i;
         }
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return level[a] < level[b]; });
+        // (within a level the row checks come first: the window walk decodes them once per level entry)
+        auto is_row = [&](uint32_t i) {
+            const int16_t* c = t->checks + 4 * (size_t)(k0 + i);
+            const int      lv = level[i];
+            const bool     a_on = c[0] == lv, b_on = c[2] == lv;
+            if (a_on == b_on || t->unit_delay[u] < 1) return false;
+            const int16_t *first = a_on ? c + 2 : c, *second = a_on ? c : c + 2;
+            if (first[0] < 0) return false;
+            const int ka = (int)(t->comp_pat_begin[c0 + first[0] + 1] - t->comp_pat_begin[c0 + first[0]]);
+            return (int)first[1] <= ka - 1 && second[1] >= 0;
+        };
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            if (level[a] != level[b]) return level[a] < level[b];
+            return is_row(a) && !is_row(b);
+        });
 
         // match programs: one (occurrence row, shift) step per literal symbol, or per pair of
         // adjacent literal symbols when the alphabet is small enough for pair rows
@@ -203,6 +217,10 @@ int build_library(const bss_table* t, BuiltLibrary& out, std::string& error)
             // window walk: every component after the first must be tied to an earlier one by a row check
             bool window = t->unit_delay[u] >= 1 && head + pat_words + 2 * NK <= kBlobStageWords;
             for (uint32_t c = 1; c < C; c++) window = window && row_checks[c] > 0;
+            for (uint32_t c = 0; c < C; c++) {
+                if (row_checks[c] > 255) window = false;
+                b[5 + 2 * c] |= std::min<uint32_t>(row_checks[c], 255u) << 24;
+            }
             if (window) {
                 b[3] |= kUnitWindow;
                 out.unit_flags[u] |= (uint8_t)kUnitWindow;

@@ -1590,7 +1590,7 @@ Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tun
     p.group = (p.W > 16 || n_items <= (1u << 17)) ? 32 : p.W <= 4 ? 4 : p.W <= 8 ? 8 : 16;
     // (tuning: developer knobs for experiments and for tests that force the rarely taken paths — narrow groups,
     //  tiny list capacity, heavy-item blocks — on small inputs; bss_library_set_tuning validates them)
-    if (tuning.group > 0) p.group = (uint32_t)tuning.group;
+    if (tuning.group > 0 && (tuning.group == 32 || (uint32_t)tuning.group >= p.W)) p.group = (uint32_t)tuning.group;   // (a narrow group holds a whole mask row)
     const uint32_t groups = kThreads / p.group;
     // Several waves of CTAs, so that the hardware scheduler evens out chunks of unequal cost;
     // a chunk holds at least one item per group.

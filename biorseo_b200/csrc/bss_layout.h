@@ -34,7 +34,8 @@ constexpr int      kWindowBandMax = 255;       // widest pair (v - u) a sequence
 //   [2] gate unit or kNoGate
 //   [3] word offset of the checks << 16 | unit flags (kUnitWindow)
 //   [4 + 2c]   k_c | offset of the match program << 8 (16 bits, in u16 units from the start of the blob) | kCompOverlap | kCompGeneric
-//   [5 + 2c]   first check ready at level c | one past the last << 8 | steps of the match program << 16
+//   [5 + 2c]   first check ready at level c | one past the last << 8 | steps of the match program << 16 | row checks of the level << 24
+//              (the row checks are the first of their level)
 //   match programs, one u16 per step: occurrence row (7 bits) | shift & 31 << 7 | shift >> 5 << 12;
 //       the match mask of the component is the AND of its rows shifted down by their shifts
 //   checks, 2 words each, ordered by the level at which both ends are placed. Word 0 is the

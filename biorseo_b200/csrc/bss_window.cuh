@@ -176,6 +176,36 @@ __device__ __forceinline__ bool match_components_any(const uint32_t* blob, const
     return true;
 }
 
+// Thinned match sets, as thin_components (bss_kernels.cu) with the first pass — which matches have another match
+// in the k-1 positions before them — on registers: the own word and the one before it are loaded once and the
+// k-1 shifted copies are funnel shifts (patterns of up to 32 bytes; longer ones take the general routine).
+// Most window items stop after that pass: their matches do not overlap on this sequence.
+__device__ __forceinline__ uint32_t thin_components_win(const uint32_t* blob, const uint32_t* M, const uint32_t* SM, uint32_t* T, uint32_t* ST, int W, int WS)
+{
+    using Gr     = Group<32>;
+    const int C  = (int)(blob[1] & 0xFFu);
+    uint32_t ovl = 0;
+    bool     slow = false;
+    for (int c = 0; c < C; c++) {
+        const uint32_t desc = blob[4 + 2 * c];
+        if (!(desc & kCompOverlap)) continue;
+        const int k = (int)(desc & 0xFFu);
+        if (k > 32) { slow = true; break; }
+        const uint32_t* Mc = M + c * W;
+        bool            any = false;
+        for (int w0 = 0; w0 < W; w0 += 32) {
+            const int      w = w0 + (int)Gr::lane();
+            const uint32_t m = w < W ? Mc[w] : 0u, prev = (w > 0 && w < W) ? Mc[w - 1] : 0u;
+            uint32_t       near = 0;
+            for (int s = 1; s < k; s++) near |= __funnelshift_l(prev, m, s);
+            any |= Gr::ballot((near & m) != 0) != 0;
+        }
+        if (any) { slow = true; break; }
+    }
+    if (!slow) return 0u;   // (nothing was written: T is only read for the components in the returned mask)
+    return thin_components<32>(blob, M, SM, T, ST, W, WS);
+}
+
 // Greedy earliest placement: does the gate unit have any placement on this sequence?
 __device__ __forceinline__ bool gate_open_any(const uint32_t* gblob, const uint32_t* occ, int WP, uint32_t* M, uint32_t* S, int W, int WS, int n)
 {
@@ -258,19 +288,24 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
         if (lane == 0) slot = (uint32_t)atomicAdd(cursor, 1ull);
         slot = Gr::first(slot);
     }
+    const bool one_seq = query.n_seqs == 1;
+    SeqCtx     sq      = load_seq(lib, query, 0);
     while (slot < n_list) {
         uint32_t next_slot = 0;
         if (!EMIT && lane == 0) next_slot = (uint32_t)atomicAdd(cursor, 1ull);   // drawn ahead: its latency hides behind this item
         const uint32_t item = EMIT ? work.alive_w[slot] : work.wlist[slot];
         if (!BSS_WIN_CHECK((uint64_t)item < (uint64_t)query.n_seqs * lib.n_units, 21)) break;
-        const uint32_t qi   = item / lib.n_units;
-        const uint32_t u    = item - qi * lib.n_units;
-        const SeqCtx   sq   = load_seq(lib, query, qi);
-        const int      n    = sq.n;
-        const uint32_t chunk = qi * plan.chunks_per_seq + u / plan.units_per_chunk;
+        uint32_t qi = 0, u = item;
+        if (!one_seq) {   // (one-sequence queries: no division, the sequence's context was loaded before the loop)
+            qi = item / lib.n_units;
+            u  = item - qi * lib.n_units;
+            sq = load_seq(lib, query, qi);
+        }
+        const int n = sq.n;
 
         uint64_t out_words = 0;
         if (EMIT) {   // records of the chunk's earlier items
+            const uint32_t chunk = qi * plan.chunks_per_seq + u / plan.units_per_chunk;
             const uint32_t v0 = (u / plan.units_per_chunk) * plan.units_per_chunk;
             uint64_t       before = 0;
             for (uint32_t v = v0 + lane; v < u; v += 32) before += (uint64_t)work.counts[sq.item0 + v] * __ldg(lib.unit_rlen + v);
@@ -290,7 +325,7 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
         const uint32_t module = blob[0] + lib.module_base;
         const int      C      = (int)(blob[1] & 0xFFu);
         const uint32_t gate   = blob[2];
-        if (!BSS_WIN_CHECK(C >= 1 && C <= (int)lib.cmax && n >= 0 && n <= (int)query.max_len && chunk < plan.n_chunks, 23)) break;
+        if (!BSS_WIN_CHECK(C >= 1 && C <= (int)lib.cmax && n >= 0 && n <= (int)query.max_len, 23)) break;
         const uint32_t* occ   = STAGE ? s_occ : sq.occ;
         const int       WP    = (int)query.occ_stride;
 
@@ -318,7 +353,7 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
             cx.pos  = col;
             cx.bits = col + lib.cmax * THREADS;
             cx.grd  = col + 2 * lib.cmax * THREADS;
-            cx.ovl  = thin_components<32>(blob, g_M, g_SM, g_T, g_ST, W, WS);
+            cx.ovl  = thin_components_win(blob, g_M, g_SM, g_T, g_ST, W, WS);
             cx.W = W; cx.WS = WS; cx.n = n; cx.C = C; cx.delay = (int)(blob[1] >> 16); cx.cs = THREADS;
             // lane l owns the words [l * per, (l + 1) * per) of the first component's candidates: lane order = position order
             const int per = (sq.Wq + 31) >> 5;
@@ -350,6 +385,7 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
                 if (item_sites > 0xFFFFFFFFull) atomicOr((unsigned long long*)(work.totals + 2), 1ull);
                 work.counts[sq.item0 + u] = (uint32_t)item_sites;
                 if (item_sites) {
+                    const uint32_t chunk = qi * plan.chunks_per_seq + u / plan.units_per_chunk;
                     where               = (uint32_t)atomicAdd((unsigned long long*)(work.totals + 5), 1ull);
                     work.alive_w[where] = item;
                     atomicAdd((unsigned long long*)&work.chunk_sites[chunk], (unsigned long long)item_sites);

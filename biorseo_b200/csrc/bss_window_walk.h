@@ -146,11 +146,10 @@ BSS_HD bool pair_allowed(const Ctx& cx, int u, int v)
 BSS_HD_MISC bool generic_pass(const Ctx& cx, int level)
 {
     const uint32_t  range = cx.blob[5 + 2 * level];
-    const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
+    const int       cb = (int)(range & 0xFFu) + (int)(range >> 24), ce = (int)((range >> 8) & 0xFFu);   // (the row checks come first)
     const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
     for (int i = cb; i < ce; i++) {
         const uint32_t ea = chk[2 * i], eb = chk[2 * i + 1];
-        if (ea & kCheckRow) continue;
         const int aa = anchor_of(ea), ba = anchor_of(eb);
         const int u  = (aa < 0 ? 0 : placed(cx, aa)) + off_of(ea);
         const int v  = (ba < 0 ? 0 : placed(cx, ba)) + off_of(eb);
@@ -159,27 +158,81 @@ BSS_HD_MISC bool generic_pass(const Ctx& cx, int level)
     return true;
 }
 
-// x = bits of word w of the chain set of component c; keeps the positions that satisfy every row check of the level.
-BSS_HD_ROW uint32_t row_filter(const Ctx& cx, int c, int w, uint32_t x)
+// The row checks of a level, decoded once per step: u = the end on the earlier component (fixed while the level is
+// scanned), ob = offset of the other end on the component being placed. The first two live in registers; units with
+// more of them per level (rare) take the rest from the descriptor (row_filter_rest).
+struct Rows {
+    int n, u0, ob0, u1, ob1;
+};
+
+// Decodes the row checks of level c (the first `n` checks of the level). False when one of them cannot hold
+// (its earlier end lies before the sequence).
+BSS_HD bool decode_rows(const Ctx& cx, int c, Rows& r)
 {
     const uint32_t  range = cx.blob[5 + 2 * c];
-    const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
-    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
-    for (int i = cb; i < ce && x; i++) {
-        const uint32_t ea = chk[2 * i];
-        if (!(ea & kCheckRow)) continue;
-        const int u = placed(cx, anchor_of(ea)) + off_of(ea);
-        if (u < 0) return 0u;
-        const int ob = off_of(chk[2 * i + 1]);
-        const int ws = w + (ob >> 5);
-        x &= funnel_r(row_word(cx, u, ws), row_word(cx, u, ws + 1), (uint32_t)ob & 31u);   // bit q = row bit q + ob
+    const int       cb = (int)(range & 0xFFu);
+    const uint32_t* chk = cx.blob + (cx.blob[3] >> 16) + 2 * cb;
+    r.n  = (int)(range >> 24);
+    r.u0 = r.u1 = 0;
+    r.ob0 = r.ob1 = 0;
+    if (r.n > 0) {
+        const uint32_t ea = chk[0];
+        r.u0  = placed(cx, anchor_of(ea)) + off_of(ea);
+        r.ob0 = off_of(chk[1]);
+        if (r.u0 < 0) return false;
+    }
+    if (r.n > 1) {
+        const uint32_t ea = chk[2];
+        r.u1  = placed(cx, anchor_of(ea)) + off_of(ea);
+        r.ob1 = off_of(chk[3]);
+        if (r.u1 < 0) return false;
+    }
+    for (int i = 2; i < r.n; i++)
+        if (placed(cx, anchor_of(chk[2 * i])) + off_of(chk[2 * i]) < 0) return false;
+    return true;
+}
+
+// bit q of the result = bit q + ob of row u of the pair mask, for the positions of word w
+BSS_HD uint32_t row_bits(const Ctx& cx, int u, int ob, int w)
+{
+    const int ws = w + (ob >> 5);
+    return funnel_r(row_word(cx, u, ws), row_word(cx, u, ws + 1), (uint32_t)ob & 31u);
+}
+
+// x = bits of word w of the chain set of component c; keeps the positions that satisfy every row check of the level.
+BSS_HD_ROW uint32_t row_filter(const Ctx& cx, int c, const Rows& r, int w, uint32_t x)
+{
+    if (r.n > 0) x &= row_bits(cx, r.u0, r.ob0, w);
+    if (r.n > 1 && x) x &= row_bits(cx, r.u1, r.ob1, w);
+    if (r.n > 2) {
+        const uint32_t* chk = cx.blob + (cx.blob[3] >> 16) + 2 * (int)(cx.blob[5 + 2 * c] & 0xFFu);
+        for (int i = 2; i < r.n && x; i++) x &= row_bits(cx, placed(cx, anchor_of(chk[2 * i])) + off_of(chk[2 * i]), off_of(chk[2 * i + 1]), w);
     }
     return x;
 }
 
-BSS_HD_ROW bool row_pass(const Ctx& cx, int c, int q)
+BSS_HD_ROW bool row_pass(const Ctx& cx, int c, const Rows& r, int q)
 {
-    return (row_filter(cx, c, q >> 5, 1u << (q & 31)) >> (q & 31)) & 1u;
+    return (row_filter(cx, c, r, q >> 5, 1u << (q & 31)) >> (q & 31)) & 1u;
+}
+
+// Window of component c below the current placement of components 0 .. c-1: the candidates lie in [start, hi].
+// False when it is empty. `r` = the decoded row checks of the level.
+BSS_HD bool level_window(const Ctx& cx, int c, const Rows& r, int& start, int& hi)
+{
+    const int kprev = (int)(cx.blob[4 + 2 * (c - 1)] & 0xFFu), kc = (int)(cx.blob[4 + 2 * c] & 0xFFu);
+    start = placed(cx, c - 1) + kprev - 1 + cx.delay;    // start of the suffix the component is searched in (inside the sequence)
+    hi    = cx.n - kc - (c < cx.C - 1 ? cx.delay : 0);   // the pattern fits and leaves room for the next component
+    if (cx.band < 0) return false;                       // no pair at all is allowed: the level's row check cannot hold
+    // v = candidate + ob must lie in (u, u + band] and inside the sequence
+    if (r.n > 0) hi = imin(hi, imin(r.u0 + cx.band, cx.n - 1) - r.ob0);
+    if (r.n > 1) hi = imin(hi, imin(r.u1 + cx.band, cx.n - 1) - r.ob1);
+    if (r.n > 2) {
+        const uint32_t* chk = cx.blob + (cx.blob[3] >> 16) + 2 * (int)(cx.blob[5 + 2 * c] & 0xFFu);
+        for (int i = 2; i < r.n; i++)
+            hi = imin(hi, imin(placed(cx, anchor_of(chk[2 * i])) + off_of(chk[2 * i]) + cx.band, cx.n - 1) - off_of(chk[2 * i + 1]));
+    }
+    return start <= hi;
 }
 
 // One step of the walk at level c (>= 1): with `enter`, the first candidate of component c below the current
@@ -190,26 +243,13 @@ BSS_HD_LEVEL int level_step(const Ctx& cx, int c, bool enter)
     const int       kc = (int)(cx.blob[4 + 2 * c] & 0xFFu), ke = imax(1, kc);
     const bool      thinned = (cx.ovl >> c) & 1u;
     const uint32_t *M = cx.M + c * cx.W, *SM = cx.SM + c * cx.WS;
-    const uint32_t *S = thinned ? cx.T + c * cx.W : M, *SS = thinned ? cx.ST + c * cx.WS : SM;
+    const uint32_t* S = thinned ? cx.T + c * cx.W : M;
     int             start, hi;
     bool            greedy;
+    Rows r;
+    if (!decode_rows(cx, c, r)) return -1;
     if (enter) {
-        const int kprev = (int)(cx.blob[4 + 2 * (c - 1)] & 0xFFu);
-        start = placed(cx, c - 1) + kprev - 1 + cx.delay;    // start of the suffix the component is searched in (inside the sequence)
-        hi    = cx.n - kc - (c < cx.C - 1 ? cx.delay : 0);   // the pattern fits and leaves room for the next component
-        if (cx.band < 0) return -1;                          // no pair at all is allowed: the level's row check cannot hold
-        const uint32_t  range = cx.blob[5 + 2 * c];
-        const int       cb = (int)(range & 0xFFu), ce = (int)((range >> 8) & 0xFFu);
-        const uint32_t* chk = cx.blob + (cx.blob[3] >> 16);
-        for (int i = cb; i < ce; i++) {   // v = candidate + ob must lie in (u, u + band] and inside the sequence
-            const uint32_t ea = chk[2 * i];
-            if (!(ea & kCheckRow)) continue;
-            const int u  = placed(cx, anchor_of(ea)) + off_of(ea);
-            const int ob = off_of(chk[2 * i + 1]);
-            if (u < 0) return -1;
-            hi = imin(hi, imin(u + cx.band, cx.n - 1) - ob);
-        }
-        if (start > hi) return -1;
+        if (!level_window(cx, c, r, start, hi)) return -1;
         greedy = thinned;   // the reference's iterator restarts at `start`: a greedy walk over all matches until it meets the thinned set
     } else {
         const uint32_t e = cx.pos[c * cx.cs];
@@ -233,7 +273,7 @@ BSS_HD_LEVEL int level_step(const Ctx& cx, int c, bool enter)
     if (greedy) {
         int q = next_set(M, SM, cx.W, cx.WS, start);
         while (q >= 0 && q <= hi && !bit_of(S, q)) {
-            if (row_pass(cx, c, q)) {
+            if (row_pass(cx, c, r, q)) {
                 cx.grd[c * cx.cs]  = 1;
                 cx.bits[c * cx.cs] = 0;
                 cx.pos[c * cx.cs]  = (uint32_t)q | ((uint32_t)hi << 16);
@@ -245,20 +285,19 @@ BSS_HD_LEVEL int level_step(const Ctx& cx, int c, bool enter)
         start = q;   // the chain has met the thinned set: it is the thinned set from here on
     }
     cx.grd[c * cx.cs] = 0;
-    int q = start;
-    while (q <= hi) {
-        q = next_set(S, SS, cx.W, cx.WS, q);   // skips the empty words through the summary
-        if (q < 0 || q > hi) return -1;
-        const int      w = q >> 5;
-        const uint32_t x = row_filter(cx, c, w, S[w] & (0xFFFFFFFFu << (q & 31)));
+    // the thinned part of the chain: a plain loop over the few words of the window (the band bounds it)
+    const int wa = start >> 5, wb = hi >> 5;
+    for (int w = wa; w <= wb; w++) {
+        uint32_t x = S[w];
+        if (w == wa) x &= 0xFFFFFFFFu << (start & 31);
+        if (w == wb) x &= 0xFFFFFFFFu >> (31 - (hi & 31));
+        if (x) x = row_filter(cx, c, r, w, x);
         if (x) {
             const int p = (w << 5) + ffs32(x) - 1;
-            if (p > hi) return -1;
             cx.bits[c * cx.cs] = x & (x - 1u);
             cx.pos[c * cx.cs]  = (uint32_t)p | ((uint32_t)hi << 16);
             return p;
         }
-        q = (w + 1) << 5;
     }
     return -1;
 }

@@ -60,7 +60,7 @@ def run_port(source, library, seq, mask):
 _announced = set()
 
 
-def best_oracle(source, library, seq, mask, timeout=120):
+def best_oracle(source, library, seq, mask, timeout=120, threads=2):
     """The reference's own code (oracle/_ref/biorseo_ref, built from /root/reference by oracle/Makefile and shipped
     to the GPU box prebuilt). Its absence is an error, not a silent switch to the restatement: set BSS_ALLOW_PORT=1
     to accept oracle/port instead (a box where the reference could not be built). Which one ran is printed once."""
@@ -74,7 +74,7 @@ def best_oracle(source, library, seq, mask, timeout=120):
     if which not in _announced:
         _announced.add(which)
         print(f"\n[oracle] parity is checked against the {which}")
-    return run_oracle(binary, "jobs", source, library, seq, mask, timeout=timeout)
+    return run_oracle(binary, "jobs", source, library, seq, mask, threads=threads, timeout=timeout)
 
 
 def ref_placements(source, library, seq, mask):
