@@ -339,6 +339,10 @@ int bss_library_set_tuning(bss_library* lib, int knob, int64_t value)
         break;
     case BSS_TUNE_WINDOW: t.window = value; break;
     case BSS_TUNE_WINDOW_STAGE: t.window_stage = value; break;
+    case BSS_TUNE_WINDOW_DRAW:
+        if (value == 0 || value > 1024) return fail(BSS_ERR_INVALID, "draw block out of range");
+        t.window_draw = value;
+        break;
     default: return fail(BSS_ERR_INVALID, "unknown tuning knob");
     }
     lib->dev_serial++;   // a cached launch graph was built for the old plan

@@ -84,6 +84,7 @@ struct Plan {
     uint32_t heavy_block;  // ranks per block of a heavy item (at most 256 blocks per item)
     uint32_t list_cap;     // rank-space walk: match-list entries per item (0 = depth-first walk only)
     uint32_t window;       // 1: items of window-walk units on narrow-band sequences go through route_kernel + window_kernel
+    uint32_t window_draw;  // list entries a warp of the window count pass draws per atomic
     uint32_t window_stage; // 1: the window kernel stages the occurrence table and the banded mask in shared memory (one sequence)
     uint32_t smem_bytes_window;   // dynamic shared memory of the window kernel
     uint32_t smem_bytes;        // dynamic shared memory of the count kernel
@@ -116,7 +117,7 @@ constexpr uint32_t kTotalsWords = 16;
 // Developer knobs (bss_library_set_tuning): force rarely taken paths on small inputs (tests), compare variants
 // (benchmarks). A negative value means automatic.
 struct Tuning {
-    int64_t group = -1, units_per_chunk = -1, heavy_ranks = -1, list_cap = -1, window = -1, window_stage = -1;
+    int64_t group = -1, units_per_chunk = -1, heavy_ranks = -1, list_cap = -1, window = -1, window_stage = -1, window_draw = -1;
 };
 
 __host__ __device__ inline int band_words(int band) { return band < 0 ? 0 : ((31 + band) >> 5) + 1; }

@@ -1621,6 +1621,7 @@ Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tun
     // Window walk: whole warps only; the query carries banded masks; the working set fits.
     p.smem_bytes_window = 4u * window_smem_words(lib.cmax, p.W, p.WS, kWinThreads);
     p.window = (p.group == 32 && n_window_units > 0 && q.bmask != nullptr && p.smem_bytes_window <= 160u * 1024u && tuning.window != 0) ? 1u : 0u;
+    p.window_draw  = tuning.window_draw > 0 ? (uint32_t)tuning.window_draw : 1u;   // (measured on c4: 1 -> 0.146 ms, 4 -> 0.166, 32 -> 0.53: balance beats atomics)
     p.window_stage = 0;
     if (p.window && n_seqs == 1 && known_band >= 0 && known_band <= kWindowBandMax && tuning.window_stage > 0) {
         // occurrence table + banded mask of the one sequence in shared memory, next to the warps' scratch

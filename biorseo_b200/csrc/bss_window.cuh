@@ -176,34 +176,52 @@ __device__ __forceinline__ bool match_components_any(const uint32_t* blob, const
     return true;
 }
 
-// Thinned match sets, as thin_components (bss_kernels.cu) with the first pass — which matches have another match
-// in the k-1 positions before them — on registers: the own word and the one before it are loaded once and the
-// k-1 shifted copies are funnel shifts (patterns of up to 32 bytes; longer ones take the general routine).
-// Most window items stop after that pass: their matches do not overlap on this sequence.
+// Thinned match sets, as thin_components (bss_kernels.cu), with the two common outcomes on registers and two
+// shared-memory words per lane: (1) no two matches of the component overlap on this sequence (nothing to thin:
+// most items), (2) matches overlap in pairs only, so that the thinned set is just the run starts. Runs of three
+// and more overlapping matches (a greedy walk per run), patterns longer than 32 bytes: the general routine.
+// Does not write the summaries ST (the window walk does not read them).
 __device__ __forceinline__ uint32_t thin_components_win(const uint32_t* blob, const uint32_t* M, const uint32_t* SM, uint32_t* T, uint32_t* ST, int W, int WS)
 {
     using Gr     = Group<32>;
     const int C  = (int)(blob[1] & 0xFFu);
     uint32_t ovl = 0;
-    bool     slow = false;
-    for (int c = 0; c < C; c++) {
+    bool     general = false;
+    for (int c = 0; c < C && !general; c++) {
         const uint32_t desc = blob[4 + 2 * c];
         if (!(desc & kCompOverlap)) continue;
         const int k = (int)(desc & 0xFFu);
-        if (k > 32) { slow = true; break; }
+        if (k > 32) { general = true; break; }
         const uint32_t* Mc = M + c * W;
+        uint32_t*       Tc = T + c * W;
         bool            any = false;
-        for (int w0 = 0; w0 < W; w0 += 32) {
+        for (int w0 = 0; w0 < W; w0 += 32) {   // followers: matches with another match in the k-1 positions before them
             const int      w = w0 + (int)Gr::lane();
             const uint32_t m = w < W ? Mc[w] : 0u, prev = (w > 0 && w < W) ? Mc[w - 1] : 0u;
             uint32_t       near = 0;
             for (int s = 1; s < k; s++) near |= __funnelshift_l(prev, m, s);
-            any |= Gr::ballot((near & m) != 0) != 0;
+            near &= m;
+            if (w < W) Tc[w] = near;
+            any |= Gr::ballot(near != 0) != 0;
         }
-        if (any) { slow = true; break; }
+        if (!any) continue;   // no two matches overlap on this sequence: the chain from any start is M itself
+        Gr::sync();
+        bool deep = false;    // a follower of a follower: a run of three matches or more
+        for (int w0 = 0; w0 < W; w0 += 32) {
+            const int      w = w0 + (int)Gr::lane();
+            const uint32_t t = w < W ? Tc[w] : 0u, prev = (w > 0 && w < W) ? Tc[w - 1] : 0u;
+            uint32_t       f2 = 0;
+            for (int s = 1; s < k; s++) f2 |= __funnelshift_l(prev, t, s);
+            deep |= Gr::ballot((f2 & t) != 0) != 0;
+        }
+        if (deep) { general = true; break; }
+        ovl |= 1u << c;
+        Gr::sync();
+        for (int w = (int)Gr::lane(); w < W; w += 32) Tc[w] = Mc[w] & ~Tc[w];   // run starts
     }
-    if (!slow) return 0u;   // (nothing was written: T is only read for the components in the returned mask)
-    return thin_components<32>(blob, M, SM, T, ST, W, WS);
+    Gr::sync();
+    if (general) return thin_components<32>(blob, M, SM, T, ST, W, WS);   // (recomputes every component)
+    return ovl;
 }
 
 // Greedy earliest placement: does the gate unit have any placement on this sequence?
@@ -279,20 +297,26 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
     }
 #endif
 
-    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(work.totals + 8);
+    // Count pass: the warps draw blocks of plan.window_draw consecutive list entries from one cursor. Measured on the
+    // headline workload, one entry per draw is best (0.146 ms; 4 per draw 0.166, 32 per draw 0.53 ms): the atomic's
+    // latency hides behind the item in hand, while larger blocks leave warps without work at the end.
+    unsigned int*  cursor = reinterpret_cast<unsigned int*>(work.totals + 8);
+    const uint32_t draw   = plan.window_draw;
+    uint32_t       block_end = 0;   // count pass: one past the last slot of the block in hand
     uint32_t            slot;
     if (EMIT) {
         slot = blockIdx.x * warps + warp;
     } else {
         slot = 0;
-        if (lane == 0) slot = (uint32_t)atomicAdd(cursor, 1ull);
-        slot = Gr::first(slot);
+        if (lane == 0) slot = atomicAdd(cursor, draw);
+        slot      = Gr::first(slot);
+        block_end = slot + draw;
     }
     const bool one_seq = query.n_seqs == 1;
     SeqCtx     sq      = load_seq(lib, query, 0);
     while (slot < n_list) {
         uint32_t next_slot = 0;
-        if (!EMIT && lane == 0) next_slot = (uint32_t)atomicAdd(cursor, 1ull);   // drawn ahead: its latency hides behind this item
+        if (!EMIT && lane == 0 && slot + 1 == block_end) next_slot = atomicAdd(cursor, draw);   // drawn ahead: its latency hides behind this item
         const uint32_t item = EMIT ? work.alive_w[slot] : work.wlist[slot];
         if (!BSS_WIN_CHECK((uint64_t)item < (uint64_t)query.n_seqs * lib.n_units, 21)) break;
         uint32_t qi = 0, u = item;
@@ -396,7 +420,12 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
                 where = Gr::first(where);
                 if (BSS_WIN_CHECK((uint64_t)where < (uint64_t)query.n_seqs * lib.n_units, 26)) work.lane_counts_w[(size_t)where * 32 + lane] = (uint32_t)lane_sites;
             }
-            slot = Gr::first(next_slot);
+            if (slot + 1 == block_end) {   // (uniform)
+                slot      = Gr::first(next_slot);
+                block_end = slot + draw;
+            } else {
+                slot++;
+            }
         } else {
             slot += gridDim.x * warps;
         }

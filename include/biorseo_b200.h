@@ -140,6 +140,7 @@ int  bss_library_set_module_base(bss_library* lib, uint32_t base);
 #define BSS_TUNE_LIST_CAP         3   /* match-list entries per item of the rank-space walk (0: off)   */
 #define BSS_TUNE_WINDOW           4   /* 0: never take the window walk                                 */
 #define BSS_TUNE_WINDOW_STAGE     5   /* 1: window kernel stages occurrence table + banded mask in shared memory (cp.async.bulk) */
+#define BSS_TUNE_WINDOW_DRAW      6   /* list entries a warp of the window count pass draws per atomic (1..1024)        */
 int  bss_library_set_tuning(bss_library* lib, int knob, int64_t value);
 uint32_t bss_library_units(const bss_library* lib);
 uint32_t bss_library_window_units(const bss_library* lib);   /* units every component of which is tied by a pair to an earlier one */
