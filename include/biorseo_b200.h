@@ -233,6 +233,9 @@ typedef struct bss_exchange bss_exchange;
 int       bss_exchange_create(int device, uint32_t world, uint32_t rank, uint64_t capacity_words, uint32_t header_words, bss_exchange** out);
 int       bss_exchange_handle(const bss_exchange* x, void* handle64);
 int       bss_exchange_open(bss_exchange* x, const void* handles /* world x 64 bytes, in rank order */);
+/* The same for ONE process that drives every GPU itself (bss_sharded_* below): `all` holds the world exchanges in
+ * rank order, each created on its own device; plain peer access (cudaDeviceEnablePeerAccess), no IPC. */
+int       bss_exchange_open_local(bss_exchange* const* all, uint32_t world);
 uint32_t* bss_exchange_block(const bss_exchange* x);      /* device memory: [header_words | capacity_words] */
 uint64_t  bss_exchange_capacity(const bss_exchange* x);   /* record words per rank (rounded up to a multiple of 4) */
 int       bss_exchange_run_async(bss_exchange* x, void* cuda_stream, const uint32_t** d_out, const uint64_t** d_result);

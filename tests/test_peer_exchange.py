@@ -65,13 +65,13 @@ def _worker(rank, world, port, out_dir):
         h2, r2, c2 = small.block_pointers()
         seq = synth.sequence(150, 3)
         q = dev.query([seq], [synth.mask_all(150)])
-        big = torch.empty(1 << 16, dtype=torch.int32, device="cuda")
-        rc, n_words, _ = dev.search_query_into(q, big.data_ptr(), big.numel())
-        assert rc == 0 and n_words > c2
-        # (the search itself refuses to write into the small block; put the count where the exchange reads it)
-        torch.as_tensor(sharded._DevicePointer(h2, 2, "<i8"), device="cuda")[1] = n_words
+        # the search refuses to write records into the small block but still leaves its word count in the header:
+        # that is what tells every rank about the overflow
+        dev.search_query_into_async(q, r2, c2, seq_begin_ptr=h2)
         _, result = small.exchange_async(stream.cuda_stream)
+        rc, n_words, _ = dev.search_wait()
         torch.cuda.synchronize()
+        assert rc == b.capi.BSS_ERR_OVERFLOW and n_words > c2, (rc, n_words)
         assert result.tolist()[world + 1] == 1
         small.close()
         q.close()
