@@ -7,7 +7,7 @@
 NVCC     ?= nvcc
 CXX      ?= g++
 LIB      := biorseo_b200/lib/libbiorseo_b200.so
-CUDA_SRC := $(addprefix biorseo_b200/csrc/,bss_kernels.cu bss_mask.cu bss_index.cu bss_probe.cu bss_exchange.cu bss_capi.cu bss_blob.cpp)
+CUDA_SRC := $(addprefix biorseo_b200/csrc/,bss_kernels.cu bss_mask.cu bss_index.cu bss_probe.cu bss_exchange.cu bss_sharded.cu bss_capi.cu bss_blob.cpp)
 HOST_SRC := $(addprefix biorseo_b200/host/,Motif.cpp Pool.cpp mini_json.cpp module_library.cpp site_search.cpp fasta.cpp bsh_capi.cpp)
 HEADERS  := $(wildcard biorseo_b200/csrc/*.cuh biorseo_b200/csrc/*.h biorseo_b200/host/*.h include/*.h)
 

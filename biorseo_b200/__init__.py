@@ -4,4 +4,4 @@ The product is the shared library (CUDA kernels for sm_100a behind a C ABI, C++ 
 with the reference's Motif / Pool interfaces). This Python package is only the binding
 used by the test-suite and bench.py.
 """
-from .api import (DeviceLibrary, HostBatch, HostLibrary, Query, SearchError, Sites, canonical_pair_mask, pack_mask, read_fasta)  # noqa: F401
+from .api import (DeviceLibrary, HostBatch, HostLibrary, Query, SearchError, ShardedLibrary, Sites, canonical_pair_mask, pack_mask, read_fasta)  # noqa: F401

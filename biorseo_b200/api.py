@@ -171,6 +171,66 @@ class HostLibrary:
             raise SearchError(rc, (self._lib.bsh_last_error() or b"").decode())
         return DeviceLibrary(h, self)
 
+    def shard_ranges(self, n_shards, typical_len=0):
+        """Contiguous module ranges [(begin, end)] balanced by search cost (bss_shard_ranges: host only)."""
+        t = self.raw_table()
+        begin = (C.c_uint32 * (n_shards + 1))()
+        _check(self._lib.bss_shard_ranges(C.byref(t), n_shards, typical_len, begin))
+        return [(int(begin[r]), int(begin[r + 1])) for r in range(n_shards)]
+
+    def to_devices(self, n_gpus, devices=None, typical_len=0):
+        """The library cut over n_gpus GPUs of this box, driven by ONE process (bss_sharded_create)."""
+        t = self.raw_table()
+        h = C.c_void_p()
+        dev = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        _check(self._lib.bss_sharded_create(C.byref(t), dev, n_gpus, typical_len, C.byref(h)))
+        return ShardedLibrary(h, self)
+
+
+class ShardedLibrary:
+    """One library over several GPUs in one process (include/biorseo_b200.h, bss_sharded_*): every GPU owns a
+    contiguous module range; a search returns the ranges' records as one stream in canonical order."""
+
+    def __init__(self, handle, host):
+        self._lib = capi.load()
+        self._h = handle
+        self.host = host
+        self.n_gpus = int(self._lib.bss_sharded_gpus(handle))
+
+    def ranges(self):
+        out = []
+        for r in range(self.n_gpus):
+            d, b, e = C.c_int(), C.c_uint32(), C.c_uint32()
+            _check(self._lib.bss_sharded_range(self._h, r, C.byref(d), C.byref(b), C.byref(e)))
+            out.append((d.value, b.value, e.value))
+        return out
+
+    def search_host(self, batch):
+        """Host buffers in (HostBatch), host records out: bss_search_sharded."""
+        h = C.c_void_p()
+        _check(self._lib.bss_search_sharded(self._h, batch.n_seqs, batch.seqs.ctypes.data_as(C.c_void_p), batch.seq_begin.ctypes.data_as(capi.u64p),
+                                            batch.masks.ctypes.data_as(C.c_void_p), batch.mask_begin.ctypes.data_as(capi.u64p), C.byref(h)))
+        return Sites(h, batch.n_seqs, owner=self)
+
+    def search(self, seq, mask):
+        return self.search_host(HostBatch([seq], [mask]))
+
+    def shard_stats(self, shard):
+        st = capi.BssStats()
+        _check(self._lib.bss_last_stats(C.c_void_p(self._lib.bss_sharded_library(self._h, shard)), C.byref(st)))
+        return {name: getattr(st, name) for name, _ in capi.BssStats._fields_}
+
+    def close(self):
+        if self._h:
+            self._lib.bss_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 def read_fasta(path):
     """Records of a (multi-record) FASTA file as (name, sequence, structure) tuples: the C++ reader of the batch

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbiorseo_b200.so")
 
-CUDA_SOURCES = ["csrc/bss_kernels.cu", "csrc/bss_mask.cu", "csrc/bss_index.cu", "csrc/bss_probe.cu", "csrc/bss_exchange.cu", "csrc/bss_capi.cu", "csrc/bss_blob.cpp"]
+CUDA_SOURCES = ["csrc/bss_kernels.cu", "csrc/bss_mask.cu", "csrc/bss_index.cu", "csrc/bss_probe.cu", "csrc/bss_exchange.cu", "csrc/bss_sharded.cu", "csrc/bss_capi.cu", "csrc/bss_blob.cpp"]
 HOST_SOURCES = ["host/Motif.cpp", "host/Pool.cpp", "host/mini_json.cpp", "host/module_library.cpp",
                 "host/site_search.cpp", "host/fasta.cpp", "host/bsh_capi.cpp"]
 HEADERS = ["csrc/bss_device.cuh", "csrc/bss_layout.h", "csrc/bss_window.cuh", "csrc/bss_window_walk.h", "host/Motif.h", "host/Pool.h", "host/mini_json.h", "host/module_library.h",

@@ -16,7 +16,7 @@ KIND_JSON, KIND_RIN, KIND_DESC = 0, 1, 2
 C3_COMPONENT_LESS_LINKS, C3_INTERIOR = 0, 1
 IDX_SECTIONS = ("var_begin", "var_first", "var_second", "var_c3_terms", "overlap_begin", "overlap_vars", "pair_begin", "pair_partner",
                 "row_first_pair")
-TUNE = {"group": 0, "units_per_chunk": 1, "heavy_ranks": 2, "list_cap": 3, "window": 4, "window_stage": 5, "window_draw": 6}
+TUNE = {"group": 0, "units_per_chunk": 1, "heavy_ranks": 2, "list_cap": 3, "window": 4, "window_stage": 5, "window_draw": 6, "pattern_table": 7}
 KIND_OF_SOURCE = {"jsonfolder": KIND_JSON, "rinfolder": KIND_RIN, "descfolder": KIND_DESC}
 
 u32p = C.POINTER(C.c_uint32)
@@ -64,10 +64,19 @@ SIGNATURES = {
     "bss_search_wait": (C.c_int, [C.c_void_p, u64p, u64p]),
     "bss_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "bss_search_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, u64p, C.c_void_p, u64p, C.POINTER(C.c_void_p)]),
+    "bss_search_batch_resident": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, u64p, C.c_void_p, u64p, C.POINTER(C.c_void_p)]),
+    "bss_sharded_create": (C.c_int, [C.POINTER(BssTable), C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "bss_sharded_destroy": (None, [C.c_void_p]),
+    "bss_sharded_gpus": (C.c_uint32, [C.c_void_p]),
+    "bss_sharded_range": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "bss_sharded_library": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "bss_search_sharded": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, u64p, C.c_void_p, u64p, C.POINTER(C.c_void_p)]),
+    "bss_shard_ranges": (C.c_int, [C.POINTER(BssTable), C.c_uint32, C.c_uint32, u32p]),
     "bss_gather_cut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bss_exchange_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p)]),
     "bss_exchange_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bss_exchange_open": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bss_exchange_open_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
     "bss_exchange_block": (C.c_void_p, [C.c_void_p]),
     "bss_exchange_capacity": (C.c_uint64, [C.c_void_p]),
     "bss_exchange_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
@@ -77,6 +86,7 @@ SIGNATURES = {
     "bss_sites_records": (u32p, [C.c_void_p]),
     "bss_sites_device_records": (C.c_void_p, [C.c_void_p]),
     "bss_sites_seq_word_begin": (u64p, [C.c_void_p]),
+    "bss_sites_copy_out": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "bss_sites_free": (None, [C.c_void_p]),
     "bss_site_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "bss_site_index_count": (C.c_uint64, [C.c_void_p, C.c_int]),

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <unordered_map>
 
 #include "biorseo_b200.h"
 
@@ -24,6 +25,23 @@ bool can_self_overlap(const uint8_t* p, uint32_t k)
         if (ok) return true;
     }
     return false;
+}
+
+// Match program of one pattern: one (occurrence row, shift) step per literal symbol, or per pair of adjacent
+// literal symbols when the alphabet is small enough for pair rows.
+void append_program(const uint8_t* p, uint32_t k, const int* code_of, bool pairs, uint32_t ns, std::vector<uint16_t>& program)
+{
+    for (uint32_t j = 0; j < k;) {
+        if (p[j] == '.') { j++; continue; }
+        uint32_t row = (uint32_t)code_of[p[j]], shift = j;
+        if (pairs && j + 1 < k && p[j + 1] != '.') {
+            row = ns + row * ns + (uint32_t)code_of[p[j + 1]];
+            j += 2;
+        } else {
+            j += 1;
+        }
+        program.push_back((uint16_t)(row | ((shift & 31u) << 7) | ((shift >> 5) << 12)));
+    }
 }
 
 int fail(std::string& error, int code, const char* what)
@@ -128,17 +146,7 @@ int build_library(const bss_table* t, BuiltLibrary& out, std::string& error)
             if (t->comp_pat_begin[c + 1] < pb || k > BSS_MAX_PATTERN) return fail(error, BSS_ERR_LIMIT, "component pattern longer than BSS_MAX_PATTERN");
             const uint8_t* p = t->pattern + pb;
             const uint32_t first_step = (uint32_t)program.size();
-            for (uint32_t j = 0; j < k;) {
-                if (p[j] == '.') { j++; continue; }
-                uint32_t row = (uint32_t)code_of[p[j]], shift = j;
-                if (pairs && j + 1 < k && p[j + 1] != '.') {
-                    row = ns + row * ns + (uint32_t)code_of[p[j + 1]];
-                    j += 2;
-                } else {
-                    j += 1;
-                }
-                program.push_back((uint16_t)(row | ((shift & 31u) << 7) | ((shift >> 5) << 12)));
-            }
+            append_program(p, k, code_of, pairs, ns, program);
             prog_range[c - c0] = {first_step, (uint32_t)program.size() - first_step};
         }
         if (u < t->n_units) {   // uniform symbols: a pattern with l literal symbols matches one position in |alphabet|^l
@@ -230,6 +238,61 @@ int build_library(const bss_table* t, BuiltLibrary& out, std::string& error)
         if (blob.size() > 0x7FFFFFFFu) return fail(error, BSS_ERR_LIMIT, "library too large");
     }
     out.unit_off[n_all] = (uint32_t)blob.size();
+
+    // pattern table: slots for the patterns shared by several components of searched units
+    out.pat_blob.clear();
+    out.pat_off.assign(1, 0);
+    out.pat_tslot.clear();
+    out.unit_slots.assign(4 * (size_t)std::max<uint32_t>(1, t->n_units), (uint16_t)kNoSlot);
+    out.n_slots = out.n_tslots = out.n_lean_units = 0;
+    {
+        std::unordered_map<std::string, uint32_t> uses;   // pattern -> components of searched units that carry it
+        const uint32_t searched_comps = t->n_units ? t->unit_comp_begin[t->n_units] : 0;
+        for (uint32_t c = 0; c < searched_comps; c++)
+            uses[std::string(reinterpret_cast<const char*>(t->pattern) + t->comp_pat_begin[c], t->comp_pat_begin[c + 1] - t->comp_pat_begin[c])]++;
+        std::unordered_map<std::string, uint32_t> slot_of;
+        const bool     pairs = alphabet.size() <= kPairAlphabet;
+        const uint32_t ns    = (uint32_t)alphabet.size();
+        for (uint32_t u = 0; u < t->n_units; u++) {
+            const uint32_t c0 = t->unit_comp_begin[u], C = t->unit_comp_begin[u + 1] - c0;
+            bool           every = C <= 4;
+            for (uint32_t c = 0; c < C; c++) {
+                const uint32_t    pb = t->comp_pat_begin[c0 + c], k = t->comp_pat_begin[c0 + c + 1] - pb;
+                const std::string key(reinterpret_cast<const char*>(t->pattern) + pb, k);
+                uint32_t          slot = kNoSlot;
+                if (uses[key] >= kSlotMinUses) {
+                    auto it = slot_of.find(key);
+                    if (it != slot_of.end()) {
+                        slot = it->second;
+                    } else if (out.n_slots < kSlotMax) {
+                        slot         = out.n_slots++;
+                        slot_of[key] = slot;
+                        std::vector<uint16_t> program;
+                        append_program(t->pattern + pb, k, code_of, pairs, ns, program);
+                        const bool     overlap = can_self_overlap(t->pattern + pb, k);
+                        const uint32_t words   = ((uint32_t)program.size() + 1) / 2;
+                        const size_t   base    = out.pat_blob.size();
+                        out.pat_blob.resize(base + 6 + words, 0);
+                        uint32_t* b = out.pat_blob.data() + base;
+                        b[1] = 1u;                               // one component, no check, delay 0
+                        b[2] = kNoGate;
+                        b[3] = (6u + words) << 16;
+                        b[4] = k | (12u << 8) | (overlap ? kCompOverlap : 0u);
+                        b[5] = (uint32_t)program.size() << 16;
+                        if (!program.empty()) std::memcpy(b + 6, program.data(), program.size() * sizeof(uint16_t));
+                        out.pat_off.push_back((uint32_t)out.pat_blob.size());
+                        out.pat_tslot.push_back(overlap ? (uint16_t)out.n_tslots++ : (uint16_t)kNoSlot);
+                    }
+                }
+                if (c < 4) out.unit_slots[4 * (size_t)u + c] = (uint16_t)slot;
+                every = every && slot != kNoSlot;
+            }
+            if (every && (out.unit_flags[u] & kUnitWindow) && t->unit_gate[u] == kNoGate) {
+                out.unit_flags[u] |= (uint8_t)kUnitLean;
+                out.n_lean_units++;
+            }
+        }
+    }
     out.list_density    = 0.f;
     if (!density.empty()) {
         const size_t at = (density.size() - 1) * 98 / 100;

@@ -7,6 +7,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -106,7 +107,8 @@ struct bss_library {
     cudaEvent_t  ev[4]      = {nullptr, nullptr, nullptr, nullptr};
     bss::DevLibrary       dev{};
     DeviceBuffer          d_blob, d_unit_off, d_unit_rlen, d_unit_probe, d_unit_flags, d_prefilter;
-    uint32_t              n_modules = 0, n_units = 0, n_window_units = 0;
+    DeviceBuffer          d_pat_blob, d_pat_off, d_pat_tslot, d_unit_slots, d_ptab_m, d_ptab_t, d_pflag;   // pattern table: slots (library), rows (per search)
+    uint32_t              n_modules = 0, n_units = 0, n_window_units = 0, n_lean_units = 0;
     bss::Tuning           tuning;
     std::vector<uint32_t> module_components;
     // work buffers, reused across searches
@@ -118,7 +120,7 @@ struct bss_library {
         uint64_t query_serial = 0, capacity = 0, dev_serial = 0;
         const void *records = nullptr, *seq_out = nullptr, *stream = nullptr, *counts = nullptr, *alive = nullptr, *lanes = nullptr, *heavy = nullptr,
                    *chunk_sites = nullptr, *chunk_words = nullptr, *seq_begin = nullptr, *prefilter = nullptr, *wlist = nullptr, *alive_w = nullptr,
-                   *lanes_w = nullptr;
+                   *ptab_m = nullptr, *ptab_t = nullptr, *pflag = nullptr;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof *this) == 0; }
     } graph_key;
     cudaGraphExec_t graph_exec = nullptr;
@@ -155,6 +157,7 @@ struct bss_sites {
     DeviceBuffer          d_records;
     PinnedBuffer          h_records;
     bool                  fetched = false;
+    bool                  pooled  = false;   // h_records comes from (and returns to) the process-wide pinned pool: a result no library owns
     std::vector<uint64_t> seq_word_begin;
 };
 
@@ -255,6 +258,10 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     BSS_CUDA_LIB(upload(lib->d_unit_rlen, built.unit_rlen.data(), built.unit_rlen.size()));
     BSS_CUDA_LIB(upload(lib->d_unit_flags, built.unit_flags.data(), built.unit_flags.size()));
     BSS_CUDA_LIB(upload(lib->d_unit_probe, built.unit_probe.data(), built.unit_probe.size() * 2));
+    BSS_CUDA_LIB(upload(lib->d_pat_blob, built.pat_blob.data(), built.pat_blob.size() * 4));
+    BSS_CUDA_LIB(upload(lib->d_pat_off, built.pat_off.data(), built.pat_off.size() * 4));
+    BSS_CUDA_LIB(upload(lib->d_pat_tslot, built.pat_tslot.data(), built.pat_tslot.size() * 2));
+    BSS_CUDA_LIB(upload(lib->d_unit_slots, built.unit_slots.data(), built.unit_slots.size() * 2));
     BSS_CUDA_LIB(lib->h_totals.reserve(8 * bss::kTotalsWords));
     BSS_CUDA_LIB(lib->d_totals.reserve(8 * bss::kTotalsWords));
 #undef BSS_CUDA_LIB
@@ -263,6 +270,13 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     lib->dev.unit_rlen  = static_cast<const uint8_t*>(lib->d_unit_rlen.ptr);
     lib->dev.unit_flags = static_cast<const uint8_t*>(lib->d_unit_flags.ptr);
     lib->dev.unit_probe = built.has_probes ? static_cast<const uint16_t*>(lib->d_unit_probe.ptr) : nullptr;
+    lib->dev.pat_blob   = static_cast<const uint32_t*>(lib->d_pat_blob.ptr);
+    lib->dev.pat_off    = static_cast<const uint32_t*>(lib->d_pat_off.ptr);
+    lib->dev.pat_tslot  = static_cast<const uint16_t*>(lib->d_pat_tslot.ptr);
+    lib->dev.unit_slots = static_cast<const uint16_t*>(lib->d_unit_slots.ptr);
+    lib->dev.n_slots    = built.n_slots;
+    lib->dev.n_tslots   = built.n_tslots;
+    lib->n_lean_units   = built.n_lean_units;
     lib->dev.n_units    = t->n_units;
     lib->dev.n_symbols  = (uint32_t)built.alphabet.size();
     lib->dev.cmax       = built.cmax;
@@ -287,6 +301,7 @@ void bss_library_destroy(bss_library* lib)
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
     for (DeviceBuffer* b : {&lib->oneshot.storage, &lib->d_blob, &lib->d_unit_off, &lib->d_unit_rlen, &lib->d_unit_probe, &lib->d_unit_flags, &lib->d_prefilter,
+                            &lib->d_pat_blob, &lib->d_pat_off, &lib->d_pat_tslot, &lib->d_unit_slots, &lib->d_ptab_m, &lib->d_ptab_t, &lib->d_pflag,
                             &lib->d_alive, &lib->d_lane_counts, &lib->d_heavy, &lib->d_counts, &lib->d_chunks, &lib->d_wlist, &lib->d_alive_w,
                             &lib->d_lane_counts_w, &lib->d_placements, &lib->d_idx_work, &lib->d_idx_hist, &lib->spare_idx_main, &lib->spare_idx_overlap,
                             &lib->d_totals, &lib->d_seq_word_begin, &lib->spare_records})
@@ -343,6 +358,7 @@ int bss_library_set_tuning(bss_library* lib, int knob, int64_t value)
         if (value == 0 || value > 1024) return fail(BSS_ERR_INVALID, "draw block out of range");
         t.window_draw = value;
         break;
+    case BSS_TUNE_PATTERN_TABLE: t.dict = value; break;
     default: return fail(BSS_ERR_INVALID, "unknown tuning knob");
     }
     lib->dev_serial++;   // a cached launch graph was built for the old plan
@@ -633,14 +649,23 @@ int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::W
         BSS_CUDA(lib->d_prefilter.reserve(4 * ((n_items + 31) / 32) + 4));
         work.prefilter = static_cast<uint32_t*>(lib->d_prefilter.ptr);
     }
-    work.wlist = work.alive_w = work.lane_counts_w = nullptr;
+    work.wlist = work.alive_w = nullptr;
     if (plan.window) {
         BSS_CUDA(lib->d_wlist.reserve(std::max<uint64_t>(4, n_items * 4)));
         BSS_CUDA(lib->d_alive_w.reserve(std::max<uint64_t>(4, n_items * 4)));
-        BSS_CUDA(lib->d_lane_counts_w.reserve(std::max<uint64_t>(4, n_items * 128)));
         work.wlist         = static_cast<uint32_t*>(lib->d_wlist.ptr);
         work.alive_w       = static_cast<uint32_t*>(lib->d_alive_w.ptr);
-        work.lane_counts_w = static_cast<uint32_t*>(lib->d_lane_counts_w.ptr);
+    }
+    work.ptab_m = work.ptab_t = nullptr;
+    work.pflag  = nullptr;
+    if (plan.dict) {
+        const uint64_t ns = q->dev.n_seqs;
+        BSS_CUDA(lib->d_ptab_m.reserve(std::max<uint64_t>(4, 4 * ns * lib->dev.n_slots * (plan.W + plan.WS))));
+        BSS_CUDA(lib->d_ptab_t.reserve(std::max<uint64_t>(4, 4 * ns * lib->dev.n_tslots * plan.W)));
+        BSS_CUDA(lib->d_pflag.reserve(std::max<uint64_t>(4, ns * lib->dev.n_slots)));
+        work.ptab_m = static_cast<uint32_t*>(lib->d_ptab_m.ptr);
+        work.ptab_t = static_cast<uint32_t*>(lib->d_ptab_t.ptr);
+        work.pflag  = static_cast<uint8_t*>(lib->d_pflag.ptr);
     }
     work.counts         = static_cast<uint32_t*>(lib->d_counts.ptr);
     work.chunk_sites    = static_cast<uint64_t*>(lib->d_chunks.ptr);
@@ -684,6 +709,7 @@ uint32_t count_launches(const bss_library* lib, const bss_query* q, const bss::P
     if (plan.window || (lib->dev.unit_probe && q->dev.kmers)) n++;
     if (ordinary) n += 1u + (plan.group == 32 && plan.list_cap ? 1u : 0u);
     if (plan.window) n++;
+    if (plan.dict && lib->dev.n_slots && q->dev.n_seqs) n++;   // pattern_kernel
     return n;
 }
 
@@ -858,7 +884,7 @@ int bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* 
         key.records = d_records; key.seq_out = d_seq_word_begin; key.stream = st; key.counts = work.counts; key.alive = work.alive;
         key.lanes = work.lane_counts; key.heavy = work.heavy_items; key.chunk_sites = work.chunk_sites; key.chunk_words = work.chunk_words;
         key.seq_begin = work.seq_word_begin; key.prefilter = work.prefilter; key.wlist = work.wlist; key.alive_w = work.alive_w;
-        key.lanes_w = work.lane_counts_w;
+        key.ptab_m = work.ptab_m; key.ptab_t = work.ptab_t; key.pflag = work.pflag;
         if (!lib->graph_exec || !(key == lib->graph_key)) {
             if (lib->graph_exec) { cudaGraphExecDestroy(lib->graph_exec); lib->graph_exec = nullptr; }
             cudaGraph_t graph = nullptr;
@@ -939,19 +965,109 @@ int bss_gather_cut(bss_library* lib, const uint32_t* d_blocks, uint32_t world, u
     });
 }
 
-int bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
-                     const uint64_t* mask_begin, bss_sites** out)
+}   // extern "C"
+
+namespace {
+
+int search_host_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
+                      const uint64_t* mask_begin, int fetch, bss_sites** out)
 {
-    return guarded([&]() -> int {
     if (!out) return fail(BSS_ERR_INVALID, "null argument");
     *out = nullptr;
     if (!lib) return fail(BSS_ERR_INVALID, "null argument");
     bss_query* q  = &lib->oneshot;   // device storage kept between calls: no allocation once it has grown
     int        rc = query_fill(lib, q, n_seqs, seqs, seq_begin, masks, mask_begin, false);
     if (rc != BSS_OK) return rc;
-    rc = bss_search_query(lib, q, 1, out);
+    rc = bss_search_query(lib, q, fetch, out);
     if (rc == BSS_OK) lib->stats.h2d_bytes = q->h2d_bytes;
     return rc;
+}
+
+// A few pinned host buffers kept for the results that no library owns (bss_search_sharded): page-locking memory
+// costs far more than a small search.
+struct PinnedPool {
+    std::mutex                mu;
+    std::vector<PinnedBuffer> spare;
+    PinnedBuffer take(size_t bytes)
+    {
+        PinnedBuffer b;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            size_t best = spare.size();
+            for (size_t i = 0; i < spare.size(); i++)
+                if (spare[i].cap >= bytes && (best == spare.size() || spare[i].cap < spare[best].cap)) best = i;
+            if (best < spare.size()) {
+                b = spare[best];
+                spare.erase(spare.begin() + (long)best);
+            }
+        }
+        if (b.reserve(bytes) != cudaSuccess) b.release();
+        return b;
+    }
+    void give(PinnedBuffer b)
+    {
+        if (!b.ptr) return;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (spare.size() < 4) { spare.push_back(b); return; }
+            size_t smallest = 0;
+            for (size_t i = 1; i < spare.size(); i++)
+                if (spare[i].cap < spare[smallest].cap) smallest = i;
+            if (spare[smallest].cap < b.cap) std::swap(spare[smallest], b);
+        }
+        b.release();
+    }
+} g_pinned_pool;
+
+}   // namespace
+
+bss_sites* bss::new_host_sites(uint64_t n_sites, uint64_t n_words, const std::vector<uint64_t>& seq_word_begin, uint32_t** records)
+{
+    bss_sites* s = new bss_sites();
+    s->h_records = g_pinned_pool.take(std::max<uint64_t>(16, n_words * 4));
+    if (!s->h_records.ptr) {
+        delete s;
+        return nullptr;
+    }
+    s->pooled         = true;
+    s->fetched        = true;
+    s->n_sites        = n_sites;
+    s->n_words        = n_words;
+    s->seq_word_begin = seq_word_begin;
+    *records          = static_cast<uint32_t*>(s->h_records.ptr);
+    return s;
+}
+
+extern "C" {
+
+int bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
+                     const uint64_t* mask_begin, bss_sites** out)
+{
+    return guarded([&]() -> int { return search_host_batch(lib, n_seqs, seqs, seq_begin, masks, mask_begin, 1, out); });
+}
+
+int bss_search_batch_resident(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin, const uint32_t* masks,
+                              const uint64_t* mask_begin, bss_sites** out)
+{
+    return guarded([&]() -> int { return search_host_batch(lib, n_seqs, seqs, seq_begin, masks, mask_begin, 0, out); });
+}
+
+int bss_sites_copy_out(const bss_sites* s, uint64_t word_begin, uint64_t n_words, uint32_t* host_dst)
+{
+    return guarded([&]() -> int {
+    if (!s || (!host_dst && n_words)) return fail(BSS_ERR_INVALID, "null argument");
+    if (word_begin > s->n_words || n_words > s->n_words - word_begin) return fail(BSS_ERR_INVALID, "range outside the record stream");
+    if (!n_words) return BSS_OK;
+    if (s->fetched && s->h_records.ptr) {
+        std::memcpy(host_dst, static_cast<const uint32_t*>(s->h_records.ptr) + word_begin, n_words * 4);
+        return BSS_OK;
+    }
+    if (!s->lib || !s->d_records.ptr) return fail(BSS_ERR_INVALID, "the records are gone (library destroyed)");
+    BSS_CUDA(cudaSetDevice(s->lib->device));
+    BSS_CUDA(cudaMemcpyAsync(host_dst, static_cast<const uint32_t*>(s->d_records.ptr) + word_begin, n_words * 4, cudaMemcpyDeviceToHost, s->lib->stream));
+    BSS_CUDA(cudaStreamSynchronize(s->lib->stream));
+    s->lib->stats.d2h_bytes += n_words * 4;
+    return BSS_OK;
     });
 }
 
@@ -981,6 +1097,7 @@ void bss_sites_free(bss_sites* s)
         if (s->h_records.cap > s->lib->spare_host.cap) std::swap(s->h_records, s->lib->spare_host);
     }
     s->d_records.release();
+    if (s->pooled) { g_pinned_pool.give(s->h_records); s->h_records = PinnedBuffer{}; }
     s->h_records.release();
     delete s;
 }
@@ -1195,7 +1312,7 @@ int bss_debug_counts(bss_library* lib, uint32_t* counts, uint32_t n, uint32_t* l
 {
     cudaStreamSynchronize(lib->stream);
     if (n && lib->d_counts.ptr) cudaMemcpy(counts, lib->d_counts.ptr, 4ull * n, cudaMemcpyDeviceToHost);
-    if (n_rows && lib->d_lane_counts_w.ptr) cudaMemcpy(lanes_w, lib->d_lane_counts_w.ptr, 128ull * n_rows, cudaMemcpyDeviceToHost);
+    (void)lanes_w;   // (the window walk no longer keeps per-lane counts)
     if (n_rows && lib->d_alive_w.ptr) cudaMemcpy(alive_w, lib->d_alive_w.ptr, 4ull * n_rows, cudaMemcpyDeviceToHost);
     return (int)cudaGetLastError();
 }

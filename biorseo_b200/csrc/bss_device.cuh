@@ -8,9 +8,17 @@
 #include <stdexcept>
 #include <string>
 
+#include <vector>
+
 #include "bss_layout.h"
 
+struct bss_sites;
+
 namespace bss {
+
+// A result handle that no library owns (bss_search_sharded): pinned host records of n_words words, to be filled by
+// the caller through *records. Null when the pinned memory cannot be had.
+bss_sites* new_host_sites(uint64_t n_sites, uint64_t n_words, const std::vector<uint64_t>& seq_word_begin, uint32_t** records);
 
 // Sets the thread-local message behind bss_last_error() and returns `code` (bss_capi.cu).
 int set_error(int code, const std::string& what);
@@ -44,7 +52,12 @@ struct DevLibrary {
     const uint32_t* unit_off;    // [n_units + n_gates + 1] word offsets into blob
     const uint8_t*  unit_rlen;   // [n_units] words per record of the unit: components + 1
     const uint16_t* unit_probe;  // [n_units][4] k-mer probes (longest window of 4..6 consecutive literal symbols) of up to four components, 0xFFFF = none; null: no filter
-    const uint8_t*  unit_flags;  // [n_units] kUnitWindow
+    const uint8_t*  unit_flags;  // [n_units] kUnitWindow, kUnitLean
+    const uint32_t* pat_blob;    // pattern table: one-component descriptors of the slots (bss_layout.h)
+    const uint32_t* pat_off;     // [n_slots + 1] word offsets into pat_blob
+    const uint16_t* pat_tslot;   // [n_slots] row of the slot's thinned set, or kNoSlot
+    const uint16_t* unit_slots;  // [n_units][4] slots of the first four components, kNoSlot = none
+    uint32_t        n_slots, n_tslots;
     uint32_t        n_units;     // searched units
     uint32_t        n_symbols;   // alphabet size
     uint32_t        cmax;        // max components per unit (gates included)
@@ -85,6 +98,9 @@ struct Plan {
     uint32_t list_cap;     // rank-space walk: match-list entries per item (0 = depth-first walk only)
     uint32_t window;       // 1: items of window-walk units on narrow-band sequences go through route_kernel + window_kernel
     uint32_t window_draw;  // list entries a warp of the window count pass draws per atomic
+    uint32_t window_qcap;  // window walk: entries per level queue (at least the widest band + 1)
+    uint32_t window_kw;    // window walk: stash words per lane = words a band window can span
+    uint32_t dict;         // 1: the pattern table of this (query, library) is built at the start of the search and the window pass reads it
     uint32_t window_stage; // 1: the window kernel stages the occurrence table and the banded mask in shared memory (one sequence)
     uint32_t smem_bytes_window;   // dynamic shared memory of the window kernel
     uint32_t smem_bytes;        // dynamic shared memory of the count kernel
@@ -110,14 +126,18 @@ struct Work {
     // window walk (route_kernel, window_kernel)
     uint32_t* wlist;         // [n_seqs * n_units] items routed to the window pass, in arrival order
     uint32_t* alive_w;       // [n_seqs * n_units] window items with sites, in completion order
-    uint32_t* lane_counts_w; // [n_seqs * n_units][32] sites found by every lane of the window walk
+    // pattern table of this search (pattern_kernel): per (sequence, slot) the match set + its word summary, the thinned set
+    // of the slots that can overlap themselves, and flags (bit 0: the pattern occurs, bit 1: its matches overlap on this sequence)
+    uint32_t* ptab_m;        // [n_seqs][n_slots][W + WS]
+    uint32_t* ptab_t;        // [n_seqs][n_tslots][W]
+    uint8_t*  pflag;         // [n_seqs][n_slots]
 };
 constexpr uint32_t kTotalsWords = 16;
 
 // Developer knobs (bss_library_set_tuning): force rarely taken paths on small inputs (tests), compare variants
 // (benchmarks). A negative value means automatic.
 struct Tuning {
-    int64_t group = -1, units_per_chunk = -1, heavy_ranks = -1, list_cap = -1, window = -1, window_stage = -1, window_draw = -1;
+    int64_t group = -1, units_per_chunk = -1, heavy_ranks = -1, list_cap = -1, window = -1, window_stage = -1, window_draw = -1, dict = -1;
 };
 
 __host__ __device__ inline int band_words(int band) { return band < 0 ? 0 : ((31 + band) >> 5) + 1; }

@@ -1619,14 +1619,20 @@ Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tun
     p.smem_bytes      = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, false);
     p.smem_bytes_emit = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, true);
     // Window walk: whole warps only; the query carries banded masks; the working set fits.
-    p.smem_bytes_window = 4u * window_smem_words(lib.cmax, p.W, p.WS, kWinThreads);
+    const int widest    = known_band == INT32_MIN ? kWindowBandMax : std::min(std::max(known_band, 0), kWindowBandMax);
+    p.window_kw         = (uint32_t)band_words(widest);
+    p.window_qcap       = std::max(64u, ((uint32_t)widest + 1u + 31u) & ~31u);
+    p.smem_bytes_window = 4u * window_smem_words(lib.cmax, p.W, p.WS, kWinThreads, p.window_qcap, p.window_kw);
     p.window = (p.group == 32 && n_window_units > 0 && q.bmask != nullptr && p.smem_bytes_window <= 160u * 1024u && tuning.window != 0) ? 1u : 0u;
     p.window_draw  = tuning.window_draw > 0 ? (uint32_t)tuning.window_draw : 1u;   // (measured on c4: 1 -> 0.146 ms, 4 -> 0.166, 32 -> 0.53: balance beats atomics)
+    // Pattern table: worth it when the library shares patterns and the table of this query stays small (it is rebuilt by every search)
+    const uint64_t table_bytes = 4ull * n_seqs * ((uint64_t)lib.n_slots * (p.W + p.WS) + (uint64_t)lib.n_tslots * p.W);
+    p.dict         = (p.window && lib.n_slots > 0 && table_bytes <= (64ull << 20) && tuning.dict != 0) ? 1u : 0u;
     p.window_stage = 0;
     if (p.window && n_seqs == 1 && known_band >= 0 && known_band <= kWindowBandMax && tuning.window_stage > 0) {
         // occurrence table + banded mask of the one sequence in shared memory, next to the warps' scratch
         const uint32_t staged = 4u * (window_stage_words(q.occ_rows, q.occ_stride, max_len, (uint32_t)band_words(known_band)) +
-                                      window_smem_words(lib.cmax, p.W, p.WS, kWinThreadsStaged));
+                                      window_smem_words(lib.cmax, p.W, p.WS, kWinThreadsStaged, p.window_qcap, p.window_kw));
         if (staged <= 110u * 1024u) {   // two CTAs of 16 warps per SM
             p.window_stage      = 1;
             p.smem_bytes_window = staged;
@@ -1694,13 +1700,26 @@ cudaError_t launch_window(const DevLibrary& lib, const DevQuery& q, const Plan& 
     return cudaGetLastError();
 }
 
-cudaError_t launch_route(const DevLibrary& lib, const DevQuery& q, const Work& work, int sm_count, cudaStream_t s)
+cudaError_t launch_pattern(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, int sm_count, cudaStream_t s)
+{
+    const uint64_t tasks = (uint64_t)q.n_seqs * lib.n_slots;
+    if (tasks == 0) return cudaSuccess;
+    const uint32_t smem = 4u * (kThreads / 32) * 2u * (plan.W + plan.WS);
+    cudaError_t    e    = cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t grid = std::min<uint64_t>((tasks + kThreads / 32 - 1) / (kThreads / 32), (uint64_t)sm_count * 16);
+    pattern_kernel<<<(uint32_t)grid, kThreads, smem, s>>>(lib, q, plan, work);
+    BSS_SYNC_CHECK("pattern_kernel", s);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_route(const DevLibrary& lib, const DevQuery& q, const Work& work, uint32_t dict, int sm_count, cudaStream_t s)
 {
     const uint64_t n_items = (uint64_t)q.n_seqs * lib.n_units;
     if (n_items == 0) return cudaSuccess;
     uint64_t grid = (n_items + 255) / 256;
     if (grid > (uint64_t)sm_count * 64) grid = (uint64_t)sm_count * 64;
-    route_kernel<<<(uint32_t)grid, 256, 0, s>>>(lib, q, work, n_items);
+    route_kernel<<<(uint32_t)grid, 256, 0, s>>>(lib, q, work, n_items, dict);
     BSS_SYNC_CHECK("route_kernel", s);
     return cudaGetLastError();
 }
@@ -1708,7 +1727,8 @@ cudaError_t launch_route(const DevLibrary& lib, const DevQuery& q, const Work& w
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, bool ordinary, int sm_count, cudaStream_t s)
 {
     cudaError_t e = cudaSuccess;
-    if (plan.window) e = launch_route(lib, q, work, sm_count, s);
+    if (plan.dict) e = launch_pattern(lib, q, plan, work, sm_count, s);
+    if (plan.window && e == cudaSuccess) e = launch_route(lib, q, work, plan.dict, sm_count, s);
     else if (work.prefilter) e = launch_prefilter(lib, q, work, sm_count, s);
     if (ordinary) {
         if (e == cudaSuccess) e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, 0, s);

@@ -25,6 +25,10 @@ constexpr uint32_t kCheckOrdered = 1u << 25;   // check flag: 0 <= u < v < n hol
 constexpr uint32_t kCheckRow    = 1u << 26;    // check flag: u < v holds for every placement, u on an earlier component, v = candidate + offset >= candidate:
                                                //             the candidates that pass are the bits of mask row u shifted down by the offset (window walk)
 constexpr uint32_t kUnitWindow  = 1u;          // blob[3] / unit_flags bit: every level >= 1 has a row check and the descriptor fits the staging area (window walk eligible)
+constexpr uint32_t kUnitLean    = 2u;          // unit_flags bit: window-walk unit without a gate, at most four components, every pattern in the pattern table
+constexpr uint32_t kNoSlot      = 0xFFFFu;     // unit_slots entry: the component's pattern has no slot in the pattern table
+constexpr uint32_t kSlotMinUses = 3;           // a pattern gets a slot when at least this many components of searched units share it
+constexpr uint32_t kSlotMax     = 0xFFF0u;     // slots per library
 constexpr uint32_t kBlobStageWords = 64;       // unit descriptor words staged in shared memory per warp; larger descriptors are read in place
 constexpr int      kWindowBandMax = 255;       // widest pair (v - u) a sequence's mask may allow for the window walk
 
@@ -52,6 +56,12 @@ struct BuiltLibrary {
     std::vector<uint32_t> blob, unit_off;          // unit_off: [n_units + n_gates + 1]
     std::vector<uint8_t>  unit_rlen, unit_flags;   // [max(1, n_units)]
     std::vector<uint16_t> unit_probe;              // [4 * max(1, n_units)]
+    // Pattern table: the distinct component patterns that several units share get a slot; per query the match set (and the
+    // thinned set) of every slot is computed ONCE (pattern_kernel) instead of once per unit that uses the pattern.
+    std::vector<uint32_t> pat_blob, pat_off;       // one-component descriptors of the slots (same layout as a unit descriptor), pat_off: [n_slots + 1]
+    std::vector<uint16_t> pat_tslot;               // [n_slots] row of the slot's thinned set, kNoSlot for patterns that cannot overlap themselves
+    std::vector<uint16_t> unit_slots;              // [4 * max(1, n_units)] slots of the first four components, kNoSlot = none
+    uint32_t              n_slots = 0, n_tslots = 0, n_lean_units = 0;
     std::vector<uint32_t> module_components;       // [n_modules]
     std::vector<uint8_t>  alphabet;
     uint32_t              cmax = 1, n_window_units = 0;

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) bandmask_kernel(const DevQuery query, uin
 }
 
 // One thread per item. See the header of this file.
-__global__ void __launch_bounds__(256) route_kernel(const DevLibrary lib, const DevQuery query, const Work work, uint64_t n_items)
+__global__ void __launch_bounds__(256) route_kernel(const DevLibrary lib, const DevQuery query, const Work work, uint64_t n_items, uint32_t plan_dict)
 {
     __shared__ uint32_t warp_win[8], warp_old[8], base_win;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,6 +108,15 @@ __global__ void __launch_bounds__(256) route_kernel(const DevLibrary lib, const 
                     }
                 }
             }
+            if (alive && plan_dict) {   // pattern table: a component whose pattern does not occur ends the item
+                const uint2    sl = __ldg(reinterpret_cast<const uint2*>(lib.unit_slots) + u);
+                const uint8_t* fl = work.pflag + (size_t)qi * lib.n_slots;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t slot = ((i < 2 ? sl.x : sl.y) >> (16 * (i & 1))) & 0xFFFFu;
+                    if (slot != kNoSlot && !(fl[slot] & 1u)) alive = false;
+                }
+            }
             if (!alive) work.counts[item] = 0;
             window = alive && (__ldg(lib.unit_flags + u) & kUnitWindow) && __ldg(query.band + qi) <= kWindowBandMax;
         }
@@ -127,9 +136,11 @@ __global__ void __launch_bounds__(256) route_kernel(const DevLibrary lib, const 
     }
 }
 
-__host__ __device__ inline uint32_t window_smem_words(uint32_t cmax, uint32_t W, uint32_t WS, uint32_t threads)
+// Per warp: descriptor, match sets M and T with the summaries of both, and the walk's scratch (bss_window_walk.h):
+// decoded level parameters, saved cursors, one queue of `qcap` entries per level but the last, the stash of `kw` words per lane.
+__host__ __device__ inline uint32_t window_smem_words(uint32_t cmax, uint32_t W, uint32_t WS, uint32_t threads, uint32_t qcap, uint32_t kw)
 {
-    return (threads / 32) * (kBlobStage + 2 * cmax * (W + WS)) + 3 * cmax * threads;
+    return (threads / 32) * (kBlobStage + 2 * cmax * (W + WS) + (win::kLevelWords + 2 + 6) * cmax + (cmax > 1 ? cmax - 1 : 1) * qcap + 32 * kw);
 }
 
 // Occurrence table + banded mask of ONE sequence staged in shared memory (words), when the plan asks for it.
@@ -238,6 +249,41 @@ __device__ __forceinline__ bool gate_open_any(const uint32_t* gblob, const uint3
     return true;
 }
 
+// Pattern table of one search: one warp per (sequence, slot) computes the match set of the slot's pattern (with its word
+// summary), and for patterns that can overlap themselves the thinned set, ONCE — every unit that carries the pattern
+// reads the rows instead of matching and thinning again (the headline library holds 50 000 units over a few hundred
+// distinct short strands). Same routines as the per-unit path, on the slot's one-component descriptor.
+__global__ void __launch_bounds__(kThreads) pattern_kernel(const DevLibrary lib, const DevQuery query, const Plan plan, const Work work)
+{
+    extern __shared__ __align__(16) uint32_t smem_raw[];
+    constexpr uint32_t warps = kThreads / 32;
+    const int          W = (int)plan.W, WS = (int)plan.WS, WP = (int)query.occ_stride;
+    const uint32_t     warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* g_M  = smem_raw + warp * (2 * (W + WS));
+    uint32_t* g_SM = g_M + W;
+    uint32_t* g_T  = g_SM + WS;
+    uint32_t* g_ST = g_T + W;
+    const uint64_t n_tasks = (uint64_t)query.n_seqs * lib.n_slots;
+    for (uint64_t task = (uint64_t)blockIdx.x * warps + warp; task < n_tasks; task += (uint64_t)gridDim.x * warps) {
+        const uint32_t  qi = (uint32_t)(task / lib.n_slots), slot = (uint32_t)(task - (uint64_t)qi * lib.n_slots);
+        const SeqCtx    sq = load_seq(lib, query, qi);
+        const uint32_t* blob = lib.pat_blob + __ldg(lib.pat_off + slot);
+        uint32_t        flag = 0;
+        if (match_components_any(blob, sq.occ, WP, g_M, g_SM, W, WS, sq.n)) {
+            flag = 1u;
+            uint32_t* out = work.ptab_m + task * (size_t)(W + WS);
+            for (int i = (int)lane; i < W + WS; i += 32) out[i] = g_M[i];   // (M and its summary are contiguous)
+            if ((blob[4] & kCompOverlap) && (thin_components_win(blob, g_M, g_SM, g_T, g_ST, W, WS) & 1u)) {
+                flag |= 2u;
+                uint32_t* tout = work.ptab_t + ((size_t)qi * lib.n_tslots + __ldg(lib.pat_tslot + slot)) * (size_t)W;
+                for (int i = (int)lane; i < W; i += 32) tout[i] = g_T[i];
+            }
+        }
+        if (lane == 0) work.pflag[task] = (uint8_t)flag;
+        __syncwarp();
+    }
+}
+
 template <bool EMIT, bool STAGE>
 #ifndef BSS_WIN_MIN_CTAS
 #define BSS_WIN_MIN_CTAS 8
@@ -287,13 +333,19 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
     uint32_t* g_T    = base + warp * lib.cmax * W;                     base += warps * lib.cmax * W;
     uint32_t* g_SM   = base + warp * lib.cmax * WS;                    base += warps * lib.cmax * WS;
     uint32_t* g_ST   = base + warp * lib.cmax * WS;                    base += warps * lib.cmax * WS;
-    uint32_t* col    = base + threadIdx.x;   // three columns of cmax entries per thread, stride THREADS
+    const uint32_t qcap = plan.window_qcap, kw = plan.window_kw, qlevels = lib.cmax > 1 ? lib.cmax - 1 : 1;
+    int*      g_lp    = reinterpret_cast<int*>(base) + warp * win::kLevelWords * lib.cmax;   base += warps * win::kLevelWords * lib.cmax;
+    uint32_t* g_ctl   = base + warp * 2 * lib.cmax;                                          base += warps * 2 * lib.cmax;
+    uint32_t* g_Q     = base + warp * qlevels * qcap;                                        base += warps * qlevels * qcap;
+    uint32_t* g_stash = base + warp * 32 * kw;                                               base += warps * 32 * kw;
+    base += (base - smem_raw) & 1u;   // (8-byte alignment of the row pointers)
+    const uint32_t** g_rows = reinterpret_cast<const uint32_t**>(base) + warp * 3 * lib.cmax;      base += warps * 6 * lib.cmax;
 #ifdef BSS_DEBUG_ASSERT
     if ((g_win_skip & 64) && blockIdx.x == 0 && threadIdx.x == 0) {
         uint32_t dyn;
         asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
         printf("[win dbg] EMIT %d dyn smem %u B, plan says %u B, used %u B, cmax %u W %d WS %d n_list %u\n", (int)EMIT, dyn, plan.smem_bytes_window,
-               (uint32_t)((base - smem_raw) + 3 * lib.cmax * THREADS) * 4u, lib.cmax, W, WS, n_list);
+               (uint32_t)(base - smem_raw) * 4u, lib.cmax, W, WS, n_list);
     }
 #endif
 
@@ -358,67 +410,79 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
         if (g_win_skip & 4) alive = false;
         if ((g_win_skip >> 8) && u != (uint32_t)(g_win_skip >> 8) - 1u) alive = false;   // one unit only
 #endif
-        if (!EMIT && gate != kNoGate) {   // items on the alive list have passed their gate
-            alive = gate_open_any(lib.blob + __ldg(lib.unit_off + gate), occ, WP, g_M, g_SM, W, WS, n);
-            __syncwarp();
+        // Lean units: every pattern has a row in the pattern table of this search (pattern_kernel): no matching, no thinning
+        // here, the walk reads the table. (The route kernel has already dropped the items one of whose patterns does not occur.)
+        const bool lean = plan.dict && (__ldg(lib.unit_flags + u) & kUnitLean);
+        uint32_t   ovl  = 0;
+        if (lean) {
+            uint32_t flag = 0;
+            if ((int)lane < C) {
+                const uint32_t slot = __ldg(lib.unit_slots + 4 * (size_t)u + lane);
+                const size_t   at   = (size_t)qi * lib.n_slots + slot;
+                flag                = work.pflag[at];
+                const uint32_t* m   = work.ptab_m + at * (size_t)(W + WS);
+                g_rows[3 * lane]     = m;
+                g_rows[3 * lane + 1] = (flag & 2u) ? work.ptab_t + ((size_t)qi * lib.n_tslots + __ldg(lib.pat_tslot + slot)) * (size_t)W : m;
+                g_rows[3 * lane + 2] = m + W;
+            }
+            ovl = __ballot_sync(0xFFFFFFFFu, (flag & 2u) != 0);
+        } else {
+            if (!EMIT && gate != kNoGate) {   // items on the alive list have passed their gate
+                alive = gate_open_any(lib.blob + __ldg(lib.unit_off + gate), occ, WP, g_M, g_SM, W, WS, n);
+                __syncwarp();
+            }
+            if (alive) alive = match_components_any(blob, occ, WP, g_M, g_SM, W, WS, n);
         }
-        if (alive) alive = match_components_any(blob, occ, WP, g_M, g_SM, W, WS, n);
 
-        uint64_t lane_sites = 0, item_sites = 0;
+        uint64_t item_sites = 0;
 #ifdef BSS_DEBUG_ASSERT
         if (g_win_skip & 2) alive = false;
 #endif
         if (alive) {
-            win::Ctx cx;
-            cx.blob = blob; cx.M = g_M; cx.T = g_T; cx.SM = g_SM; cx.ST = g_ST;
+            win::Walk cx;
+            if (!lean) {
+                ovl = thin_components_win(blob, g_M, g_SM, g_T, g_ST, W, WS);
+                if ((int)lane < C) {
+                    g_rows[3 * lane]     = g_M + lane * W;
+                    g_rows[3 * lane + 1] = g_T + lane * W;
+                    g_rows[3 * lane + 2] = g_SM + lane * WS;
+                }
+            }
+            __syncwarp();
+            cx.blob = blob; cx.rows = g_rows;
             cx.band = sq.band;
-            cx.K    = band_words(sq.band);
+            cx.K    = min(band_words(sq.band), (int)kw);
             cx.bm   = STAGE ? s_bm : query.bmask + (size_t)kBandWordsMax * query.seq_begin[qi];
-            cx.pos  = col;
-            cx.bits = col + lib.cmax * THREADS;
-            cx.grd  = col + 2 * lib.cmax * THREADS;
-            cx.ovl  = thin_components_win(blob, g_M, g_SM, g_T, g_ST, W, WS);
-            cx.W = W; cx.WS = WS; cx.n = n; cx.C = C; cx.delay = (int)(blob[1] >> 16); cx.cs = THREADS;
-            // lane l owns the words [l * per, (l + 1) * per) of the first component's candidates: lane order = position order
-            const int per = (sq.Wq + 31) >> 5;
-            const int w0 = min(sq.Wq, (int)lane * per), w1 = min(sq.Wq, w0 + per);
+            cx.lp = g_lp; cx.ctl = g_ctl; cx.Q = g_Q; cx.stash = g_stash; cx.qcap = (int)qcap;
+            cx.ovl  = ovl;
+            cx.W = W; cx.WS = WS; cx.n = n; cx.C = C; cx.delay = (int)(blob[1] >> 16);
 #ifdef BSS_DEBUG_ASSERT
             if (g_win_skip & 1) { __syncwarp(); goto skip_walk; }
 #endif
+            // one warp walks the item breadth-first by level (bss_window_walk.h); the emit pass walks it again and writes
             if (EMIT) {
-                const uint64_t mine = work.lane_counts_w[(size_t)slot * 32 + lane];
-                uint64_t       total;
-                const uint64_t ex = Gr::exclusive(mine, total);
-                if (mine && BSS_WIN_CHECK(out_words + (ex + mine) * (uint64_t)(C + 1) <= work.totals[0], 24)) {
-                    const uint64_t wrote = win::walk_words<true>(cx, w0, w1, module, records + out_words + ex * (uint64_t)(C + 1));
-                    (void)BSS_WIN_CHECK(wrote == mine, 25);
-                }
+                const uint64_t wrote = win::walk<true>(cx, sq.Wq, module, records + out_words);
+                (void)BSS_WIN_CHECK(wrote == work.counts[sq.item0 + u], 25);
             } else {
-                lane_sites = win::walk_words<false>(cx, w0, w1, module, nullptr);
-                item_sites = Gr::sum(lane_sites);
+                item_sites = win::walk<false>(cx, sq.Wq, module, nullptr);
             }
         }
 #ifdef BSS_DEBUG_ASSERT
     skip_walk:
-        if (g_win_skip & 8) { item_sites = 0; lane_sites = 0; }   // walk, but drop what it found
+        if (g_win_skip & 8) item_sites = 0;   // walk, but drop what it found
 #endif
         __syncwarp();   // the warp's scratch is reused by its next item
         if (!EMIT) {
-            uint32_t where = 0;
             if (lane == 0) {
                 if (item_sites > 0xFFFFFFFFull) atomicOr((unsigned long long*)(work.totals + 2), 1ull);
                 work.counts[sq.item0 + u] = (uint32_t)item_sites;
                 if (item_sites) {
                     const uint32_t chunk = qi * plan.chunks_per_seq + u / plan.units_per_chunk;
-                    where               = (uint32_t)atomicAdd((unsigned long long*)(work.totals + 5), 1ull);
-                    work.alive_w[where] = item;
+                    const uint32_t where = (uint32_t)atomicAdd((unsigned long long*)(work.totals + 5), 1ull);
+                    work.alive_w[where]  = item;
                     atomicAdd((unsigned long long*)&work.chunk_sites[chunk], (unsigned long long)item_sites);
                     atomicAdd((unsigned long long*)&work.chunk_words[chunk], (unsigned long long)(item_sites * (uint64_t)(C + 1)));
                 }
-            }
-            if (item_sites) {
-                where = Gr::first(where);
-                if (BSS_WIN_CHECK((uint64_t)where < (uint64_t)query.n_seqs * lib.n_units, 26)) work.lane_counts_w[(size_t)where * 32 + lane] = (uint32_t)lane_sites;
             }
             if (slot + 1 == block_end) {   // (uniform)
                 slot      = Gr::first(next_slot);

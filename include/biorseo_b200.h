@@ -141,6 +141,7 @@ int  bss_library_set_module_base(bss_library* lib, uint32_t base);
 #define BSS_TUNE_WINDOW           4   /* 0: never take the window walk                                 */
 #define BSS_TUNE_WINDOW_STAGE     5   /* 1: window kernel stages occurrence table + banded mask in shared memory (cp.async.bulk) */
 #define BSS_TUNE_WINDOW_DRAW      6   /* list entries a warp of the window count pass draws per atomic (1..1024)        */
+#define BSS_TUNE_PATTERN_TABLE    7   /* 0: no pattern table (every unit matches its own patterns)                         */
 int  bss_library_set_tuning(bss_library* lib, int knob, int64_t value);
 uint32_t bss_library_units(const bss_library* lib);
 uint32_t bss_library_window_units(const bss_library* lib);   /* units every component of which is tied by a pair to an earlier one */
@@ -206,6 +207,30 @@ int  bss_search(bss_library* lib, const char* seq, uint32_t n, const uint32_t* m
 int  bss_search_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin,
                       const uint32_t* masks, const uint64_t* mask_begin, bss_sites** out);
 
+/* The same, records left in device memory (bss_sites_device_records; bss_sites_records is NULL): for callers that
+ * consume them on the device, or fetch ranges of them with bss_sites_copy_out. */
+int  bss_search_batch_resident(bss_library* lib, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin,
+                               const uint32_t* masks, const uint64_t* mask_begin, bss_sites** out);
+
+/* ---- multi-GPU in ONE process: the library cut over the GPUs of the box (SURVEY 8b "X_search_sharded") ---- */
+/* The reference's unit of parallelism is one job per module of one library (cppsrc/MOIP.cpp:246-293, and the RIN /
+ * DESC twins :159-243): the library is cut into n_gpus CONTIGUOUS module ranges balanced by a search-cost estimate
+ * (match steps + expected placements per module on a query of typical_len nucleotides; 0: 1000), every GPU owns one
+ * range (its records carry global module indices) and searches it on the replicated query; the ranges' records come
+ * back as ONE stream in canonical (sequence, module, placement) order in pinned host memory — the very stream
+ * bss_search_batch gives on one GPU, bit for bit. One host thread per GPU inside; no torch, no NCCL, no IPC.
+ * devices == NULL selects devices 0 .. n_gpus - 1. Units must come module by module (unit_module non-decreasing). */
+typedef struct bss_sharded bss_sharded;
+int          bss_sharded_create(const bss_table* table, const int* devices, uint32_t n_gpus, uint32_t typical_len, bss_sharded** out);
+void         bss_sharded_destroy(bss_sharded* s);
+uint32_t     bss_sharded_gpus(const bss_sharded* s);
+int          bss_sharded_range(const bss_sharded* s, uint32_t shard, int* device, uint32_t* module_begin, uint32_t* module_end);
+bss_library* bss_sharded_library(bss_sharded* s, uint32_t shard);   /* the range's own library handle (statistics, tuning) */
+int          bss_search_sharded(bss_sharded* s, uint32_t n_seqs, const char* seqs, const uint64_t* seq_begin,
+                                const uint32_t* masks, const uint64_t* mask_begin, bss_sites** out);
+/* The cut alone (host only, no GPU needed): module_begin[0 .. n_shards] receives the range boundaries. */
+int          bss_shard_ranges(const bss_table* table, uint32_t n_shards, uint32_t typical_len, uint32_t* module_begin);
+
 /* ---- multi-GPU: cut of a padded all-gather (biorseo_b200/sharded.py) ---- */
 /* d_blocks holds `world` blocks of block_words u32 each: [header_words of header | records | padding];
  * the last u64 of a header is the block's number of record words (what bss_search_query_into writes
@@ -247,6 +272,9 @@ uint64_t        bss_sites_words(const bss_sites* s);
 const uint32_t* bss_sites_records(const bss_sites* s);         /* pinned host memory or NULL   */
 const uint32_t* bss_sites_device_records(const bss_sites* s);  /* device memory                */
 const uint64_t* bss_sites_seq_word_begin(const bss_sites* s);  /* [n_seqs + 1] host            */
+/* Copies the words [word_begin, word_begin + n_words) of the record stream to host memory (pinned or pageable),
+ * wherever the records live. */
+int             bss_sites_copy_out(const bss_sites* s, uint64_t word_begin, uint64_t n_words, uint32_t* host_dst);
 void            bss_sites_free(bss_sites* s);
 
 /* ---- insertion-variable index (row "next" of the path: the consumer of the site list) ---- */

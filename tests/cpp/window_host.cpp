@@ -1,10 +1,10 @@
 // CPU emulation of the window pass (TEST infrastructure, not product code, never shipped in the library).
 //
-// The per-lane enumerator of window_kernel lives in a host/device header (biorseo_b200/csrc/bss_window_walk.h).
+// The warp-cooperative enumerator of window_kernel lives in a host/device header (biorseo_b200/csrc/bss_window_walk.h).
 // This harness compiles THAT source with g++ and drives it the way the kernel does — unit descriptors from the
 // product's own builder (bss_blob.cpp), match masks M and thinned sets T computed naively from the pattern
-// bytes, the banded mask re-laid like bandmask_kernel does, 32 lanes with a contiguous range of mask words each,
-// per-lane counts -> exclusive prefix -> emit — so that the CPU test-suite can compare the walk with the
+// bytes, the banded mask re-laid like bandmask_kernel does, the 32 lanes of the warp emulated by loops between the
+// walk's phases, count walk then emit walk — so that the CPU test-suite can compare the walk with the
 // flat-table interpreter on thousands of random units without a GPU. The kernel's warp-level parts (occurrence
 // table, match programs, thinning) are not exercised here; they are covered by the GPU tests.
 #include <algorithm>
@@ -124,12 +124,18 @@ int window_host_search(const bss_table* t, const char* seq_bytes, uint32_t n_u, 
                 if (w == Wm - 1 && (n & 31)) x &= (1u << (n & 31)) - 1u;
                 bm[(size_t)u * K + j] = x;
             }
-    const int cs = 32;   // column stride: 32 emulated lanes
-    // (the columns start from a poison value taken from the environment: the walk must never read a column entry it
-    //  has not written for the current item, so the result may not depend on it)
+    // the walk's scratch, as the kernel carves it per warp (bss_window.cuh): level parameters, cursors, level queues, stash.
+    // It starts from a poison value taken from the environment: the walk must never read an entry it has not written for
+    // the current item, so the result may not depend on it. WINDOW_HOST_QCAP shrinks the queues to force the "queue full,
+    // descend and come back" path on small inputs.
     const char*           poison_env = std::getenv("WINDOW_HOST_POISON");
     const uint32_t        poison = poison_env ? (uint32_t)std::strtoul(poison_env, nullptr, 0) : 0u;
-    std::vector<uint32_t> cols((size_t)3 * lib.cmax * cs, poison);
+    const char*           qcap_env = std::getenv("WINDOW_HOST_QCAP");
+    const int             widest = std::max(band, 0);
+    const int             qcap = qcap_env ? std::max(std::atoi(qcap_env), std::max(32, widest + 1)) : std::max(64, (widest + 1 + 31) & ~31);
+    const int             qlevels = std::max<int>(1, (int)lib.cmax - 1);
+    std::vector<int>      lp((size_t)bss::win::kLevelWords * lib.cmax);
+    std::vector<uint32_t> ctl((size_t)2 * lib.cmax), Q((size_t)qlevels * qcap), stash((size_t)32 * std::max(1, K));
     for (uint32_t u = 0; u < t->n_units; u++) {
         unit_window[u] = 0;
         if (!narrow || !(lib.unit_flags[u] & bss::kUnitWindow)) continue;
@@ -148,32 +154,29 @@ int window_host_search(const bss_table* t, const char* seq_bytes, uint32_t n_u, 
         if (!every) continue;
         const uint32_t ovl = thin(M, uv, W, n, T);
         summaries(M, uv.C, W, WS, SM);
-        summaries(T, uv.C, W, WS, ST);
-        bss::win::Ctx cx;
-        cx.blob = blob; cx.M = M.data(); cx.T = T.data(); cx.SM = SM.data(); cx.ST = ST.data(); cx.bm = bm.data();
-        cx.ovl = ovl; cx.W = W; cx.WS = WS; cx.n = n; cx.K = K; cx.C = uv.C; cx.delay = uv.delay; cx.band = band; cx.cs = cs;
-        std::fill(cols.begin(), cols.end(), poison);
-        const int per = (Wq + 31) >> 5;
-        uint64_t  lane_sites[32], total = 0;
-        for (int lane = 0; lane < 32; lane++) {
-            cx.pos = cols.data() + lane; cx.bits = cx.pos + lib.cmax * cs; cx.grd = cx.pos + 2 * lib.cmax * cs;
-            const int w0 = std::min(Wq, lane * per), w1 = std::min(Wq, w0 + per);
-            lane_sites[lane] = bss::win::walk_words<false>(cx, w0, w1, blob[0], nullptr);
-            total += lane_sites[lane];
+        bss::win::Walk cx;
+        std::vector<const uint32_t*> rows;
+        for (int c = 0; c < uv.C; c++) {
+            rows.push_back(M.data() + (size_t)c * W);
+            rows.push_back(T.data() + (size_t)c * W);
+            rows.push_back(SM.data() + (size_t)c * WS);
         }
-        const size_t R = (size_t)uv.C + 1, base = out.size();
+        cx.blob = blob; cx.rows = rows.data(); cx.bm = bm.data();
+        cx.lp = lp.data(); cx.ctl = ctl.data(); cx.Q = Q.data(); cx.stash = stash.data(); cx.qcap = qcap;
+        cx.ovl = ovl; cx.W = W; cx.WS = WS; cx.n = n; cx.K = K; cx.C = uv.C; cx.delay = uv.delay; cx.band = band;
+        std::fill(lp.begin(), lp.end(), (int)poison);
+        std::fill(ctl.begin(), ctl.end(), poison);
+        std::fill(Q.begin(), Q.end(), poison);
+        std::fill(stash.begin(), stash.end(), poison);
+        const uint64_t total = bss::win::walk<false>(cx, Wq, blob[0], nullptr);
+        const size_t   R = (size_t)uv.C + 1, base = out.size();
         out.resize(base + total * R, 0xDEADBEEFu);
-        uint64_t before = 0;
-        std::fill(cols.begin(), cols.end(), ~poison);
-        for (int lane = 0; lane < 32; lane++) {
-            cx.pos = cols.data() + lane; cx.bits = cx.pos + lib.cmax * cs; cx.grd = cx.pos + 2 * lib.cmax * cs;
-            const int w0 = std::min(Wq, lane * per), w1 = std::min(Wq, w0 + per);
-            if (lane_sites[lane]) {
-                const uint64_t wrote = bss::win::walk_words<true>(cx, w0, w1, blob[0], out.data() + base + before * R);
-                if (wrote != lane_sites[lane]) return -2;
-            }
-            before += lane_sites[lane];
-        }
+        std::fill(lp.begin(), lp.end(), (int)~poison);
+        std::fill(ctl.begin(), ctl.end(), ~poison);
+        std::fill(Q.begin(), Q.end(), ~poison);
+        std::fill(stash.begin(), stash.end(), ~poison);
+        const uint64_t wrote = bss::win::walk<true>(cx, Wq, blob[0], out.data() + base);
+        if (wrote != total) return -2;
     }
     *n_words = out.size();
     *records = static_cast<uint32_t*>(std::malloc(std::max<size_t>(4, out.size() * 4)));

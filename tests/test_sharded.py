@@ -111,3 +111,18 @@ def test_cost_balanced_ranges_partition_the_library_and_beat_equal_counts():
         costs[s:e].sum() for s, e in (sharded.shard_range(costs.size, 4, r) for r in range(4)))
     assert sharded.shard_ranges_by_cost(np.zeros(0), 3) == [(0, 0), (0, 0), (0, 0)]
     assert sharded.shard_ranges_by_cost(np.zeros(5), 2) == [(0, 2), (2, 5)]
+
+
+def test_c_abi_cut_equals_the_python_cut(tmp_path):
+    """bss_shard_ranges (the cut of the single-process bss_sharded_create) against sharded.shard_ranges_by_cost (the cut of the
+    one-process-per-GPU path): the same contiguous module ranges, for JSON, RIN and DESC (gates) libraries. Host only."""
+    cheap = synth.json_modules(300, 7, "c4a")
+    heavy = synth.json_modules(100, 8, "c4b")
+    libs = [b.HostLibrary.from_json_modules(sorted(cheap + [("z" + k, s, t) for k, s, t in heavy])),
+            b.HostLibrary.load("rinfolder", synth.write_rin_folder(str(tmp_path / "rin"), 150, 3, max_components=5, min_len=1)),
+            b.HostLibrary.load("descfolder", synth.write_desc_folder(str(tmp_path / "desc"), 150, 4))]
+    for host in libs:
+        for n in (230, 2000):
+            costs = sharded.module_costs(host.table(), n)
+            for world in (1, 2, 3, 4, 8):
+                assert host.shard_ranges(world, n) == sharded.shard_ranges_by_cost(costs, world), (host.kind, n, world)

@@ -1,8 +1,8 @@
 """CPU emulation of the window pass against the flat-table interpreter (no GPU).
 
-The per-lane enumerator of window_kernel is host/device source (biorseo_b200/csrc/bss_window_walk.h);
+The warp-cooperative enumerator of window_kernel is host/device source (biorseo_b200/csrc/bss_window_walk.h);
 tests/cpp/window_host.cpp compiles that very source with g++ and drives it like the kernel does (descriptors
-from the product's builder, 32 lanes, count -> prefix -> emit). Here its record stream must equal the
+from the product's builder, the 32 lanes as loops, count walk then emit walk). Here its record stream must equal the
 interpreter's, bit for bit and in order, on the units the window walk is eligible for: JSON / DESC libraries,
 random tables with row checks, overlapping chains, empty components, ends outside their component, narrow and
 wide bands. The kernel around it is covered by the GPU parity tests."""
@@ -187,3 +187,26 @@ def test_empty_mask(harness):
     seq = bytes(rng.choice([65, 67], 80).tolist())
     mask = np.zeros((80, 3), np.uint32)
     check(harness, table, seq, mask, min_window=20)   # band = -1: only units without any check can have sites
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_scratch_is_never_read_before_written_and_small_queues_give_the_same_stream(harness, monkeypatch, seed):
+    """The walk's scratch (level parameters, cursors, queues, stash) is poisoned with two different values and the
+    level queues are shrunk to the smallest legal size, which forces the "queue full: place the next level, come
+    back" path on every dense item; the record stream may not change."""
+    rng = np.random.default_rng(7000 + seed)
+    alphabet = [ord(c) for c in ("AG" if seed % 2 else "ACG")]
+    n = [150, 220, 96][seed % 3]
+    table = tables.window_table(rng, 50, alphabet, max_comp=4, max_len=3)
+    seq = low_complexity(rng, alphabet, n)
+    mask = tables.banded_random_mask(n, seed, [40, 90, 20][seed % 3], [1.0, 0.8][seed % 2])
+    base, flags, _ = window_search(harness, table, seq, mask)
+    assert base.size > 0
+    for poison, qcap in (("0xFFFFFFFF", "0"), ("0x5A5A5A5A", "1"), ("0", "1")):
+        monkeypatch.setenv("WINDOW_HOST_POISON", poison)
+        if qcap != "0":
+            monkeypatch.setenv("WINDOW_HOST_QCAP", qcap)   # (clamped to max(32, band + 1) by the harness)
+        got, flags2, _ = window_search(harness, table, seq, mask)
+        assert np.array_equal(flags, flags2) and np.array_equal(got, base), (poison, qcap)
+    want = expected_of_window_units(table, seq, mask, flags)
+    assert np.array_equal(base, want)
