@@ -15,12 +15,17 @@ std::vector<uint32_t> build_pair_mask(size_t n, const std::function<bool(size_t,
     return mask;
 }
 
-InsertionSiteSearch::~InsertionSiteSearch()
+InsertionSiteSearch::~InsertionSiteSearch() { release(); }
+
+void InsertionSiteSearch::release()
 {
     if (device_library_) bss_library_destroy(device_library_);
+    if (sharded_) bss_sharded_destroy(sharded_);
+    device_library_ = nullptr;
+    sharded_        = nullptr;
 }
 
-bool InsertionSiteSearch::open(const std::string& source, const std::string& source_path, int device, std::string& err)
+bool InsertionSiteSearch::load(const std::string& source, const std::string& source_path, std::string& err)
 {
     LibraryKind kind;
     if (source == "jsonfolder") kind = KIND_JSON;
@@ -29,20 +34,39 @@ bool InsertionSiteSearch::open(const std::string& source, const std::string& sou
     else { err = "Unknown module source."; return false; }
     if (!library_.load(kind, source_path, err)) return false;
     Motif::delay = library_.delay();
-    if (device_library_) { bss_library_destroy(device_library_); device_library_ = nullptr; }
+    release();
+    return true;
+}
+
+bool InsertionSiteSearch::open(const std::string& source, const std::string& source_path, int device, std::string& err)
+{
+    if (!load(source, source_path, err)) return false;
     const bss_table table = library_.table();
     if (bss_library_create(&table, device, &device_library_) != BSS_OK) { err = bss_last_error(); return false; }
+    return true;
+}
+
+bool InsertionSiteSearch::open_sharded(const std::string& source, const std::string& source_path, unsigned n_gpus, unsigned typical_len, std::string& err)
+{
+    if (!load(source, source_path, err)) return false;
+    const bss_table table = library_.table();
+    if (bss_sharded_create(&table, nullptr, n_gpus, typical_len, &sharded_) != BSS_OK) { err = bss_last_error(); return false; }
     return true;
 }
 
 bool InsertionSiteSearch::run(const std::string& seq, const std::vector<uint32_t>& pair_mask, std::vector<Motif>& sites, VariableIndex* index,
                               std::string& err)
 {
-    if (!device_library_) { err = "no library open"; return false; }
+    if (!device_library_ && !sharded_) { err = "no library open"; return false; }
+    if (index && sharded_) { err = "the variable index needs the records on one device: open() the library on one GPU"; return false; }
     const size_t n = seq.size();
     if (pair_mask.size() != n * ((n + 31) / 32)) { err = "pair mask has the wrong size"; return false; }
-    bss_sites* found = nullptr;
-    if (bss_search(device_library_, seq.data(), (uint32_t)n, pair_mask.data(), &found) != BSS_OK) { err = bss_last_error(); return false; }
+    bss_sites*     found         = nullptr;
+    const uint64_t seq_begin[2]  = {0, n};
+    const uint64_t mask_begin[2] = {0, pair_mask.size()};
+    const int      rc = sharded_ ? bss_search_sharded(sharded_, 1, seq.data(), seq_begin, pair_mask.data(), mask_begin, &found)
+                                 : bss_search(device_library_, seq.data(), (uint32_t)n, pair_mask.data(), &found);
+    if (rc != BSS_OK) { err = bss_last_error(); return false; }
     const uint32_t* rec = bss_sites_records(found);
     const uint64_t  end = bss_sites_words(found);
     sites.reserve(sites.size() + bss_sites_count(found));
@@ -77,7 +101,7 @@ bool InsertionSiteSearch::run(const std::string& seq, const std::vector<uint32_t
 bool InsertionSiteSearch::run_batch(const std::vector<std::string>& seqs, const std::vector<std::vector<uint32_t>>& masks,
                                     std::vector<std::vector<Motif>>& sites, std::string& err)
 {
-    if (!device_library_) { err = "no library open"; return false; }
+    if (!device_library_ && !sharded_) { err = "no library open"; return false; }
     if (masks.size() != seqs.size()) { err = "one pair mask per sequence is needed"; return false; }
     std::string           all;
     std::vector<uint32_t> all_masks;
@@ -92,7 +116,9 @@ bool InsertionSiteSearch::run_batch(const std::vector<std::string>& seqs, const 
     }
     all_masks.push_back(0u);   // never read: keeps data() valid for an all-empty batch
     bss_sites* found = nullptr;
-    if (bss_search_batch(device_library_, (uint32_t)seqs.size(), all.c_str(), seq_begin.data(), all_masks.data(), mask_begin.data(), &found) != BSS_OK) {
+    const int rc = sharded_ ? bss_search_sharded(sharded_, (uint32_t)seqs.size(), all.c_str(), seq_begin.data(), all_masks.data(), mask_begin.data(), &found)
+                            : bss_search_batch(device_library_, (uint32_t)seqs.size(), all.c_str(), seq_begin.data(), all_masks.data(), mask_begin.data(), &found);
+    if (rc != BSS_OK) {
         err = bss_last_error();
         return false;
     }

@@ -42,6 +42,12 @@ class InsertionSiteSearch
     // `source` is the reference's "jsonfolder" | "rinfolder" | "descfolder"
     // (cppsrc/biorseo.cpp:150-165). Also sets Motif::delay like the reference's main().
     bool open(const std::string& source, const std::string& source_path, int device, std::string& err);
+    // The same over n_gpus GPUs of this box (devices 0 .. n_gpus - 1) in ONE process: the library is cut into contiguous
+    // module ranges balanced by search cost, one per GPU (bss_sharded_create) — the reference's Pool of one job per module
+    // (cppsrc/MOIP.cpp:246-293) spread over the GPUs. run / run_batch then return the very list the one-GPU search returns.
+    // typical_len: expected query length, for the cost estimate (0: 1000). The variable index (run with `index`) needs
+    // the records on one device and is not available in this mode.
+    bool open_sharded(const std::string& source, const std::string& source_path, unsigned n_gpus, unsigned typical_len, std::string& err);
 
     // Appends every insertion site of the library on `seq` to `sites`, in canonical
     // (module, placement) order. There is no CPU fallback: fails when no GPU is usable.
@@ -76,6 +82,9 @@ class InsertionSiteSearch
   private:
     ModuleLibrary library_;
     bss_library*  device_library_ = nullptr;
+    bss_sharded*  sharded_ = nullptr;     // set instead of device_library_ by open_sharded
+    bool load(const std::string& source, const std::string& source_path, std::string& err);
+    void release();
 };
 
 }   // namespace bsh

@@ -23,6 +23,11 @@
 // (bsh::InsertionSiteSearch::run_batch -> bss_search_batch); the pair mask of each record is the canonical one
 // (AU / GC / GU pairs, 4 <= v - u < 100, u < n - 6). Output lines: record name \t site.
 //
+//   dropin <source> <library path> <seq.txt> <mask.bin> gpus=N        dropin <source> <library path> <file.fa> - batch-gpus=N
+//
+// The same searches with the library cut over N GPUs of the box in this one process
+// (bsh::InsertionSiteSearch::open_sharded -> bss_sharded_create / bss_search_sharded): the output must not change.
+//
 // Exit codes: 0 ok, 3 search failed (e.g. no GPU: there is no CPU fallback), 2 usage / input.
 #include <cstdint>
 #include <cstdio>
@@ -159,7 +164,9 @@ static int run_batch_mode(char** argv)
         masks.push_back(bsh::build_pair_mask(n, canonical));
     }
     bsh::InsertionSiteSearch search;
-    if (!search.open(argv[1], argv[2], -1, err)) {
+    const std::string mode = argv[5];
+    const unsigned    gpus = mode.rfind("batch-gpus=", 0) == 0 ? (unsigned)std::stoul(mode.substr(11)) : 0u;
+    if (!(gpus ? search.open_sharded(argv[1], argv[2], gpus, 120, err) : search.open(argv[1], argv[2], -1, err))) {
         std::cerr << "ERR: " << err << "\n";
         return 3;
     }
@@ -184,8 +191,9 @@ int main(int argc, char** argv)
 {
     const bool with_constraints = argc == 6 && std::string(argv[5]) == "constraints";
     const bool with_index = (argc == 6 && std::string(argv[5]) == "index") || with_constraints;
-    if (argc == 6 && std::string(argv[5]) == "batch") return run_batch_mode(argv);
-    if (argc != 5 && !with_index) {
+    if (argc == 6 && std::string(argv[5]).rfind("batch", 0) == 0) return run_batch_mode(argv);
+    const unsigned gpus = argc == 6 && std::string(argv[5]).rfind("gpus=", 0) == 0 ? (unsigned)std::stoul(std::string(argv[5]).substr(5)) : 0u;
+    if (argc != 5 && !with_index && !gpus) {
         std::cerr << "usage: dropin <source> <library> <seq.txt> <mask.bin>\n";
         return 2;
     }
@@ -223,7 +231,7 @@ int main(int argc, char** argv)
         return 0;
     }
     bsh::InsertionSiteSearch search;
-    if (!search.open(argv[1], argv[2], -1, err)) {
+    if (!(gpus ? search.open_sharded(argv[1], argv[2], gpus, (unsigned)n, err) : search.open(argv[1], argv[2], -1, err))) {
         std::cerr << "ERR: " << err << "\n";
         return 3;
     }

@@ -75,6 +75,27 @@ def test_random_libraries_through_the_cpp_dropin(dropin, source, n, tmp_path):
     assert sorted(line for line in res.stdout.split("\n") if line) == util.best_oracle(source, lib, seq, mask)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("source,n", [("jsonfolder", 640), ("rinfolder", 230), ("descfolder", 150)])
+def test_sharded_dropin_gives_the_same_list(dropin, source, n, tmp_path):
+    """bsh::InsertionSiteSearch::open_sharded (one process, the library cut over the GPUs of the box; one range on a
+    one-GPU box) against the one-GPU drop-in: the same sites in the same order."""
+    import torch
+    gpus = min(torch.cuda.device_count(), 4)
+    seq = synth.sequence(n, 32)
+    mask = synth.mask_canonical(seq, seed=6, keep=0.6)
+    if source == "jsonfolder":
+        lib = synth.write_json(str(tmp_path / "lib.json"), synth.json_modules(300, 10, "c1"))
+    elif source == "rinfolder":
+        lib = synth.write_rin_folder(str(tmp_path / "rin"), 120, 10, max_components=3, min_len=2)
+    else:
+        lib = synth.write_desc_folder(str(tmp_path / "desc"), 120, 10)
+    one = _run(dropin, source, lib, seq, mask, tmp_path)
+    many = _run(dropin, source, lib, seq, mask, tmp_path, f"gpus={gpus}")
+    assert one.returncode == 0 and many.returncode == 0, (one.stderr, many.stderr)
+    assert one.stdout and many.stdout == one.stdout
+
+
 def _csv_lines(rng, n, count):
     lines = ["motif,score,positions"]
     for i in range(count):
