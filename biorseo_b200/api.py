@@ -63,7 +63,7 @@ class HostLibrary:
 
     @classmethod
     def load_compiled(cls, path):
-        """Reads a library written by save_compiled(): no parsing, no validation."""
+        """Maps a library written by save_compiled(): the flat table is used in place, nothing is parsed."""
         lib = capi.load()
         h = C.c_void_p()
         _check(lib.bsh_library_load_compiled(str(path).encode(), C.byref(h)), host=True)
@@ -102,6 +102,11 @@ class HostLibrary:
     @property
     def n_modules(self):
         return self._lib.bsh_library_modules(self._h)
+
+    @property
+    def mapped_bytes(self):
+        """Size of the file mapping the flat table lives in (a library from load_compiled), else 0."""
+        return int(self._lib.bsh_library_mapped_bytes(self._h))
 
     @property
     def n_seen(self):

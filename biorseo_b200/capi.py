@@ -102,6 +102,7 @@ SIGNATURES = {
     "bsh_library_new": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "bsh_library_save_compiled": (C.c_int, [C.c_void_p, C.c_char_p]),
     "bsh_library_load_compiled": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "bsh_library_mapped_bytes": (C.c_uint64, [C.c_void_p]),
     "bsh_library_kind": (C.c_int, [C.c_void_p]),
     "bsh_library_add_json": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]),
     "bsh_library_seal": (C.c_int, [C.c_void_p]),

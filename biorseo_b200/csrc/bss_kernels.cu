@@ -1679,7 +1679,7 @@ cudaError_t launch_window(const DevLibrary& lib, const DevQuery& q, const Plan& 
                           int sm_count, cudaStream_t s)
 {
     // persistent warps: the list lengths are read on the device
-    const uint32_t most   = plan.window_stage ? 2u : 8u;
+    const uint32_t most   = plan.window_stage ? 2u : (uint32_t)BSS_WIN_MIN_CTAS;
     const uint32_t per_sm = plan.smem_bytes_window ? std::min<uint32_t>(most, (200u * 1024u) / plan.smem_bytes_window) : most;
     uint32_t grid = (uint32_t)sm_count * (per_sm ? per_sm : 1u);
     uint32_t smem = plan.smem_bytes_window;

@@ -96,6 +96,8 @@ int bsh_library_load_compiled(const char* path, bsh_library** out)
 
 int bsh_library_kind(const bsh_library* lib) { return lib ? (int)lib->lib.kind() : -1; }
 
+uint64_t bsh_library_mapped_bytes(const bsh_library* lib) { return lib ? (uint64_t)lib->lib.mapped_bytes() : 0; }
+
 int bsh_library_new(int kind, bsh_library** out)
 {
     return host_guarded([&]() -> int {

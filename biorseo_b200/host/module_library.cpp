@@ -8,6 +8,11 @@
 #include <fstream>
 #include <sstream>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "mini_json.h"
 
 namespace bsh {
@@ -119,9 +124,16 @@ bool json_struct_ok(const std::string& ss)
 
 void ModuleLibrary::clear(LibraryKind kind)
 {
-    *this = ModuleLibrary();
-    kind_ = kind;
+    unmap();
+    mapped_table_ = bss_table{};
+    modules_.clear(); rejected_.clear(); units_.clear(); gates_.clear();
+    unit_module_.clear(); unit_delay_.clear(); unit_gate_.clear(); unit_comp_begin_.clear(); comp_pat_begin_.clear(); unit_check_begin_.clear();
+    pattern_.clear(); checks_.clear();
+    n_seen_ = 0;
+    kind_   = kind;
 }
+
+ModuleLibrary::~ModuleLibrary() { unmap(); }
 
 char ModuleLibrary::push_unit(uint32_t module, uint32_t delay, uint32_t gate, const std::vector<std::string>& patterns,
                               const std::vector<LinkSpec>& checks, bool is_gate)
@@ -526,118 +538,212 @@ bool ModuleLibrary::load(LibraryKind kind, const std::string& path, std::string&
 }
 
 // ---- compiled library file -------------------------------------------------------------------
-// "BSHLIB1\0", u32 kind, u64 n_seen, modules, rejected, units, gates. Integers little-endian,
-// strings and vectors length-prefixed (u32). Every count is checked against the file size.
+// Everything load() produces, laid out so that the file can be MAPPED and used in place: a fixed little-endian header,
+// an offset table, then 16-byte aligned sections holding plain arrays. The flat component table the device library is
+// built from (bss_table) is eight of those sections: after load_compiled its pointers point straight into the mapping —
+// nothing is parsed, nothing is copied (the pages are read by the upload itself). Module identifiers, link recipes and
+// the reject log (what turns records back into Motif objects) are sections too and are unpacked into modules_ / rejected_.
+//   header   "BSHLIB2\0", u32 kind, u32 sections, u32 modules, u32 units, u32 gates, u32 0, u64 modules seen, u64 file size
+//   table    sections x { u32 id, u32 bytes per element, u64 byte offset, u64 elements }
+// Every offset, count and index is checked against the file before use; a damaged file is refused, never trusted.
 namespace {
 
-struct Writer {
-    std::string out;
-    void u8(uint8_t v) { out.push_back((char)v); }
-    void u32(uint32_t v) { for (int i = 0; i < 4; i++) out.push_back((char)(v >> (8 * i))); }
-    void u64(uint64_t v) { for (int i = 0; i < 8; i++) out.push_back((char)(v >> (8 * i))); }
-    void i16(int16_t v) { out.push_back((char)(uint8_t)v); out.push_back((char)((uint16_t)v >> 8)); }
-    void str(const std::string& s) { u32((uint32_t)s.size()); out += s; }
-    void link(const LinkSpec& l) { i16(l.a.anchor); i16(l.a.off); i16(l.b.anchor); i16(l.b.off); u8(l.long_range ? 1 : 0); }
-};
+const char kMagic[8] = {'B', 'S', 'H', 'L', 'I', 'B', '2', 0};
 
-struct Reader {
-    const std::string& in;
-    size_t             at = 0;
-    bool               ok = true;
-    explicit Reader(const std::string& s) : in(s) {}
-    bool need(size_t n) { if (!ok || in.size() - at < n) ok = false; return ok; }
-    uint8_t u8() { if (!need(1)) return 0; return (uint8_t)in[at++]; }
-    uint32_t u32() { if (!need(4)) return 0; uint32_t v = 0; for (int i = 0; i < 4; i++) v |= (uint32_t)(uint8_t)in[at++] << (8 * i); return v; }
-    uint64_t u64() { if (!need(8)) return 0; uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)(uint8_t)in[at++] << (8 * i); return v; }
-    int16_t i16() { if (!need(2)) return 0; uint16_t v = (uint8_t)in[at] | ((uint16_t)(uint8_t)in[at + 1] << 8); at += 2; return (int16_t)v; }
-    // a count of items that take at least `each` bytes apiece
-    uint32_t count(size_t each) { const uint32_t n = u32(); if (ok && (uint64_t)n * each > in.size() - at) ok = false; return ok ? n : 0; }
-    std::string str() { const uint32_t n = count(1); std::string s; if (ok) { s.assign(in, at, n); at += n; } return s; }
-    LinkSpec link() { LinkSpec l; l.a.anchor = i16(); l.a.off = i16(); l.b.anchor = i16(); l.b.off = i16(); l.long_range = u8() != 0; return l; }
+enum SectionId : uint32_t {
+    S_UNIT_MODULE = 1, S_UNIT_DELAY, S_UNIT_GATE, S_UNIT_COMP_BEGIN, S_COMP_PAT_BEGIN, S_PATTERN, S_UNIT_CHECK_BEGIN, S_CHECKS,
+    S_MOD_FIRST_UNIT, S_MOD_N_UNITS, S_MOD_SOURCE, S_MOD_K_BEGIN, S_MOD_K, S_MOD_LINK_BEGIN, S_MOD_LINKS, S_MOD_ID_BEGIN, S_MOD_ID,
+    S_REJ_ID_BEGIN, S_REJ_ID, S_REJ_CODE, S_END
 };
+constexpr uint32_t kSections = S_END - 1;
+const uint32_t     kElemSize[kSections] = {4, 4, 4, 4, 4, 1, 4, 2, 4, 4, 4, 4, 4, 4, 2, 4, 1, 4, 1, 1};
 
-const char kMagic[8] = {'B', 'S', 'H', 'L', 'I', 'B', '1', 0};
+struct FileHeader {
+    char     magic[8];
+    uint32_t kind, n_sections, n_modules, n_units, n_gates, reserved;
+    uint64_t n_seen, file_size;
+};
+struct SectionEntry {
+    uint32_t id, elem_size;
+    uint64_t offset, count;
+};
+static_assert(sizeof(FileHeader) == 48 && sizeof(SectionEntry) == 24, "the file layout is fixed");
+
+template <typename T>
+const T* section(const char* base, const SectionEntry* table, SectionId id) { return reinterpret_cast<const T*>(base + table[id - 1].offset); }
+
+// begin[] has n + 1 entries, starts at 0, never decreases and ends at `total`
+bool offsets_ok(const uint32_t* begin, uint64_t entries, uint64_t n, uint64_t total)
+{
+    if (entries != n + 1 || begin[0] != 0 || begin[n] != total) return false;
+    for (uint64_t i = 0; i < n; i++)
+        if (begin[i] > begin[i + 1]) return false;
+    return true;
+}
 
 }   // namespace
 
 bool ModuleLibrary::save_compiled(const std::string& path, std::string& err) const
 {
-    Writer w;
-    w.out.assign(kMagic, kMagic + 8);
-    w.u32((uint32_t)kind_);
-    w.u64(n_seen_);
-    w.u32((uint32_t)modules_.size());
+    if (map_base_) {   // a mapped library is its file
+        std::ofstream f(path, std::ios::binary | std::ios::trunc);
+        if (!f || !f.write(static_cast<const char*>(map_base_), (std::streamsize)map_size_)) { err = "cannot write " + path; return false; }
+        return true;
+    }
+    // the module side as arrays
+    std::vector<uint32_t> first_unit, n_units, source, k_begin(1, 0), k, link_begin(1, 0), id_begin(1, 0), rej_begin(1, 0);
+    std::vector<int16_t>  links;
+    std::vector<uint8_t>  ids, rej_ids, rej_codes;
     for (const ModuleInfo& m : modules_) {
-        w.str(m.id);
-        w.u32((uint32_t)m.source);
-        w.u32((uint32_t)m.k.size());
-        for (uint32_t k : m.k) w.u32(k);
-        w.u32((uint32_t)m.links.size());
-        for (const LinkSpec& l : m.links) w.link(l);
-        w.u32(m.first_unit);
-        w.u32(m.n_units);
-    }
-    w.u32((uint32_t)rejected_.size());
-    for (const Rejected& r : rejected_) { w.str(r.id); w.u8((uint8_t)r.code); }
-    for (const std::vector<Unit>* set : {&units_, &gates_}) {
-        w.u32((uint32_t)set->size());
-        for (const Unit& u : *set) {
-            w.u32(u.module); w.u32(u.delay); w.u32(u.gate);
-            w.u32((uint32_t)u.patterns.size());
-            for (const std::string& p : u.patterns) w.str(p);
-            w.u32((uint32_t)u.checks.size());
-            for (const LinkSpec& c : u.checks) w.link(c);
+        first_unit.push_back(m.first_unit);
+        n_units.push_back(m.n_units);
+        source.push_back((uint32_t)m.source);
+        k.insert(k.end(), m.k.begin(), m.k.end());
+        k_begin.push_back((uint32_t)k.size());
+        for (const LinkSpec& l : m.links) {
+            const int16_t packed[5] = {l.a.anchor, l.a.off, l.b.anchor, l.b.off, (int16_t)(l.long_range ? 1 : 0)};
+            links.insert(links.end(), packed, packed + 5);
         }
+        link_begin.push_back((uint32_t)(links.size() / 5));
+        ids.insert(ids.end(), m.id.begin(), m.id.end());
+        id_begin.push_back((uint32_t)ids.size());
     }
+    for (const Rejected& r : rejected_) {
+        rej_ids.insert(rej_ids.end(), r.id.begin(), r.id.end());
+        rej_begin.push_back((uint32_t)rej_ids.size());
+        rej_codes.push_back((uint8_t)r.code);
+    }
+    const bss_table t = table();
+    const uint32_t  n_all = t.n_units + t.n_gates, n_comps = unit_comp_begin_.back(), n_checks = unit_check_begin_.back();
+    struct Piece { const void* data; uint64_t count; };
+    const Piece pieces[kSections] = {
+        {t.unit_module, n_all}, {t.unit_delay, n_all}, {t.unit_gate, t.n_units}, {t.unit_comp_begin, (uint64_t)n_all + 1}, {t.comp_pat_begin, (uint64_t)n_comps + 1},
+        {t.pattern, pattern_.size()}, {t.unit_check_begin, (uint64_t)n_all + 1}, {t.checks, 4ull * n_checks},
+        {first_unit.data(), first_unit.size()}, {n_units.data(), n_units.size()}, {source.data(), source.size()}, {k_begin.data(), k_begin.size()}, {k.data(), k.size()},
+        {link_begin.data(), link_begin.size()}, {links.data(), links.size()}, {id_begin.data(), id_begin.size()}, {ids.data(), ids.size()},
+        {rej_begin.data(), rej_begin.size()}, {rej_ids.data(), rej_ids.size()}, {rej_codes.data(), rej_codes.size()}};
+    FileHeader   h{};
+    SectionEntry entries[kSections];
+    std::memcpy(h.magic, kMagic, 8);
+    h.kind = (uint32_t)kind_; h.n_sections = kSections; h.n_modules = t.n_modules; h.n_units = t.n_units; h.n_gates = t.n_gates; h.n_seen = n_seen_;
+    uint64_t at = (sizeof h + sizeof entries + 15) & ~15ull;
+    for (uint32_t i = 0; i < kSections; i++) {
+        entries[i] = {i + 1, kElemSize[i], at, pieces[i].count};
+        at         = (at + pieces[i].count * kElemSize[i] + 15) & ~15ull;
+    }
+    h.file_size = at;
+    std::string out((size_t)at, '\0');
+    std::memcpy(&out[0], &h, sizeof h);
+    std::memcpy(&out[sizeof h], entries, sizeof entries);
+    for (uint32_t i = 0; i < kSections; i++)
+        if (pieces[i].count) std::memcpy(&out[(size_t)entries[i].offset], pieces[i].data, (size_t)(pieces[i].count * kElemSize[i]));
     std::ofstream f(path, std::ios::binary | std::ios::trunc);
-    if (!f || !f.write(w.out.data(), (std::streamsize)w.out.size())) { err = "cannot write " + path; return false; }
+    if (!f || !f.write(out.data(), (std::streamsize)out.size())) { err = "cannot write " + path; return false; }
     return true;
+}
+
+void ModuleLibrary::unmap()
+{
+    if (map_base_) munmap(map_base_, map_size_);
+    map_base_ = nullptr;
+    map_size_ = 0;
 }
 
 bool ModuleLibrary::load_compiled(const std::string& path, std::string& err)
 {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) { err = "cannot open " + path; return false; }
-    std::stringstream ss;
-    ss << f.rdbuf();
-    const std::string bytes = ss.str();
-    if (bytes.size() < 8 || std::memcmp(bytes.data(), kMagic, 8) != 0) { err = path + " is not a compiled module library"; return false; }
-    Reader r(bytes);
-    r.at = 8;
-    const uint32_t kind = r.u32();
-    if (!r.ok || kind > 2) { err = path + ": bad header"; return false; }
-    clear((LibraryKind)kind);
-    n_seen_ = (size_t)r.u64();
-    const uint32_t n_modules = r.count(24);
-    modules_.resize(n_modules);
-    for (ModuleInfo& m : modules_) {
-        m.id     = r.str();
-        m.source = (source_type)r.u32();
-        m.k.resize(r.count(4));
-        for (uint32_t& k : m.k) k = r.u32();
-        m.links.resize(r.count(9));
-        for (LinkSpec& l : m.links) l = r.link();
-        m.first_unit = r.u32();
-        m.n_units    = r.u32();
+    clear(KIND_JSON);
+    const int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+    if (fd < 0) { err = "cannot open " + path; return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < (off_t)(sizeof(FileHeader) + kSections * sizeof(SectionEntry))) {
+        ::close(fd);
+        err = path + " is not a compiled module library";
+        return false;
     }
-    rejected_.resize(r.count(5));
-    for (Rejected& x : rejected_) { x.id = r.str(); x.code = (char)r.u8(); }
-    for (std::vector<Unit>* set : {&units_, &gates_}) {
-        set->resize(r.count(20));
-        for (Unit& u : *set) {
-            u.module = r.u32(); u.delay = r.u32(); u.gate = r.u32();
-            u.patterns.resize(r.count(4));
-            for (std::string& p : u.patterns) p = r.str();
-            u.checks.resize(r.count(9));
-            for (LinkSpec& c : u.checks) c = r.link();
+    void* base = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);   // (the mapping keeps the file)
+    if (base == MAP_FAILED) { err = "cannot map " + path; return false; }
+    map_base_ = base;
+    map_size_ = (size_t)st.st_size;
+    auto refuse = [&](const std::string& why) { clear(KIND_JSON); err = path + ": " + why; return false; };
+    const char*       bytes = static_cast<const char*>(base);
+    const FileHeader& h     = *reinterpret_cast<const FileHeader*>(bytes);
+    if (std::memcmp(h.magic, kMagic, 8) != 0) return refuse("not a compiled module library");
+    if (h.kind > 2 || h.n_sections != kSections || h.file_size != map_size_) return refuse("truncated or corrupt compiled library");
+    const SectionEntry* e = reinterpret_cast<const SectionEntry*>(bytes + sizeof(FileHeader));
+    uint64_t            floor = sizeof(FileHeader) + kSections * sizeof(SectionEntry);
+    for (uint32_t i = 0; i < kSections; i++) {
+        if (e[i].id != i + 1 || e[i].elem_size != kElemSize[i] || (e[i].offset & 15) || e[i].offset < floor || e[i].offset > map_size_ ||
+            e[i].count > (map_size_ - e[i].offset) / kElemSize[i])
+            return refuse("truncated or corrupt compiled library");
+        floor = e[i].offset + e[i].count * kElemSize[i];
+    }
+    // the flat table, in place
+    const uint64_t  n_all = (uint64_t)h.n_units + h.n_gates;
+    const uint32_t *ucb = section<uint32_t>(bytes, e, S_UNIT_COMP_BEGIN), *cpb = section<uint32_t>(bytes, e, S_COMP_PAT_BEGIN),
+                   *uck = section<uint32_t>(bytes, e, S_UNIT_CHECK_BEGIN), *umod = section<uint32_t>(bytes, e, S_UNIT_MODULE),
+                   *ugate = section<uint32_t>(bytes, e, S_UNIT_GATE);
+    bool sane = e[S_UNIT_MODULE - 1].count == n_all && e[S_UNIT_DELAY - 1].count == n_all && e[S_UNIT_GATE - 1].count == h.n_units &&
+                e[S_UNIT_COMP_BEGIN - 1].count == n_all + 1 && e[S_UNIT_CHECK_BEGIN - 1].count == n_all + 1 && e[S_COMP_PAT_BEGIN - 1].count >= 1;
+    sane = sane && offsets_ok(ucb, e[S_UNIT_COMP_BEGIN - 1].count, n_all, e[S_COMP_PAT_BEGIN - 1].count - 1);
+    sane = sane && offsets_ok(cpb, e[S_COMP_PAT_BEGIN - 1].count, e[S_COMP_PAT_BEGIN - 1].count - 1, e[S_PATTERN - 1].count);
+    sane = sane && offsets_ok(uck, e[S_UNIT_CHECK_BEGIN - 1].count, n_all, e[S_CHECKS - 1].count / 4) && e[S_CHECKS - 1].count % 4 == 0;
+    for (uint64_t u = 0; sane && u < n_all; u++) sane = umod[u] < h.n_modules && ucb[u + 1] > ucb[u];
+    for (uint64_t u = 0; sane && u < h.n_units; u++) sane = ugate[u] == NO_GATE || (ugate[u] >= h.n_units && ugate[u] < n_all);
+    // the module side
+    const uint32_t *first_unit = section<uint32_t>(bytes, e, S_MOD_FIRST_UNIT), *n_units = section<uint32_t>(bytes, e, S_MOD_N_UNITS),
+                   *source = section<uint32_t>(bytes, e, S_MOD_SOURCE), *k_begin = section<uint32_t>(bytes, e, S_MOD_K_BEGIN),
+                   *k = section<uint32_t>(bytes, e, S_MOD_K), *link_begin = section<uint32_t>(bytes, e, S_MOD_LINK_BEGIN),
+                   *id_begin = section<uint32_t>(bytes, e, S_MOD_ID_BEGIN), *rej_begin = section<uint32_t>(bytes, e, S_REJ_ID_BEGIN);
+    const int16_t* links = section<int16_t>(bytes, e, S_MOD_LINKS);
+    const uint64_t n_rej = e[S_REJ_CODE - 1].count;
+    sane = sane && e[S_MOD_FIRST_UNIT - 1].count == h.n_modules && e[S_MOD_N_UNITS - 1].count == h.n_modules && e[S_MOD_SOURCE - 1].count == h.n_modules &&
+           e[S_MOD_LINKS - 1].count % 5 == 0;
+    sane = sane && offsets_ok(k_begin, e[S_MOD_K_BEGIN - 1].count, h.n_modules, e[S_MOD_K - 1].count);
+    sane = sane && offsets_ok(link_begin, e[S_MOD_LINK_BEGIN - 1].count, h.n_modules, e[S_MOD_LINKS - 1].count / 5);
+    sane = sane && offsets_ok(id_begin, e[S_MOD_ID_BEGIN - 1].count, h.n_modules, e[S_MOD_ID - 1].count);
+    sane = sane && offsets_ok(rej_begin, e[S_REJ_ID_BEGIN - 1].count, n_rej, e[S_REJ_ID - 1].count);
+    for (uint32_t m = 0; sane && m < h.n_modules; m++) {
+        const uint32_t C = k_begin[m + 1] - k_begin[m];
+        sane = C >= 1 && (uint64_t)first_unit[m] + n_units[m] <= h.n_units;
+        // every unit of the module places C components (rebuild() reads p[0 .. C-1] of its records), every link end names one of them
+        for (uint32_t u = first_unit[m]; sane && u < first_unit[m] + n_units[m]; u++) sane = umod[u] == m && ucb[u + 1] - ucb[u] == C;
+        for (uint32_t l = link_begin[m]; sane && l < link_begin[m + 1]; l++)
+            sane = links[5 * l] >= -1 && links[5 * l] < (int)C && links[5 * l + 2] >= -1 && links[5 * l + 2] < (int)C;
+    }
+    if (!sane) return refuse("truncated or corrupt compiled library");
+    kind_   = (LibraryKind)h.kind;
+    n_seen_ = (size_t)h.n_seen;
+    modules_.resize(h.n_modules);
+    const char* ids = section<char>(bytes, e, S_MOD_ID);
+    for (uint32_t m = 0; m < h.n_modules; m++) {
+        ModuleInfo& info = modules_[m];
+        info.id.assign(ids + id_begin[m], ids + id_begin[m + 1]);
+        info.source = (source_type)source[m];
+        info.k.assign(k + k_begin[m], k + k_begin[m + 1]);
+        info.links.resize(link_begin[m + 1] - link_begin[m]);
+        for (size_t l = 0; l < info.links.size(); l++) {
+            const int16_t* p = links + 5 * (link_begin[m] + l);
+            info.links[l]    = LinkSpec{{p[0], p[1]}, {p[2], p[3]}, p[4] != 0};
         }
+        info.first_unit = first_unit[m];
+        info.n_units    = n_units[m];
     }
-    bool sane = r.ok && r.at == bytes.size();
-    for (const Unit& u : units_) sane = sane && u.module < modules_.size() && (u.gate == NO_GATE || u.gate < gates_.size()) && !u.patterns.empty();
-    for (const Unit& u : gates_) sane = sane && u.module < modules_.size() && !u.patterns.empty();
-    for (const ModuleInfo& m : modules_) sane = sane && (uint64_t)m.first_unit + m.n_units <= units_.size() && !m.k.empty();
-    if (!sane) { clear((LibraryKind)kind); err = path + ": truncated or corrupt compiled library"; return false; }
-    finish();
+    const char*    rej_ids   = section<char>(bytes, e, S_REJ_ID);
+    const uint8_t* rej_codes = section<uint8_t>(bytes, e, S_REJ_CODE);
+    rejected_.resize(n_rej);
+    for (uint64_t i = 0; i < n_rej; i++) rejected_[i] = Rejected{std::string(rej_ids + rej_begin[i], rej_ids + rej_begin[i + 1]), (char)rej_codes[i]};
+    mapped_table_.n_modules        = h.n_modules;
+    mapped_table_.n_units          = h.n_units;
+    mapped_table_.n_gates          = h.n_gates;
+    mapped_table_.unit_module      = umod;
+    mapped_table_.unit_delay       = section<uint32_t>(bytes, e, S_UNIT_DELAY);
+    mapped_table_.unit_gate        = ugate;
+    mapped_table_.unit_comp_begin  = ucb;
+    mapped_table_.comp_pat_begin   = cpb;
+    mapped_table_.pattern          = section<uint8_t>(bytes, e, S_PATTERN);
+    mapped_table_.unit_check_begin = uck;
+    mapped_table_.checks           = section<int16_t>(bytes, e, S_CHECKS);
     return true;
 }
 
@@ -666,6 +772,7 @@ void ModuleLibrary::finish()
 
 bss_table ModuleLibrary::table() const
 {
+    if (map_base_) return mapped_table_;   // the arrays of the mapped file, in place
     bss_table t;
     t.n_modules        = (uint32_t)modules_.size();
     t.n_units          = (uint32_t)units_.size();

@@ -51,6 +51,11 @@ struct Rejected {
 class ModuleLibrary
 {
   public:
+    ModuleLibrary() {}
+    ~ModuleLibrary();
+    ModuleLibrary(const ModuleLibrary&) = delete;              // (may own a file mapping)
+    ModuleLibrary& operator=(const ModuleLibrary&) = delete;
+
     // Loads `path` (a .json file, or a folder of RIN / .desc files). Returns false with
     // `err` set when the library itself cannot be read; bad modules are only rejected.
     bool load(LibraryKind kind, const std::string& path, std::string& err);
@@ -69,12 +74,16 @@ class ModuleLibrary
     // Record [module, p_0 .. p_{C-1}] -> the Motif the reference would have pushed.
     Motif rebuild(const uint32_t* record) const;
 
-    // Compiled form: everything load() produces (accepted modules with their link recipes, the
-    // searchable units, the reject log), in one little-endian binary file. Loading it replaces the
-    // per-run JSON parse / directory walk / per-module validation of cppsrc/MOIP.cpp:159-188,
-    // 211-234, 259-288 by one sequential read.
+    // Compiled form: everything load() produces (accepted modules with their link recipes, the flat
+    // table of searchable units, the reject log), in one little-endian binary file of plain aligned
+    // arrays. load_compiled MAPS it: table() then points into the mapping (no parse, no copy); only the
+    // module identifiers and link recipes are unpacked. It replaces the per-run JSON parse / directory
+    // walk / per-module validation of cppsrc/MOIP.cpp:159-188, 211-234, 259-288, and the RIN re-read
+    // of every placement (cppsrc/Motif.cpp:115-151).
     bool save_compiled(const std::string& path, std::string& err) const;
     bool load_compiled(const std::string& path, std::string& err);
+    // Size of the file mapping behind table() (0: the table lives in this object's own arrays).
+    size_t mapped_bytes() const { return map_size_; }
 
     // Direct construction (synthetic libraries in benchmarks and tests).
     void clear(LibraryKind kind);
@@ -91,6 +100,12 @@ class ModuleLibrary
     char push_unit(uint32_t module, uint32_t delay, uint32_t gate, const std::vector<std::string>& patterns,
                    const std::vector<LinkSpec>& checks, bool is_gate);
     void finish();
+    void unmap();
+
+    // a compiled library mapped from disk: the flat arrays live in the mapping
+    void*     map_base_ = nullptr;
+    size_t    map_size_ = 0;
+    bss_table mapped_table_{};
 
     LibraryKind             kind_ = KIND_JSON;
     std::vector<ModuleInfo> modules_;

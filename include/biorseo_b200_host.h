@@ -24,11 +24,14 @@ typedef struct bsh_library bsh_library;
 
 /* Parse + validate a library from disk. 0 on success. */
 int  bsh_library_load(int kind, const char* path, bsh_library** out);
-/* Compiled form of a loaded library (one binary file: accepted modules with their link recipes,
- * searchable units, reject log). Loading it replaces the per-run JSON parse / directory walk /
- * validation of cppsrc/MOIP.cpp:159-188, 211-234, 259-288 by one sequential read. */
+/* Compiled form of a loaded library: one binary file of plain aligned arrays (fixed little-endian header, offset
+ * table, sections). bsh_library_load_compiled MAPS the file (mmap): the flat table bsh_library_table returns then
+ * points straight into the mapping — no parse, no copy; only module identifiers, link recipes and the reject log
+ * are unpacked. Replaces the per-run JSON parse / directory walk / validation of cppsrc/MOIP.cpp:159-188, 211-234,
+ * 259-288 and the per-placement RIN re-read of cppsrc/Motif.cpp:115-151. Damaged files are refused. */
 int  bsh_library_save_compiled(const bsh_library* lib, const char* path);
 int  bsh_library_load_compiled(const char* path, bsh_library** out);
+uint64_t bsh_library_mapped_bytes(const bsh_library* lib);                  /* size of the mapping behind the table, 0 if none */
 int  bsh_library_kind(const bsh_library* lib);                              /* BSH_KIND_* */
 /* Build a JSON-style library in memory (synthetic benchmarks): new, add..., seal. */
 int  bsh_library_new(int kind, bsh_library** out);
