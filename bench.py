@@ -407,17 +407,25 @@ def main():
         # Library shards of one box hold similar numbers of sites: the search writes header + records
         # straight into this rank's block of a padded single-collective exchange. Very large streams
         # take the exact-size point-to-point all-gather-v instead (no padding, no final cut).
-        padded = world > 1 and with_collective and n_words <= (4 << 20)
-        gatherer = sharded.PaddedGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=int(1.25 * n_words) + 1024) if padded else None
+        # (capacity: the largest shard stream of the job with 25 % head-room; the peer-memory exchange holds 2 x world x capacity words)
+        cap_words = int(1.25 * n_words) + 1024
+        if world > 1:
+            t = torch.tensor([cap_words], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cap_words = int(t.item())
+        padded = world > 1 and with_collective and 8 * world * cap_words <= (48 << 30)
+        use_peer = padded and os.environ.get("BSS_EXCHANGE", "p2p") == "p2p"
+        gatherer = sharded.PaddedGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=cap_words) if padded and not use_peer else None
         # The exchange of choice: ONE kernel over NVLink peer memory (counts, records and completion flags as peer-to-peer
         # stores); the padded NCCL all-gather + cut kernel when peer mapping is unavailable (BSS_EXCHANGE=nccl forces it).
         peer = None
-        if padded and os.environ.get("BSS_EXCHANGE", "p2p") == "p2p":
+        if use_peer:
             try:
-                peer = sharded.PeerGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=int(1.25 * n_words) + 1024)
+                peer = sharded.PeerGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=cap_words)
             except RuntimeError as exc:
                 if rank == 0:
                     sys.stderr.write(f"bench: {exc}; using the NCCL all-gather\n")
+                gatherer = sharded.PaddedGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=cap_words)
         exchange_name["value"] = "peer-memory kernel (bss_exchange)" if peer is not None else "NCCL all_gather_into_tensor + cut kernel" if padded else "NCCL grouped send/recv"
 
         gathered = []
@@ -473,6 +481,7 @@ def main():
                     sys.stderr.write("bench: the peer-memory exchange failed its warm-up check; using the NCCL all-gather\n")
                 peer.close()
                 peer = None
+                gatherer = sharded.PaddedGatherer(torch.device("cuda", local_rank), n_seqs=len(w["seqs"]), capacity_words=cap_words)
                 exchange_name["value"] = "NCCL all_gather_into_tensor + cut kernel (peer-memory exchange failed its check)"
                 gathered.clear()
                 for _ in range(warmup):
@@ -491,21 +500,28 @@ def main():
         # (the flush in between is outside them).
         events = []
         breakdown.clear()
+        host_t0 = time.perf_counter()
         for _ in range(steps):
+            ef = torch.cuda.Event(enable_timing=True)
+            ef.record(stream)
             flush.fill_(1)                      # evict the previous step's lines from L2
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             step()
             e1.record(stream)
-            events.append((e0, breakdown[-1], e1))
+            events.append((e0, breakdown[-1], e1, ef))
+        host_enqueue_ms = 1e3 * (time.perf_counter() - host_t0) / steps     # host time to queue one step (the device runs behind)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         wall = time.perf_counter() - wall0
         st = finish()                           # sizes of the last search checked (every step runs the same search)
-        step_ms = [a.elapsed_time(z) for a, _, z in events]
-        search_ms = float(np.mean([a.elapsed_time(m) for a, m, _ in events]))      # this rank's search, device time
-        exchange_ms = float(np.mean([m.elapsed_time(z) for _, m, z in events]))    # exchange kernel, waiting for the slowest peer included
+        step_ms = [a.elapsed_time(z) for a, _, z, _ in events]
+        search_ms = float(np.mean([a.elapsed_time(m) for a, m, _, _ in events]))      # this rank's search, device time
+        exchange_ms = float(np.mean([m.elapsed_time(z) for _, m, z, _ in events]))    # exchange kernel, waiting for the slowest peer included
+        flush_ms = float(np.mean([f.elapsed_time(a) for a, _, _, f in events]))       # the L2 flush between steps (outside the step's events)
+        # device time from the end of a step to the start of the next one's flush: > 0 means the device waited for the host to queue work
+        idle_ms = float(np.mean([events[i][2].elapsed_time(events[i + 1][3]) for i in range(len(events) - 1)])) if len(events) > 1 else 0.0
         launches = steps * st["kernel_launches"]
         # per-kernel device times (the library's own events belong to the last search queued): a few more steps, one at a time, untimed
         for _ in range(3):
@@ -547,16 +563,36 @@ def main():
             total_ms = float(t.item())
             # per-rank breakdown: units, sites, search time, exchange time (its wait for the slowest peer included), and the
             # skew = how much earlier than the slowest rank this rank's search ended
-            mine = torch.tensor([int(table["n_units"]), n_sites, n_words, search_ms, exchange_ms, float(sum(step_ms)) / steps], dtype=torch.float64, device="cuda")
+            mine = torch.tensor([int(table["n_units"]), n_sites, n_words, search_ms, exchange_ms, float(sum(step_ms)) / steps, flush_ms, idle_ms, host_enqueue_ms],
+                                dtype=torch.float64, device="cuda")
             every = torch.empty(world * mine.numel(), dtype=torch.float64, device="cuda")
             dist.all_gather_into_tensor(every, mine)
             rows = every.view(world, -1).tolist()
             slowest = max(r[3] for r in rows)
+            words_all = sum(r[2] for r in rows)
             per_rank = [{"rank": i, "units": int(r[0]), "sites": int(r[1]), "words": int(r[2]), "search_ms": r[3], "exchange_ms": r[4],
-                         "skew_ms": slowest - r[3], "step_ms": r[5]} for i, r in enumerate(rows)]
+                         "skew_ms": slowest - r[3], "step_ms": r[5], "flush_ms": r[6], "device_idle_between_steps_ms": r[7], "host_enqueue_ms": r[8],
+                         # what the rank receives over the links in one exchange / its exchange time (the wait for the slowest peer included)
+                         "exchange_in_gbs": 4.0 * (words_all - r[2]) / (r[4] * 1e-3) / 1e9 if r[4] > 0 else None} for i, r in enumerate(rows)]
             sites_all = int(sum(r[1] for r in rows))
         job_tested = tested_total if strong else world * tested_per_step
-        res = {"workload": w, "table": table, "value": job_tested * steps / (total_ms * 1e-3), "scaling": "strong" if strong else "weak",
+        link = None
+        if world > 1 and with_collective and 4 * (words_all if per_rank else 0) >= (64 << 20):
+            # the box's own peer-copy rate, measured here: every rank sends 256 MiB to its right neighbour and receives from its left one (NCCL)
+            buf_out, buf_in = torch.empty(64 << 20, dtype=torch.int32, device="cuda"), torch.empty(64 << 20, dtype=torch.int32, device="cuda")
+            ms = []
+            for i in range(4):
+                a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, buf_out, (rank + 1) % world), dist.P2POp(dist.irecv, buf_in, (rank - 1) % world)]):
+                    req.wait()
+                z.record(stream)
+                torch.cuda.synchronize()
+                if i:
+                    ms.append(a.elapsed_time(z))
+            link = {"measured_peer_copy_gbs_per_direction": (256 << 20) / (min(ms) * 1e-3) / 1e9, "how": "NCCL send/recv ring of 256 MiB per rank, best of 3"}
+            del buf_out, buf_in
+        res = {"workload": w, "table": table, "value": job_tested * steps / (total_ms * 1e-3), "scaling": "strong" if strong else "weak", "link": link,
                "ms_per_step": total_ms / steps, "sites": n_sites, "words": n_words, "launches": launches, "clocks": clocks,
                "kernel_ms": {k: float(np.mean(v)) for k, v in kernel_ms.items()}, "wall_s": wall, "tested_per_step": tested_per_step,
                "sites_per_s": sites_all * steps / (total_ms * 1e-3), "seq_lens": seq_lens, "per_rank": per_rank, "units_total": units_total,
@@ -667,7 +703,7 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": config_of(w, units_total),
             "exchange": exchange_name["value"] if world > 1 else None, "parity": parity,
-            "per_rank": main_res["per_rank"], "limiter": main_res["limiter"], "routing": main_res["stats"],
+            "per_rank": main_res["per_rank"], "limiter": main_res["limiter"], "link": main_res.get("link"), "routing": main_res["stats"],
             "weak_scaling": None if weak_res is None else {"value": weak_res["value"], "ms_per_step": weak_res["ms_per_step"], "units_per_gpu": weak_res["units_total"],
                                                            "sites_per_s": weak_res["sites_per_s"], "per_rank": weak_res["per_rank"], "limiter": weak_res["limiter"]},
             "sites_per_s": main_res["sites_per_s"], "sites_per_step_per_gpu": main_res["sites"],

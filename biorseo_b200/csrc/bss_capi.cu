@@ -687,13 +687,11 @@ cudaError_t record_event(bss_library* lib, int i, bool capturing)
 int enqueue_count(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, bool ordinary, bool capturing = false)
 {
     cudaStream_t st = lib->stream;
-    BSS_CUDA(cudaMemsetAsync(work.totals, 0, 8 * bss::kTotalsWords, st));
-    BSS_CUDA(cudaMemsetAsync(work.chunk_sites, 0, 16 * (size_t)(plan.n_chunks + 1), st));
-    BSS_CUDA(cudaMemsetAsync(work.seq_word_begin, 0, 8 * (size_t)(q->dev.n_seqs + 1), st));
+    BSS_CUDA(bss::launch_reset(plan, work, q->dev.n_seqs, st));
     BSS_CUDA(record_event(lib, 0, capturing));
     BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, ordinary, lib->sm_count, st));
     BSS_CUDA(record_event(lib, 1, capturing));
-    BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));
+    if (!bss::scan_is_fused(plan)) BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));   // (else the window count pass has done it)
     BSS_CUDA(record_event(lib, 2, capturing));
     return BSS_OK;
 }
@@ -704,8 +702,8 @@ constexpr size_t kTotalsFetch = 64;   // bytes of the totals the host reads: [0]
 // kernels of the count side of a search: route / prefilter, ordinary count, heavy count, window count, scan
 uint32_t count_launches(const bss_library* lib, const bss_query* q, const bss::Plan& plan, bool ordinary)
 {
-    if (!plan.n_chunks) return 1u;   // the scan alone
-    uint32_t n = 1u;
+    if (!plan.n_chunks) return 2u;   // reset + the scan alone
+    uint32_t n = bss::scan_is_fused(plan) ? 1u : 2u;   // reset, scan
     if (plan.window || (lib->dev.unit_probe && q->dev.kmers)) n++;
     if (ordinary) n += 1u + (plan.group == 32 && plan.list_cap ? 1u : 0u);
     if (plan.window) n++;

@@ -155,6 +155,11 @@ cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, 
 // `ordinary`: the ordinary count passes are needed (some item may not take the window walk)
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, bool ordinary, int sm_count, cudaStream_t s);
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s);
+// totals, chunk totals and per-sequence offsets zeroed by one kernel
+cudaError_t launch_reset(const Plan& plan, const Work& work, uint32_t n_seqs, cudaStream_t s);
+// (measured: the scan run by the last CTA of the window count pass — 128 threads, serial tail — costs more than the launch
+//  it saves: c4 count + scan 0.127 -> 0.141 ms; it stays a kernel of its own)
+inline bool scan_is_fused(const Plan&) { return false; }
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
                         uint32_t n_alive, uint32_t n_heavy, uint64_t capacity_words, bool ordinary, int sm_count, cudaStream_t s);
 // Exact number of placements the reference's enumerator materialises before its filters (cppsrc/Motif.cpp:466-474),

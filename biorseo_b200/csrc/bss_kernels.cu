@@ -1040,6 +1040,68 @@ __device__ __forceinline__ SeqCtx load_seq(const DevLibrary& lib, const DevQuery
     return sq;
 }
 
+// Block-wide exclusive prefix of one u64 per thread (any whole number of warps up to 32); `total` = block sum.
+__device__ __forceinline__ uint64_t block_exclusive(uint64_t v, uint64_t* warp_sums, uint64_t& total)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    uint64_t       wt;
+    const uint64_t in_warp = Group<32>::exclusive(v, wt);
+    __syncthreads();   // warp_sums may still be read from the previous call
+    if (lane == 31) warp_sums[warp] = wt;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t       all;
+        const uint64_t ex = Group<32>::exclusive(lane < n_warps ? warp_sums[lane] : 0ull, all);
+        warp_sums[lane]   = ex;
+        if (lane == 0) warp_sums[32] = all;
+    }
+    __syncthreads();
+    total = warp_sums[32];
+    return warp_sums[warp] + in_warp;
+}
+
+// Exclusive prefix of the per-chunk word counts, totals, and per-sequence word offsets: one CTA. The chunk totals were
+// accumulated with atomics by other SMs: they are read past L1.
+__device__ __forceinline__ void scan_chunks(const Plan& plan, const Work& work, uint32_t n_seqs, uint64_t* warp_sums)
+{
+    uint64_t carry_words = 0, carry_sites = 0;   // identical in every thread
+    for (uint32_t base = 0; base < plan.n_chunks; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t w = i < plan.n_chunks ? __ldcg(work.chunk_words + i) : 0;
+        const uint64_t s = i < plan.n_chunks ? __ldcg(work.chunk_sites + i) : 0;
+        uint64_t       tw, ts;
+        const uint64_t ew = block_exclusive(w, warp_sums, tw);
+        block_exclusive(s, warp_sums, ts);
+        if (i < plan.n_chunks) {
+            work.chunk_words[i] = carry_words + ew;
+            if (i % plan.chunks_per_seq == 0) work.seq_word_begin[i / plan.chunks_per_seq] = carry_words + ew;
+        }
+        carry_words += tw;
+        carry_sites += ts;
+    }
+    if (threadIdx.x == 0) {
+        work.chunk_words[plan.n_chunks] = carry_words;
+        work.seq_word_begin[n_seqs]     = carry_words;
+        work.totals[0]                  = carry_words;
+        work.totals[1]                  = carry_sites;
+    }
+}
+
+__global__ void __launch_bounds__(1024) scan_kernel(const Plan plan, const Work work, uint32_t n_seqs)
+{
+    __shared__ uint64_t warp_sums[33];
+    scan_chunks(plan, work, n_seqs, warp_sums);
+}
+
+// One kernel instead of three memsets at the head of a search: totals, chunk totals, per-sequence offsets.
+__global__ void __launch_bounds__(256) reset_kernel(const Work work, uint32_t n_chunks, uint32_t n_seqs)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (i < kTotalsWords) work.totals[i] = 0;
+    for (uint32_t j = i; j < 2 * (n_chunks + 1); j += stride) work.chunk_sites[j] = 0;   // (chunk_words follows chunk_sites)
+    for (uint32_t j = i; j <= n_seqs; j += stride) work.seq_word_begin[j] = 0;
+}
+
 #include "bss_window.cuh"
 
 // Count pass (EMIT = false): one CTA per chunk = (sequence, contiguous unit range); the groups
@@ -1376,53 +1438,6 @@ __global__ void __launch_bounds__(kThreads, BSS_MIN_CTAS) search_kernel(const De
     }
 }
 
-// Block-wide exclusive prefix of one u64 per thread (1024 threads); `total` = block sum.
-__device__ __forceinline__ uint64_t block_exclusive(uint64_t v, uint64_t* warp_sums, uint64_t& total)
-{
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t       wt;
-    const uint64_t in_warp = Group<32>::exclusive(v, wt);
-    __syncthreads();   // warp_sums may still be read from the previous call
-    if (lane == 31) warp_sums[warp] = wt;
-    __syncthreads();
-    if (warp == 0) {
-        uint64_t       all;
-        const uint64_t ex = Group<32>::exclusive(warp_sums[lane], all);
-        warp_sums[lane]   = ex;
-        if (lane == 0) warp_sums[32] = all;
-    }
-    __syncthreads();
-    total = warp_sums[32];
-    return warp_sums[warp] + in_warp;
-}
-
-// Exclusive prefix of the per-chunk word counts, totals, and per-sequence word offsets.
-__global__ void __launch_bounds__(1024) scan_kernel(const Plan plan, const Work work, uint32_t n_seqs)
-{
-    __shared__ uint64_t warp_sums[33];
-    uint64_t            carry_words = 0, carry_sites = 0;   // identical in every thread
-    for (uint32_t base = 0; base < plan.n_chunks; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint64_t w = i < plan.n_chunks ? work.chunk_words[i] : 0;
-        const uint64_t s = i < plan.n_chunks ? work.chunk_sites[i] : 0;
-        uint64_t       tw, ts;
-        const uint64_t ew = block_exclusive(w, warp_sums, tw);
-        block_exclusive(s, warp_sums, ts);
-        if (i < plan.n_chunks) {
-            work.chunk_words[i] = carry_words + ew;
-            if (i % plan.chunks_per_seq == 0) work.seq_word_begin[i / plan.chunks_per_seq] = carry_words + ew;
-        }
-        carry_words += tw;
-        carry_sites += ts;
-    }
-    if (threadIdx.x == 0) {
-        work.chunk_words[plan.n_chunks] = carry_words;
-        work.seq_word_begin[n_seqs]     = carry_words;
-        work.totals[0]                  = carry_words;
-        work.totals[1]                  = carry_sites;
-    }
-}
-
 // band[q] = max v - u over the set bits (u, v), u < v < n, of the pair mask of sequence q.
 // One warp per mask row; grid = (sequences, row slices).
 __global__ void __launch_bounds__(256) band_kernel(const DevQuery query, int32_t* __restrict__ band)
@@ -1737,6 +1752,14 @@ cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& p
     }
     if (e == cudaSuccess && plan.window && plan.n_chunks) e = launch_window<false>(lib, q, plan, work, nullptr, 0, sm_count, s);
     return e;
+}
+
+cudaError_t launch_reset(const Plan& plan, const Work& work, uint32_t n_seqs, cudaStream_t s)
+{
+    const uint32_t items = std::max(2 * (plan.n_chunks + 1), n_seqs + 1);
+    reset_kernel<<<std::min<uint32_t>((items + 255) / 256, 64u), 256, 0, s>>>(work, plan.n_chunks, n_seqs);
+    BSS_SYNC_CHECK("reset_kernel", s);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s)

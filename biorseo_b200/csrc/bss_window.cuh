@@ -294,8 +294,7 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
     constexpr int THREADS = STAGE ? kWinThreadsStaged : kWinThreads;
     using Gr = Group<32>;
     const uint32_t n_list = (uint32_t)work.totals[EMIT ? 5 : 6];
-    if (n_list == 0) return;
-    if (EMIT && work.totals[0] > capacity_words) return;   // the records would not fit: nothing is written
+    if (EMIT && (n_list == 0 || work.totals[0] > capacity_words)) return;   // nothing to write / the records would not fit: nothing is written
     extern __shared__ __align__(16) uint32_t smem_raw[];
     constexpr uint32_t warps = THREADS / 32;
     const int          W = (int)plan.W, WS = (int)plan.WS;
@@ -366,6 +365,7 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
     }
     const bool one_seq = query.n_seqs == 1;
     SeqCtx     sq      = load_seq(lib, query, 0);
+    if (!EMIT && n_list == 0) return;
     while (slot < n_list) {
         uint32_t next_slot = 0;
         if (!EMIT && lane == 0 && slot + 1 == block_end) next_slot = atomicAdd(cursor, draw);   // drawn ahead: its latency hides behind this item

@@ -255,8 +255,14 @@ class PeerGatherer:
         rc = self._lib.bss_exchange_run_async(self._h, C.c_void_p(cuda_stream), C.byref(out), C.byref(res))
         if rc != 0:
             raise RuntimeError((self._lib.bss_last_error() or b"").decode())
-        return (torch.as_tensor(_DevicePointer(out.value, self.world * self.capacity, "<i4"), device=self.device),
-                torch.as_tensor(_DevicePointer(res.value, self.world + 2, "<i8"), device=self.device))
+        # (the two output buffers and the result block never move: their tensor views are made once — wrapping raw device
+        #  memory costs tens of microseconds, which is a whole exchange of a small stream)
+        views = self.__dict__.setdefault("_views", {})
+        key = (out.value, res.value)
+        if key not in views:
+            views[key] = (torch.as_tensor(_DevicePointer(out.value, self.world * self.capacity, "<i4"), device=self.device),
+                          torch.as_tensor(_DevicePointer(res.value, self.world + 2, "<i8"), device=self.device))
+        return views[key]
 
     def close(self):
         if getattr(self, "_h", None):
