@@ -656,8 +656,12 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-    traffic_path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    traffic_table = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    traffic_table = {}
+    for name in ("r01_traffic.json", "r02_traffic.json"):    # DRAM bytes per launch from the committed ncu captures; the later round wins
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            for wl, per_kernel in json.load(open(path)).items():
+                traffic_table.setdefault(wl, {}).update(per_kernel)
 
     def roofline(res):
         km = res["kernel_ms"]
@@ -667,8 +671,10 @@ def main():
         # the count kernel reads the inputs, the emit kernel reads them again and writes the sites
         algo = {"count_ms": b_in, "scan_ms": 0, "emit_ms": b_in + b_out}[name]
         achieved = algo / (km[name] * 1e-3) / 1e9 if km[name] > 0 else 0.0
-        return {"bound": "hbm", "kernel": {"count_ms": "search_kernel<G,false> (match+count)", "scan_ms": "scan_kernel",
-                                           "emit_ms": "search_kernel<G,true> (emit)"}[name],
+        windowed = res["stats"]["window_items"] > 0
+        return {"bound": "hbm", "kernel": {"count_ms": "pattern_kernel + route_kernel + window_kernel<count> (pattern table, routing, window walk)" if windowed
+                                           else "search_kernel<G,false> (match+count)", "scan_ms": "scan_kernel",
+                                           "emit_ms": "window_kernel<emit>" if windowed else "search_kernel<G,true> (emit)"}[name],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": algo, "kernel_ms": km[name], "peak_source": peak_src,
                 "all_kernels_ms": km}

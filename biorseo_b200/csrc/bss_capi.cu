@@ -684,14 +684,15 @@ cudaError_t record_event(bss_library* lib, int i, bool capturing)
 }
 
 // Queues the count pass (+ heavy count) and the scan.
-int enqueue_count(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, bool ordinary, bool capturing = false)
+int enqueue_count(bss_library* lib, const bss_query* q, const bss::Plan& plan, const bss::Work& work, bool ordinary, bool capturing = false,
+                  uint64_t* d_seq_out = nullptr)
 {
     cudaStream_t st = lib->stream;
     BSS_CUDA(bss::launch_reset(plan, work, q->dev.n_seqs, st));
     BSS_CUDA(record_event(lib, 0, capturing));
     BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, ordinary, lib->sm_count, st));
     BSS_CUDA(record_event(lib, 1, capturing));
-    if (!bss::scan_is_fused(plan)) BSS_CUDA(bss::launch_scan(q->dev, plan, work, st));   // (else the window count pass has done it)
+    BSS_CUDA(bss::launch_scan(q->dev, plan, work, plan.n_chunks ? d_seq_out : nullptr, st));
     BSS_CUDA(record_event(lib, 2, capturing));
     return BSS_OK;
 }
@@ -703,7 +704,7 @@ constexpr size_t kTotalsFetch = 64;   // bytes of the totals the host reads: [0]
 uint32_t count_launches(const bss_library* lib, const bss_query* q, const bss::Plan& plan, bool ordinary)
 {
     if (!plan.n_chunks) return 2u;   // reset + the scan alone
-    uint32_t n = bss::scan_is_fused(plan) ? 1u : 2u;   // reset, scan
+    uint32_t n = 2u;                 // reset, scan
     if (plan.window || (lib->dev.unit_probe && q->dev.kmers)) n++;
     if (ordinary) n += 1u + (plan.group == 32 && plan.list_cap ? 1u : 0u);
     if (plan.window) n++;
@@ -864,13 +865,12 @@ int bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* 
     cudaStream_t st      = lib->stream;
     const bool   emitting = plan.n_chunks && d_records && capacity_words;
     auto enqueue = [&](bool capturing) -> int {
-        int r = enqueue_count(lib, q, plan, work, ordinary, capturing);
+        // The per-sequence offsets (their last entry is the number of record words) always reach the caller's header — the scan
+        // writes them there — also when the records do not fit: a sharded exchange behind this search then sees the true count
+        // on every rank and raises its overflow flag instead of forwarding a stale one.
+        int r = enqueue_count(lib, q, plan, work, ordinary, capturing, d_seq_word_begin);
         if (r != BSS_OK) return r;
         if (emitting) BSS_CUDA(bss::launch_emit(lib->dev, q->dev, plan, work, d_records, 0xFFFFFFFFu, 0, capacity_words, ordinary, lib->sm_count, st));
-        // The per-sequence offsets (their last entry is the number of record words) always reach the caller's header,
-        // also when the records did not fit: a sharded exchange behind this search then sees the true count on every
-        // rank and raises its overflow flag instead of forwarding a stale one.
-        if (d_seq_word_begin && plan.n_chunks) BSS_CUDA(bss::launch_offsets_copy(work, d_seq_word_begin, q->dev.n_seqs + 1, st));
         BSS_CUDA(record_event(lib, 3, capturing));
         BSS_CUDA(cudaMemcpyAsync(lib->h_totals.ptr, work.totals, kTotalsFetch, cudaMemcpyDeviceToHost, st));
         return BSS_OK;

@@ -154,12 +154,11 @@ cudaError_t launch_gather_cut(const uint32_t* blocks, uint32_t world, uint64_t b
 cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, uint32_t* kmers, cudaStream_t s);
 // `ordinary`: the ordinary count passes are needed (some item may not take the window walk)
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, bool ordinary, int sm_count, cudaStream_t s);
-cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s);
+// seq_out (may be null): device copy of the per-sequence word offsets for the caller, written by the scan itself
+cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, uint64_t* seq_out, cudaStream_t s);
 // totals, chunk totals and per-sequence offsets zeroed by one kernel
 cudaError_t launch_reset(const Plan& plan, const Work& work, uint32_t n_seqs, cudaStream_t s);
-// (measured: the scan run by the last CTA of the window count pass — 128 threads, serial tail — costs more than the launch
-//  it saves: c4 count + scan 0.127 -> 0.141 ms; it stays a kernel of its own)
-inline bool scan_is_fused(const Plan&) { return false; }
+
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
                         uint32_t n_alive, uint32_t n_heavy, uint64_t capacity_words, bool ordinary, int sm_count, cudaStream_t s);
 // Exact number of placements the reference's enumerator materialises before its filters (cppsrc/Motif.cpp:466-474),
@@ -168,7 +167,6 @@ cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& pl
 size_t      placements_words_per_warp(uint32_t max_len);
 cudaError_t launch_placements(const DevLibrary& lib, const DevQuery& q, const Plan& plan, uint64_t* scratch, size_t per_warp, uint32_t n_ctas,
                               unsigned long long* total, cudaStream_t s);
-cudaError_t launch_offsets_copy(const Work& work, uint64_t* dst, uint32_t n, cudaStream_t s);
 
 // Integer-issue probe (bss_probe.cu): SHF + LOP3 only, all SMs; *thread_ops = operations issued by the launch.
 cudaError_t launch_int_issue_probe(uint32_t iters, int sm_count, uint32_t* sink, uint64_t* thread_ops, cudaStream_t s);

@@ -1062,7 +1062,9 @@ __device__ __forceinline__ uint64_t block_exclusive(uint64_t v, uint64_t* warp_s
 
 // Exclusive prefix of the per-chunk word counts, totals, and per-sequence word offsets: one CTA. The chunk totals were
 // accumulated with atomics by other SMs: they are read past L1.
-__device__ __forceinline__ void scan_chunks(const Plan& plan, const Work& work, uint32_t n_seqs, uint64_t* warp_sums)
+// `seq_out` (may be null): the caller's copy of the per-sequence offsets (its last entry is the record-word count an
+// exchange behind the search reads), written here instead of by a copy kernel of its own.
+__device__ __forceinline__ void scan_chunks(const Plan& plan, const Work& work, uint32_t n_seqs, uint64_t* warp_sums, uint64_t* __restrict__ seq_out)
 {
     uint64_t carry_words = 0, carry_sites = 0;   // identical in every thread
     for (uint32_t base = 0; base < plan.n_chunks; base += blockDim.x) {
@@ -1074,7 +1076,10 @@ __device__ __forceinline__ void scan_chunks(const Plan& plan, const Work& work, 
         block_exclusive(s, warp_sums, ts);
         if (i < plan.n_chunks) {
             work.chunk_words[i] = carry_words + ew;
-            if (i % plan.chunks_per_seq == 0) work.seq_word_begin[i / plan.chunks_per_seq] = carry_words + ew;
+            if (i % plan.chunks_per_seq == 0) {
+                work.seq_word_begin[i / plan.chunks_per_seq] = carry_words + ew;
+                if (seq_out) seq_out[i / plan.chunks_per_seq] = carry_words + ew;
+            }
         }
         carry_words += tw;
         carry_sites += ts;
@@ -1082,15 +1087,16 @@ __device__ __forceinline__ void scan_chunks(const Plan& plan, const Work& work, 
     if (threadIdx.x == 0) {
         work.chunk_words[plan.n_chunks] = carry_words;
         work.seq_word_begin[n_seqs]     = carry_words;
+        if (seq_out) seq_out[n_seqs] = carry_words;
         work.totals[0]                  = carry_words;
         work.totals[1]                  = carry_sites;
     }
 }
 
-__global__ void __launch_bounds__(1024) scan_kernel(const Plan plan, const Work work, uint32_t n_seqs)
+__global__ void __launch_bounds__(1024) scan_kernel(const Plan plan, const Work work, uint32_t n_seqs, uint64_t* __restrict__ seq_out)
 {
     __shared__ uint64_t warp_sums[33];
-    scan_chunks(plan, work, n_seqs, warp_sums);
+    scan_chunks(plan, work, n_seqs, warp_sums, seq_out);
 }
 
 // One kernel instead of three memsets at the head of a search: totals, chunk totals, per-sequence offsets.
@@ -1614,6 +1620,11 @@ Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tun
     uint32_t       upc     = (lib.n_units + per_seq - 1) / (per_seq ? per_seq : 1);
     upc                    = ((upc + groups - 1) / groups) * groups;
     if (upc < groups) upc = groups;
+    // Every item takes the window pass (a library of window units on narrow-band sequences): the chunks only carry the
+    // output offsets then — few large ones make the scan one short step (the emit pass sums the counts of a chunk's earlier units).
+    const bool window_only = n_window_units == lib.n_units && lib.n_units > 0 && q.bmask != nullptr && known_band != INT32_MIN && known_band <= kWindowBandMax &&
+                             p.group == 32 && tuning.window != 0;
+    if (window_only && n_seqs <= 64) upc = std::max(upc, 256u);
     if (tuning.units_per_chunk > 0) upc = (uint32_t)tuning.units_per_chunk;
     if (upc > kMaxChunkUnits) upc = kMaxChunkUnits;
     p.units_per_chunk = upc;
@@ -1762,9 +1773,9 @@ cudaError_t launch_reset(const Plan& plan, const Work& work, uint32_t n_seqs, cu
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, cudaStream_t s)
+cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, uint64_t* seq_out, cudaStream_t s)
 {
-    scan_kernel<<<1, 1024, 0, s>>>(plan, work, q.n_seqs);
+    scan_kernel<<<1, plan.n_chunks > 512 ? 1024 : 512, 0, s>>>(plan, work, q.n_seqs, seq_out);
     BSS_SYNC_CHECK("scan_kernel", s);
     return cudaGetLastError();
 }
@@ -1797,20 +1808,6 @@ cudaError_t launch_placements(const DevLibrary& lib, const DevQuery& q, const Pl
 }
 
 size_t placements_words_per_warp(uint32_t max_len) { return placements_scratch_words(max_len); }
-
-// The per-sequence word offsets go to the caller's header whether or not the records fitted (its last entry is the
-// number of record words: what an exchange behind the search reads, and what tells every rank about an overflow).
-__global__ void offsets_copy_kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint32_t n)
-{
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
-}
-
-cudaError_t launch_offsets_copy(const Work& work, uint64_t* dst, uint32_t n, cudaStream_t s)
-{
-    if (n == 0) return cudaSuccess;
-    offsets_copy_kernel<<<n > 4096 ? 16 : 1, 256, 0, s>>>(work.seq_word_begin, dst, n);
-    return cudaGetLastError();
-}
 
 }   // namespace bss
 
