@@ -661,7 +661,8 @@ def main():
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
             for wl, per_kernel in json.load(open(path)).items():
-                traffic_table.setdefault(wl, {}).update(per_kernel)
+                if isinstance(per_kernel, dict):
+                    traffic_table.setdefault(wl, {}).update(per_kernel)
 
     def roofline(res):
         km = res["kernel_ms"]

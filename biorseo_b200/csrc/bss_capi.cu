@@ -105,6 +105,7 @@ struct bss_library {
     int          sm_count   = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t  ev[4]      = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t  ev_band    = nullptr;   // the bands of the one-shot query have reached h_band
     bss::DevLibrary       dev{};
     DeviceBuffer          d_blob, d_unit_off, d_unit_rlen, d_unit_probe, d_unit_flags, d_prefilter;
     DeviceBuffer          d_pat_blob, d_pat_off, d_pat_tslot, d_unit_slots, d_ptab_m, d_ptab_t, d_pflag;   // pattern table: slots (library), rows (per search)
@@ -140,7 +141,8 @@ struct bss_library {
     bool            graphs_ok  = true;
     uint64_t        dev_serial = 1;   // bumped when launch parameters held by value change (module base, tuning)
     bss_query    oneshot;       // storage of the host-buffer entry points (bss_search, bss_search_batch), reused across calls
-    PinnedBuffer h_totals;
+    PinnedBuffer h_totals, h_band;
+    bool         band_pending = false;   // one-shot query: the bands are on their way to h_band (ev_band)
     // one spare set of result buffers, recycled by bss_sites_free
     DeviceBuffer spare_records;
     PinnedBuffer spare_host;
@@ -248,6 +250,7 @@ int bss_library_create(const bss_table* t, int device, bss_library** out)
     BSS_CUDA_LIB(cudaStreamCreateWithFlags(&lib->own_stream, cudaStreamNonBlocking));
     lib->stream = lib->own_stream;
     for (auto& ev : lib->ev) BSS_CUDA_LIB(cudaEventCreate(&ev));
+    BSS_CUDA_LIB(cudaEventCreateWithFlags(&lib->ev_band, cudaEventDisableTiming));
     auto upload = [&](DeviceBuffer& d, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e_ = d.reserve(std::max<size_t>(4, bytes));
         if (e_ == cudaSuccess && bytes) e_ = cudaMemcpy(d.ptr, src, bytes, cudaMemcpyHostToDevice);
@@ -300,13 +303,14 @@ void bss_library_destroy(bss_library* lib)
     if (lib->graph_exec) cudaGraphExecDestroy(lib->graph_exec);
     for (auto& ev : lib->ev)
         if (ev) cudaEventDestroy(ev);
+    if (lib->ev_band) cudaEventDestroy(lib->ev_band);
     for (DeviceBuffer* b : {&lib->oneshot.storage, &lib->d_blob, &lib->d_unit_off, &lib->d_unit_rlen, &lib->d_unit_probe, &lib->d_unit_flags, &lib->d_prefilter,
                             &lib->d_pat_blob, &lib->d_pat_off, &lib->d_pat_tslot, &lib->d_unit_slots, &lib->d_ptab_m, &lib->d_ptab_t, &lib->d_pflag,
                             &lib->d_alive, &lib->d_lane_counts, &lib->d_heavy, &lib->d_counts, &lib->d_chunks, &lib->d_wlist, &lib->d_alive_w,
                             &lib->d_lane_counts_w, &lib->d_placements, &lib->d_idx_work, &lib->d_idx_hist, &lib->spare_idx_main, &lib->spare_idx_overlap,
                             &lib->d_totals, &lib->d_seq_word_begin, &lib->spare_records})
         b->release();
-    for (PinnedBuffer* b : {&lib->spare_idx_host_main, &lib->spare_idx_host_overlap, &lib->h_idx_totals, &lib->h_totals, &lib->spare_host}) b->release();
+    for (PinnedBuffer* b : {&lib->spare_idx_host_main, &lib->spare_idx_host_overlap, &lib->h_idx_totals, &lib->h_totals, &lib->h_band, &lib->spare_host}) b->release();
     if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
     delete lib;
 }
@@ -454,10 +458,19 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     q->n_symbols      = ns;
     q->pair_rows      = lib->dev.pair_rows;
     std::memcpy(q->alphabet, lib->dev.alphabet, sizeof q->alphabet);
+    // widest pair the mask allows, per sequence: bounds the window a tied component is searched in
+    // The host-buffer entry points (the library's own one-shot query) learn the widest band without an extra wait: the bands
+    // are copied to pinned memory right behind the band kernel, and the host reads them while the banded masks and the
+    // occurrence table are still being built (search_host_batch). A search then leaves out the passes no item will take.
+    int32_t* band_host = nullptr;
+    if (q == &lib->oneshot && !wait && !device_mask && n_seqs && lib->h_band.reserve(4 * (size_t)n_seqs) == cudaSuccess) band_host = static_cast<int32_t*>(lib->h_band.ptr);
+    lib->band_pending = false;
+    if (e == cudaSuccess && !device_mask) {   // (a device-built mask gets its band afterwards)
+        e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), const_cast<uint32_t*>(q->dev.bmask), band_host, lib->ev_band, st);
+        lib->band_pending = e == cudaSuccess && band_host != nullptr;
+    }
     // per-symbol (and per-symbol-pair) occurrence bit rows of every sequence, matched against by every unit
     if (e == cudaSuccess) e = bss::launch_occ(lib->dev, q->dev, reinterpret_cast<uint32_t*>(d + off_occ), const_cast<uint32_t*>(q->dev.kmers), st);
-    // widest pair the mask allows, per sequence: bounds the window a tied component is searched in
-    if (e == cudaSuccess && !device_mask) e = bss::launch_band(q->dev, reinterpret_cast<int32_t*>(d + off_band), const_cast<uint32_t*>(q->dev.bmask), st);   // (a device-built mask gets its band afterwards)
     // (copies from pageable host memory are staged before cudaMemcpyAsync returns: sb / mb may go out of scope)
     q->known_band = INT32_MIN;
     if (e == cudaSuccess && wait && !device_mask) e = read_back_band(lib, q);
@@ -547,7 +560,7 @@ int bss_query_create_pij(bss_library* lib, const char* seq, uint32_t n, const fl
         cudaError_t    e = d_pij.reserve(extent * 4);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_pij.ptr, pij, extent * 4, cudaMemcpyHostToDevice, lib->stream);
         if (e == cudaSuccess) e = bss::launch_pair_mask(static_cast<const float*>(d_pij.ptr), n, row_stride, col_stride, theta, const_cast<uint32_t*>(q->dev.masks), lib->sm_count, lib->stream);
-        if (e == cudaSuccess) e = bss::launch_band(q->dev, const_cast<int32_t*>(q->dev.band), const_cast<uint32_t*>(q->dev.bmask), lib->stream);
+        if (e == cudaSuccess) e = bss::launch_band(q->dev, const_cast<int32_t*>(q->dev.band), const_cast<uint32_t*>(q->dev.bmask), nullptr, nullptr, lib->stream);
         if (e == cudaSuccess) e = read_back_band(lib, q);
         d_pij.release();
         if (e != cudaSuccess) rc = cuda_fail(e, "bss_query_create_pij");
@@ -976,6 +989,14 @@ int search_host_batch(bss_library* lib, uint32_t n_seqs, const char* seqs, const
     bss_query* q  = &lib->oneshot;   // device storage kept between calls: no allocation once it has grown
     int        rc = query_fill(lib, q, n_seqs, seqs, seq_begin, masks, mask_begin, false);
     if (rc != BSS_OK) return rc;
+    if (lib->band_pending) {   // the bands have been on their way since the band kernel ended
+        BSS_CUDA(cudaEventSynchronize(lib->ev_band));
+        const int32_t* band = static_cast<const int32_t*>(lib->h_band.ptr);
+        int            widest = -1;
+        for (uint32_t i = 0; i < n_seqs; i++) widest = std::max(widest, (int)band[i]);
+        q->known_band     = widest;
+        lib->band_pending = false;
+    }
     rc = bss_search_query(lib, q, fetch, out);
     if (rc == BSS_OK) lib->stats.h2d_bytes = q->h2d_bytes;
     return rc;

@@ -145,7 +145,7 @@ __host__ __device__ inline int band_words(int band) { return band < 0 ? 0 : ((31
 // known_band: the widest band over the query's sequences when the host knows it (>= -1), else INT32_MIN
 Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tuning& tuning, uint32_t n_window_units, int known_band);
 
-cudaError_t launch_band(const DevQuery& q, int32_t* band, uint32_t* bmask, cudaStream_t s);
+cudaError_t launch_band(const DevQuery& q, int32_t* band, uint32_t* bmask, int32_t* band_host, cudaEvent_t copied, cudaStream_t s);
 // bit v of row u (u < v) = v >= u + 4 && u + 6 < n && pij[u * row_stride + v * col_stride] > theta
 cudaError_t launch_pair_mask(const float* pij, uint32_t n, uint64_t row_stride, uint64_t col_stride, float theta, uint32_t* mask,
                              int sm_count, cudaStream_t s);

@@ -1667,7 +1667,9 @@ Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tun
     return p;
 }
 
-cudaError_t launch_band(const DevQuery& q, int32_t* band, uint32_t* bmask, cudaStream_t s)
+// band: [n_seqs]; band_host (may be null): pinned host copy of the bands, queued right behind the band kernel and marked by
+// `copied` — the host can read the widest band while the banded masks (and whatever is queued next) are still being built.
+cudaError_t launch_band(const DevQuery& q, int32_t* band, uint32_t* bmask, int32_t* band_host, cudaEvent_t copied, cudaStream_t s)
 {
     if (q.n_seqs == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(band, 0xFF, sizeof(int32_t) * (size_t)q.n_seqs, s);   // -1: no pair allowed
@@ -1678,6 +1680,11 @@ cudaError_t launch_band(const DevQuery& q, int32_t* band, uint32_t* bmask, cudaS
     dim3 grid(q.n_seqs, slices);
     band_kernel<<<grid, 256, 0, s>>>(q, band);
     BSS_SYNC_CHECK("band_kernel", s);
+    if (band_host) {
+        e = cudaMemcpyAsync(band_host, band, sizeof(int32_t) * (size_t)q.n_seqs, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaEventRecord(copied, s);
+        if (e != cudaSuccess) return e;
+    }
     if (bmask) bandmask_kernel<<<grid, 256, 0, s>>>(q, bmask);   // (reads the bands the kernel before it wrote)
     BSS_SYNC_CHECK("bandmask_kernel", s);
     return cudaGetLastError();

@@ -410,7 +410,7 @@ def test_window_tables_against_interpreter(seed):
             assert st["window_items"] > 0 and st["window_items"] + st["ordinary_items"] <= 60
         else:
             assert st["window_items"] == 0
-        one = dev.search(seq, mask)        # the host-buffer path does not know the band: every pass is queued
+        one = dev.search(seq, mask)        # the host-buffer path: the band comes back while the query tables are built
         assert np.array_equal(one.records(), expect), tuning
         for h in (got, one):
             h.close()

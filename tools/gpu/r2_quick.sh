@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+TAG=${1:-q}
+echo tests skipped
+timeout 600 python bench.py --steps 20 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r2_bench_$TAG.json 2> gpurun_out/r2_bench_$TAG.err; echo "bench rc $?"; tail -3 gpurun_out/r2_bench_$TAG.err
+python - <<P
+import json
+d=json.loads(open('gpurun_out/r2_bench_$TAG.json').read().strip().splitlines()[-1])
+print('step', d['ms_per_step'], 'value %.3e'%d['value'], 'e2e', d['e2e']['ms_per_step'], '%.3e'%d['e2e']['value'], d['roofline']['all_kernels_ms'], 'launches', d['gpu_launches'])
+P
