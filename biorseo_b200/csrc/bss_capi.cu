@@ -113,7 +113,7 @@ struct bss_library {
     bss::Tuning           tuning;
     std::vector<uint32_t> module_components;
     // work buffers, reused across searches
-    DeviceBuffer d_counts, d_chunks, d_totals, d_seq_word_begin, d_alive, d_lane_counts, d_heavy, d_wlist, d_alive_w, d_lane_counts_w;
+    DeviceBuffer d_counts, d_chunks, d_totals, d_seq_word_begin, d_alive, d_lane_counts, d_heavy, d_wlist, d_alive_w, d_lane_counts_w, d_kept;
     uint32_t     n_alive = 0, n_heavy = 0, n_alive_w = 0;   // items with sites / parked heavy items / window items with sites of the last count pass
     DeviceBuffer d_placements;               // scratch of bss_placements_enumerated
     // bss_search_query_into replays its launch sequence as a CUDA graph while its arguments stay the same
@@ -121,7 +121,7 @@ struct bss_library {
         uint64_t query_serial = 0, capacity = 0, dev_serial = 0;
         const void *records = nullptr, *seq_out = nullptr, *stream = nullptr, *counts = nullptr, *alive = nullptr, *lanes = nullptr, *heavy = nullptr,
                    *chunk_sites = nullptr, *chunk_words = nullptr, *seq_begin = nullptr, *prefilter = nullptr, *wlist = nullptr, *alive_w = nullptr,
-                   *ptab_m = nullptr, *ptab_t = nullptr, *pflag = nullptr;
+                   *ptab_m = nullptr, *ptab_t = nullptr, *pflag = nullptr, *kept = nullptr;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof *this) == 0; }
     } graph_key;
     cudaGraphExec_t graph_exec = nullptr;
@@ -142,6 +142,7 @@ struct bss_library {
     uint64_t        dev_serial = 1;   // bumped when launch parameters held by value change (module base, tuning)
     bss_query    oneshot;       // storage of the host-buffer entry points (bss_search, bss_search_batch), reused across calls
     PinnedBuffer h_totals, h_band;
+    uint64_t     last_words = 0;         // record words of the previous bss_search_query: the size of the next blind download
     bool         band_pending = false;   // one-shot query: the bands are on their way to h_band (ev_band)
     // one spare set of result buffers, recycled by bss_sites_free
     DeviceBuffer spare_records;
@@ -306,7 +307,7 @@ void bss_library_destroy(bss_library* lib)
     if (lib->ev_band) cudaEventDestroy(lib->ev_band);
     for (DeviceBuffer* b : {&lib->oneshot.storage, &lib->d_blob, &lib->d_unit_off, &lib->d_unit_rlen, &lib->d_unit_probe, &lib->d_unit_flags, &lib->d_prefilter,
                             &lib->d_pat_blob, &lib->d_pat_off, &lib->d_pat_tslot, &lib->d_unit_slots, &lib->d_ptab_m, &lib->d_ptab_t, &lib->d_pflag,
-                            &lib->d_alive, &lib->d_lane_counts, &lib->d_heavy, &lib->d_counts, &lib->d_chunks, &lib->d_wlist, &lib->d_alive_w,
+                            &lib->d_alive, &lib->d_lane_counts, &lib->d_heavy, &lib->d_counts, &lib->d_chunks, &lib->d_wlist, &lib->d_alive_w, &lib->d_kept,
                             &lib->d_lane_counts_w, &lib->d_placements, &lib->d_idx_work, &lib->d_idx_hist, &lib->spare_idx_main, &lib->spare_idx_overlap,
                             &lib->d_totals, &lib->d_seq_word_begin, &lib->spare_records})
         b->release();
@@ -662,11 +663,17 @@ int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::W
         BSS_CUDA(lib->d_prefilter.reserve(4 * ((n_items + 31) / 32) + 4));
         work.prefilter = static_cast<uint32_t*>(lib->d_prefilter.ptr);
     }
-    work.wlist = work.alive_w = nullptr;
+    work.wlist = work.alive_w = work.kept = nullptr;
+    work.kept_slots = 0;
     if (plan.window) {
         BSS_CUDA(lib->d_wlist.reserve(std::max<uint64_t>(4, n_items * 4)));
         BSS_CUDA(lib->d_alive_w.reserve(std::max<uint64_t>(4, n_items * 4)));
         work.wlist         = static_cast<uint32_t*>(lib->d_wlist.ptr);
+        if (n_items < 0x80000000ull) {   // (the alive list marks kept items with its top bit)
+            work.kept_slots = (uint32_t)std::min<uint64_t>(n_items, 1u << 20);
+            BSS_CUDA(lib->d_kept.reserve(std::max<uint64_t>(4, 128ull * work.kept_slots)));
+            work.kept = static_cast<uint32_t*>(lib->d_kept.ptr);
+        }
         work.alive_w       = static_cast<uint32_t*>(lib->d_alive_w.ptr);
     }
     work.ptab_m = work.ptab_t = nullptr;
@@ -814,6 +821,20 @@ int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites*
         if (e != cudaSuccess) return bail(cuda_fail(e, "emit launch"));
         emitted = true;
     }
+    // A stream of similar searches (the same library on query after query) downloads blind as well: the records of as many
+    // words as the previous search produced and the per-sequence offsets are queued behind the blind emit, so that the host
+    // waits ONCE for totals, offsets and records; only what is missing (a larger result) takes a second copy.
+    uint64_t copied_words = 0;
+    bool     offsets_copied = false;
+    s->seq_word_begin.assign(q->dev.n_seqs + 1, 0);
+    if (emitted && fetch && lib->last_words && lib->last_words <= guess_words &&
+        s->h_records.reserve(std::max<uint64_t>(16, lib->last_words * 4)) == cudaSuccess) {
+        e = cudaMemcpyAsync(s->h_records.ptr, s->d_records.ptr, lib->last_words * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->seq_word_begin.data(), work.seq_word_begin, 8 * (size_t)(q->dev.n_seqs + 1), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "records download"));
+        copied_words   = lib->last_words;
+        offsets_copied = true;
+    }
     e = cudaMemcpyAsync(lib->h_totals.ptr, work.totals, kTotalsFetch, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return bail(cuda_fail(e, "count pass"));
@@ -821,27 +842,41 @@ int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites*
     if (rc != BSS_OK) return bail(rc);
     s->n_words = n_words;
     s->n_sites = n_sites;
+    lib->stats.d2h_bytes += copied_words * 4;
     if (emitted && n_words <= guess_words) {
         lib->stats.kernel_launches += blind_emit_launches(plan, ordinary);   // emit, heavy emit, window emit (queued blind)
     } else {   // first search of this size: allocate, then emit with the sizes now known on the host
+        copied_words = 0;
         e = s->d_records.reserve(std::max<uint64_t>(16, n_words * 4));
         if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(records)"));
         rc = run_emit(lib, q, plan, work, ordinary, static_cast<uint32_t*>(s->d_records.ptr), n_words);
         if (rc != BSS_OK) return bail(rc);
     }
-    s->seq_word_begin.assign(q->dev.n_seqs + 1, 0);
+    bool more = false;
     if (fetch) {
+        if (n_words * 4 > s->h_records.cap) copied_words = 0;   // (growing the pinned buffer drops what it holds)
         e = s->h_records.reserve(std::max<uint64_t>(16, n_words * 4));
         if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost(records)"));
-        if (n_words) e = cudaMemcpyAsync(s->h_records.ptr, s->d_records.ptr, n_words * 4, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) return bail(cuda_fail(e, "records download"));
+        if (n_words > copied_words) {
+            e = cudaMemcpyAsync(static_cast<uint32_t*>(s->h_records.ptr) + copied_words, static_cast<const uint32_t*>(s->d_records.ptr) + copied_words,
+                                (n_words - copied_words) * 4, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "records download"));
+            lib->stats.d2h_bytes += (n_words - copied_words) * 4;
+            more = true;
+        }
         s->fetched = true;
-        lib->stats.d2h_bytes += n_words * 4;
     }
-    e = cudaMemcpyAsync(s->seq_word_begin.data(), work.seq_word_begin, 8 * (size_t)(q->dev.n_seqs + 1), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return bail(cuda_fail(e, "result download"));
+    if (!offsets_copied) {
+        e = cudaMemcpyAsync(s->seq_word_begin.data(), work.seq_word_begin, 8 * (size_t)(q->dev.n_seqs + 1), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "result download"));
+        more = true;
+    }
+    if (more || !emitted) {
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "result download"));
+    }
     lib->stats.d2h_bytes += 8 * (uint64_t)(q->dev.n_seqs + 1);
+    lib->last_words = n_words;
     rc = finish_stats(lib);
     if (rc != BSS_OK) return bail(rc);
     *out = s;
@@ -895,7 +930,7 @@ int bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* 
         key.records = d_records; key.seq_out = d_seq_word_begin; key.stream = st; key.counts = work.counts; key.alive = work.alive;
         key.lanes = work.lane_counts; key.heavy = work.heavy_items; key.chunk_sites = work.chunk_sites; key.chunk_words = work.chunk_words;
         key.seq_begin = work.seq_word_begin; key.prefilter = work.prefilter; key.wlist = work.wlist; key.alive_w = work.alive_w;
-        key.ptab_m = work.ptab_m; key.ptab_t = work.ptab_t; key.pflag = work.pflag;
+        key.ptab_m = work.ptab_m; key.ptab_t = work.ptab_t; key.pflag = work.pflag; key.kept = work.kept;
         if (!lib->graph_exec || !(key == lib->graph_key)) {
             if (lib->graph_exec) { cudaGraphExecDestroy(lib->graph_exec); lib->graph_exec = nullptr; }
             cudaGraph_t graph = nullptr;

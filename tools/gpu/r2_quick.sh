@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 TAG=${1:-q}
-echo tests skipped
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider > gpurun_out/r2_gputest_$TAG.log 2>&1; echo "pytest rc $?"; tail -5 gpurun_out/r2_gputest_$TAG.log
 timeout 600 python bench.py --steps 20 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r2_bench_$TAG.json 2> gpurun_out/r2_bench_$TAG.err; echo "bench rc $?"; tail -3 gpurun_out/r2_bench_$TAG.err
 python - <<P
 import json
