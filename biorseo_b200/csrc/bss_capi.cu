@@ -113,7 +113,7 @@ struct bss_library {
     bss::Tuning           tuning;
     std::vector<uint32_t> module_components;
     // work buffers, reused across searches
-    DeviceBuffer d_counts, d_chunks, d_totals, d_seq_word_begin, d_alive, d_lane_counts, d_heavy, d_wlist, d_alive_w, d_lane_counts_w, d_kept;
+    DeviceBuffer d_counts, d_chunks, d_totals, d_seq_word_begin, d_alive, d_lane_counts, d_heavy, d_wlist, d_alive_w, d_lane_counts_w;
     uint32_t     n_alive = 0, n_heavy = 0, n_alive_w = 0;   // items with sites / parked heavy items / window items with sites of the last count pass
     DeviceBuffer d_placements;               // scratch of bss_placements_enumerated
     // bss_search_query_into replays its launch sequence as a CUDA graph while its arguments stay the same
@@ -121,7 +121,7 @@ struct bss_library {
         uint64_t query_serial = 0, capacity = 0, dev_serial = 0;
         const void *records = nullptr, *seq_out = nullptr, *stream = nullptr, *counts = nullptr, *alive = nullptr, *lanes = nullptr, *heavy = nullptr,
                    *chunk_sites = nullptr, *chunk_words = nullptr, *seq_begin = nullptr, *prefilter = nullptr, *wlist = nullptr, *alive_w = nullptr,
-                   *ptab_m = nullptr, *ptab_t = nullptr, *pflag = nullptr, *kept = nullptr;
+                   *ptab_m = nullptr, *ptab_t = nullptr, *pflag = nullptr;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof *this) == 0; }
     } graph_key;
     cudaGraphExec_t graph_exec = nullptr;
@@ -307,7 +307,7 @@ void bss_library_destroy(bss_library* lib)
     if (lib->ev_band) cudaEventDestroy(lib->ev_band);
     for (DeviceBuffer* b : {&lib->oneshot.storage, &lib->d_blob, &lib->d_unit_off, &lib->d_unit_rlen, &lib->d_unit_probe, &lib->d_unit_flags, &lib->d_prefilter,
                             &lib->d_pat_blob, &lib->d_pat_off, &lib->d_pat_tslot, &lib->d_unit_slots, &lib->d_ptab_m, &lib->d_ptab_t, &lib->d_pflag,
-                            &lib->d_alive, &lib->d_lane_counts, &lib->d_heavy, &lib->d_counts, &lib->d_chunks, &lib->d_wlist, &lib->d_alive_w, &lib->d_kept,
+                            &lib->d_alive, &lib->d_lane_counts, &lib->d_heavy, &lib->d_counts, &lib->d_chunks, &lib->d_wlist, &lib->d_alive_w,
                             &lib->d_lane_counts_w, &lib->d_placements, &lib->d_idx_work, &lib->d_idx_hist, &lib->spare_idx_main, &lib->spare_idx_overlap,
                             &lib->d_totals, &lib->d_seq_word_begin, &lib->spare_records})
         b->release();
@@ -663,17 +663,11 @@ int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::W
         BSS_CUDA(lib->d_prefilter.reserve(4 * ((n_items + 31) / 32) + 4));
         work.prefilter = static_cast<uint32_t*>(lib->d_prefilter.ptr);
     }
-    work.wlist = work.alive_w = work.kept = nullptr;
-    work.kept_slots = 0;
+    work.wlist = work.alive_w = nullptr;
     if (plan.window) {
         BSS_CUDA(lib->d_wlist.reserve(std::max<uint64_t>(4, n_items * 4)));
         BSS_CUDA(lib->d_alive_w.reserve(std::max<uint64_t>(4, n_items * 4)));
         work.wlist         = static_cast<uint32_t*>(lib->d_wlist.ptr);
-        if (n_items < 0x80000000ull) {   // (the alive list marks kept items with its top bit)
-            work.kept_slots = (uint32_t)std::min<uint64_t>(n_items, 1u << 20);
-            BSS_CUDA(lib->d_kept.reserve(std::max<uint64_t>(4, 128ull * work.kept_slots)));
-            work.kept = static_cast<uint32_t*>(lib->d_kept.ptr);
-        }
         work.alive_w       = static_cast<uint32_t*>(lib->d_alive_w.ptr);
     }
     work.ptab_m = work.ptab_t = nullptr;
@@ -930,7 +924,7 @@ int bss_search_query_into_async(bss_library* lib, const bss_query* q, uint32_t* 
         key.records = d_records; key.seq_out = d_seq_word_begin; key.stream = st; key.counts = work.counts; key.alive = work.alive;
         key.lanes = work.lane_counts; key.heavy = work.heavy_items; key.chunk_sites = work.chunk_sites; key.chunk_words = work.chunk_words;
         key.seq_begin = work.seq_word_begin; key.prefilter = work.prefilter; key.wlist = work.wlist; key.alive_w = work.alive_w;
-        key.ptab_m = work.ptab_m; key.ptab_t = work.ptab_t; key.pflag = work.pflag; key.kept = work.kept;
+        key.ptab_m = work.ptab_m; key.ptab_t = work.ptab_t; key.pflag = work.pflag;
         if (!lib->graph_exec || !(key == lib->graph_key)) {
             if (lib->graph_exec) { cudaGraphExecDestroy(lib->graph_exec); lib->graph_exec = nullptr; }
             cudaGraph_t graph = nullptr;

@@ -126,8 +126,6 @@ struct Work {
     // window walk (route_kernel, window_kernel)
     uint32_t* wlist;         // [n_seqs * n_units] items routed to the window pass, in arrival order
     uint32_t* alive_w;       // [n_seqs * n_units] window items with sites, in completion order
-    uint32_t* kept;          // [kept_slots][32] records of the sparse window items, kept by the count pass (row = the item's slot on alive_w)
-    uint32_t  kept_slots;    // 0: nothing is kept (every alive item is walked again by the emit pass)
     // pattern table of this search (pattern_kernel): per (sequence, slot) the match set + its word summary, the thinned set
     // of the slots that can overlap themselves, and flags (bit 0: the pattern occurs, bit 1: its matches overlap on this sequence)
     uint32_t* ptab_m;        // [n_seqs][n_slots][W + WS]

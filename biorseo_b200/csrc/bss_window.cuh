@@ -138,14 +138,9 @@ __global__ void __launch_bounds__(256) route_kernel(const DevLibrary lib, const 
 
 // Per warp: descriptor, match sets M and T with the summaries of both, and the walk's scratch (bss_window_walk.h):
 // decoded level parameters, saved cursors, one queue of `qcap` entries per level but the last, the stash of `kw` words per lane.
-// Sparse items: the count pass keeps the records of an item that has at most kCaptureWords / (C + 1) sites (almost every item of
-// the banded regime) in the item's row of Work::kept, and the emit pass copies the row instead of walking the item a second time.
-constexpr uint32_t kCaptureWords = 32;
-constexpr uint32_t kKeptFlag     = 0x80000000u;   // alive_w entry: the item's records are in its row of Work::kept
-
 __host__ __device__ inline uint32_t window_smem_words(uint32_t cmax, uint32_t W, uint32_t WS, uint32_t threads, uint32_t qcap, uint32_t kw)
 {
-    return (threads / 32) * (kBlobStage + 2 * cmax * (W + WS) + (win::kLevelWords + 2 + 6) * cmax + (cmax > 1 ? cmax - 1 : 1) * qcap + 32 * kw + kCaptureWords);
+    return (threads / 32) * (kBlobStage + 2 * cmax * (W + WS) + (win::kLevelWords + 2 + 6) * cmax + (cmax > 1 ? cmax - 1 : 1) * qcap + 32 * kw);
 }
 
 // Occurrence table + banded mask of ONE sequence staged in shared memory (words), when the plan asks for it.
@@ -344,7 +339,6 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
     uint32_t* g_stash = base + warp * 32 * kw;                                               base += warps * 32 * kw;
     base += (base - smem_raw) & 1u;   // (8-byte alignment of the row pointers)
     const uint32_t** g_rows = reinterpret_cast<const uint32_t**>(base) + warp * 3 * lib.cmax;      base += warps * 6 * lib.cmax;
-    uint32_t* g_keep  = base + warp * kCaptureWords;                                         base += warps * kCaptureWords;
 #ifdef BSS_DEBUG_ASSERT
     if ((g_win_skip & 64) && blockIdx.x == 0 && threadIdx.x == 0) {
         uint32_t dyn;
@@ -375,9 +369,7 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
     while (slot < n_list) {
         uint32_t next_slot = 0;
         if (!EMIT && lane == 0 && slot + 1 == block_end) next_slot = atomicAdd(cursor, draw);   // drawn ahead: its latency hides behind this item
-        uint32_t   item = EMIT ? work.alive_w[slot] : work.wlist[slot];
-        const bool kept = EMIT && work.kept_slots && (item & kKeptFlag);   // (with a kept buffer, items number fewer than 2^31)
-        if (kept) item &= ~kKeptFlag;
+        const uint32_t item = EMIT ? work.alive_w[slot] : work.wlist[slot];
         if (!BSS_WIN_CHECK((uint64_t)item < (uint64_t)query.n_seqs * lib.n_units, 21)) break;
         uint32_t qi = 0, u = item;
         if (!one_seq) {   // (one-sequence queries: no division, the sequence's context was loaded before the loop)
@@ -394,12 +386,6 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
             uint64_t       before = 0;
             for (uint32_t v = v0 + lane; v < u; v += 32) before += (uint64_t)work.counts[sq.item0 + v] * __ldg(lib.unit_rlen + v);
             out_words = work.chunk_words[chunk] + Gr::sum(before);
-            if (kept) {   // the count pass kept this item's records: one coalesced copy, no second walk
-                const uint32_t words = work.counts[sq.item0 + u] * __ldg(lib.unit_rlen + u);
-                if (lane < words && BSS_WIN_CHECK(out_words + words <= work.totals[0], 24)) records[out_words + lane] = work.kept[(size_t)slot * kCaptureWords + lane];
-                slot += gridDim.x * warps;
-                continue;
-            }
         }
 
         // stage the unit descriptor
@@ -449,7 +435,6 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
         }
 
         uint64_t item_sites = 0;
-        bool     captured   = false;   // count pass: g_keep holds all the item's records
 #ifdef BSS_DEBUG_ASSERT
         if (g_win_skip & 2) alive = false;
 #endif
@@ -476,12 +461,10 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
 #endif
             // one warp walks the item breadth-first by level (bss_window_walk.h); the emit pass walks it again and writes
             if (EMIT) {
-                const uint64_t wrote = win::walk<win::kEmit>(cx, sq.Wq, module, records + out_words);
+                const uint64_t wrote = win::walk<true>(cx, sq.Wq, module, records + out_words);
                 (void)BSS_WIN_CHECK(wrote == work.counts[sq.item0 + u], 25);
-            } else if (work.kept_slots) {
-                item_sites = win::walk<win::kCapture>(cx, sq.Wq, module, g_keep, kCaptureWords / (uint32_t)(C + 1), &captured);
             } else {
-                item_sites = win::walk<win::kCount>(cx, sq.Wq, module, nullptr);
+                item_sites = win::walk<false>(cx, sq.Wq, module, nullptr);
             }
         }
 #ifdef BSS_DEBUG_ASSERT
@@ -490,21 +473,16 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
 #endif
         __syncwarp();   // the warp's scratch is reused by its next item
         if (!EMIT) {
-            uint32_t where = 0;
             if (lane == 0) {
                 if (item_sites > 0xFFFFFFFFull) atomicOr((unsigned long long*)(work.totals + 2), 1ull);
                 work.counts[sq.item0 + u] = (uint32_t)item_sites;
                 if (item_sites) {
                     const uint32_t chunk = qi * plan.chunks_per_seq + u / plan.units_per_chunk;
-                    where                = (uint32_t)atomicAdd((unsigned long long*)(work.totals + 5), 1ull);
-                    work.alive_w[where]  = item | (captured && where < work.kept_slots ? kKeptFlag : 0u);
+                    const uint32_t where = (uint32_t)atomicAdd((unsigned long long*)(work.totals + 5), 1ull);
+                    work.alive_w[where]  = item;
                     atomicAdd((unsigned long long*)&work.chunk_sites[chunk], (unsigned long long)item_sites);
                     atomicAdd((unsigned long long*)&work.chunk_words[chunk], (unsigned long long)(item_sites * (uint64_t)(C + 1)));
                 }
-            }
-            if (item_sites && captured) {   // (warp-uniform) the item's records go to its row of the kept buffer
-                where = Gr::first(where);
-                if (where < work.kept_slots && lane < (uint32_t)item_sites * (uint32_t)(C + 1)) work.kept[(size_t)where * kCaptureWords + lane] = g_keep[lane];
             }
             if (slot + 1 == block_end) {   // (uniform)
                 slot      = Gr::first(next_slot);

@@ -336,17 +336,10 @@ BSS_HD void lanes_sync()
 // Every site of the item. Returns their number (the same on every lane); when EMIT, writes their records
 // [module, p_0 .. p_{C-1}] from `out` on, in depth-first order. Called by all 32 lanes of a warp (device) or once
 // (host emulation).
-// MODE kCount: count only. kEmit: write every record from `out` on. kCapture: count, and while the item's records still
-// fit `out_records` records write them to `out` too (the count pass keeps the few sites of a sparse item, so that the emit
-// pass copies them instead of walking the item again); `captured` tells whether `out` holds ALL the item's records.
-constexpr int kCount = 0, kEmit = 1, kCapture = 2;
-
-template <int MODE>
-BSS_HD uint64_t walk(const Walk& cx, int Wq, uint32_t module, uint32_t* out, uint32_t out_records = 0, bool* captured = nullptr)
+template <bool EMIT>
+BSS_HD uint64_t walk(const Walk& cx, int Wq, uint32_t module, uint32_t* out)
 {
-    constexpr bool EMIT = MODE == kEmit;
     const int C = cx.C, R = C + 1;
-    bool      capturing = MODE == kCapture;
     LaneState ls[BSS_LANE_SLOTS];
     BSS_LANES_BEGIN
         (void)L;
@@ -390,8 +383,7 @@ BSS_HD uint64_t walk(const Walk& cx, int Wq, uint32_t module, uint32_t* out, uin
             }
         BSS_LANES_END
         const bool leaf = c == C - 1;
-        if (leaf && MODE == kCapture && capturing) {   // (decided below: this round's records are kept only if all of them fit)
-        } else if (leaf && !EMIT) {   // count pass: the children of the last level are only counted
+        if (leaf && !EMIT) {   // count pass: the children of the last level are only counted
             uint32_t total = 0;
 #if defined(__CUDA_ARCH__)
             total = ls[0].cnt;
@@ -406,10 +398,8 @@ BSS_HD uint64_t walk(const Walk& cx, int Wq, uint32_t module, uint32_t* out, uin
         }
         const uint32_t total = scan_lanes(ls);
         if (leaf) {
-            if (MODE == kCapture && found + total > out_records) capturing = false;   // too many sites to keep: counted only from here on
-            const bool write = EMIT || capturing;
             BSS_LANES_BEGIN
-                if (L.cnt && write) {
+                if (L.cnt) {
                     uint32_t*      rec    = out + (found + L.excl) * (uint64_t)R;
                     const uint32_t parent = c == 0 ? 0u : cx.Q[(c - 1) * cx.qcap + (int)(cur + (uint32_t)lane)];
                     for (int j = 0; j < (c == 0 ? 1 : L.nw); j++) {
@@ -467,7 +457,6 @@ BSS_HD uint64_t walk(const Walk& cx, int Wq, uint32_t module, uint32_t* out, uin
             cur = tail = 0;
         }
     }
-    if (MODE == kCapture && captured) *captured = capturing;
     return found;
 }
 
