@@ -430,7 +430,7 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     // banded masks for the window walk: only where whole warps work on an item (make_plan's rule for 32-lane groups)
     const uint64_t n_items_q   = (uint64_t)n_seqs * lib->n_units;
     const bool     with_bmask  = lib->n_window_units > 0 && ((max_len + 32) / 32 > 16 || n_items_q <= (1u << 17));
-    const size_t   bmask_words = with_bmask ? (size_t)bss::kBandWordsMax * total_len : 0;
+    const size_t   bmask_words = with_bmask ? (size_t)bss::band_stride(max_len) * total_len : 0;
     const size_t   off_sb = 0, off_mb = off_sb + 8 * (size_t)(n_seqs + 1), off_band = off_mb + 8 * (size_t)(n_seqs + 1),
                  off_occ = off_band + 4 * (((size_t)n_seqs + 3) & ~(size_t)3), off_bmask = off_occ + 4 * ((occ_words + 3) & ~(size_t)3),
                  off_mask = off_bmask + 4 * ((bmask_words + 3) & ~(size_t)3), off_seq = off_mask + 4 * total_mask, bytes = off_seq + total_len + 16;
@@ -452,6 +452,7 @@ int query_fill(bss_library* lib, bss_query* q, uint32_t n_seqs, const char* seqs
     q->dev.occ        = reinterpret_cast<const uint32_t*>(d + off_occ);
     q->dev.kmers      = with_kmers ? q->dev.occ + (size_t)n_seqs * occ_rows * occ_stride : nullptr;
     q->dev.bmask      = with_bmask ? reinterpret_cast<const uint32_t*>(d + off_bmask) : nullptr;
+    q->dev.bm_stride  = bss::band_stride(max_len);
     q->dev.occ_rows   = occ_rows;
     q->dev.occ_stride = occ_stride;
     q->dev.n_seqs     = n_seqs;
@@ -637,7 +638,7 @@ int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::W
     if (plan.smem_bytes_emit > 200 * 1024) return fail(BSS_ERR_LIMIT, "query too long for the shared-memory working set");
     // The ordinary passes can be left out when the host knows that every item takes the window walk (or ends in the
     // route kernel): a library of window-walk units on a query whose widest band it has read back.
-    ordinary = !(plan.window && lib->n_window_units == lib->n_units && q->known_band != INT32_MIN && q->known_band <= bss::kWindowBandMax);
+    ordinary = !(plan.window && lib->n_window_units == lib->n_units && q->known_band != INT32_MIN && q->known_band <= plan.window_band);
     const uint64_t n_items = (uint64_t)q->dev.n_seqs * lib->n_units;
     if (n_items >= 0xFFFFFFFFull) return fail(BSS_ERR_LIMIT, "more than 2^32 (sequence, unit) items in one search: split the batch");
     BSS_CUDA(lib->d_counts.reserve(std::max<uint64_t>(4, n_items * 4)));

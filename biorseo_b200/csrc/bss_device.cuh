@@ -44,7 +44,8 @@ constexpr int      kOccPad     = 10;           // zero words after each occurren
 constexpr int      kBlobStage  = (int)kBlobStageWords;   // unit descriptor words staged in shared memory per group
 constexpr uint32_t kMaxChunkUnits = 2048;      // units per chunk (bounds the per-CTA offset table)
 __host__ __device__ constexpr uint32_t kmer_table_word(uint32_t table) { return table == 0 ? 0u : table == 1 ? 8u : 40u; }
-constexpr uint32_t kBandWordsMax = (31 + kWindowBandMax) / 32 + 1;   // words per row of the banded pair mask, worst case
+// words reserved per position of a sequence of at most max_len nucleotides in the banded pair masks: any band fits
+__host__ __device__ constexpr uint32_t band_stride(uint32_t max_len) { return (max_len + 30) / 32 + 1; }
 
 // (the unit descriptor layout and its flags are in bss_layout.h)
 struct DevLibrary {
@@ -75,9 +76,10 @@ struct DevQuery {
     const int32_t*  band;         // [n_seqs] max v-u over the set bits above the diagonal, -1 when there is none
     const uint32_t* occ;          // [n_seqs][occ_rows][occ_stride] occurrence table (see occ_kernel)
     const uint32_t* kmers;        // [n_seqs][kKmerWords] k-mer presence bits, or null (alphabets of more than 4 symbols)
-    const uint32_t* bmask;        // banded pair masks, or null: sequence q's starts at word kBandWordsMax * seq_begin[q]; row u = K words
+    const uint32_t* bmask;        // banded pair masks, or null: sequence q's starts at word bm_stride * seq_begin[q]; row u = K words
                                   // (K = band_words(band[q])) holding mask words u >> 5 .. of row u, bits at or below the diagonal and
-                                  // beyond the sequence cleared. Built for sequences whose band is at most kWindowBandMax.
+                                  // beyond the sequence cleared.
+    uint32_t        bm_stride;    // band_stride(max_len)
     uint32_t        occ_rows;     // n_symbols, plus n_symbols^2 pair rows for small alphabets
     uint32_t        occ_stride;   // words per row: ceil((max_len + 1) / 32) + kOccPad
     uint32_t        n_seqs;
@@ -98,6 +100,7 @@ struct Plan {
     uint32_t list_cap;     // rank-space walk: match-list entries per item (0 = depth-first walk only)
     uint32_t window;       // 1: items of window-walk units on narrow-band sequences go through route_kernel + window_kernel
     uint32_t window_draw;  // list entries a warp of the window count pass draws per atomic
+    int32_t  window_band;  // widest band the window kernel's working set is sized for: sequences with a wider one stay with the ordinary passes
     uint32_t window_qcap;  // window walk: entries per level queue (at least the widest band + 1)
     uint32_t window_kw;    // window walk: stash words per lane = words a band window can span
     uint32_t dict;         // 1: the pattern table of this (query, library) is built at the start of the search and the window pass reads it

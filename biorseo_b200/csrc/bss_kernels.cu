@@ -1622,8 +1622,7 @@ Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tun
     if (upc < groups) upc = groups;
     // Every item takes the window pass (a library of window units on narrow-band sequences): the chunks only carry the
     // output offsets then — few large ones make the scan one short step (the emit pass sums the counts of a chunk's earlier units).
-    const bool window_only = n_window_units == lib.n_units && lib.n_units > 0 && q.bmask != nullptr && known_band != INT32_MIN && known_band <= kWindowBandMax &&
-                             p.group == 32 && tuning.window != 0;
+    const bool window_only = n_window_units == lib.n_units && lib.n_units > 0 && q.bmask != nullptr && known_band != INT32_MIN && known_band <= kWindowBandMax && p.group == 32 && tuning.window != 0;
     if (window_only && n_seqs <= 64) upc = std::max(upc, 256u);
     if (tuning.units_per_chunk > 0) upc = (uint32_t)tuning.units_per_chunk;
     if (upc > kMaxChunkUnits) upc = kMaxChunkUnits;
@@ -1645,11 +1644,17 @@ Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tun
     p.smem_bytes      = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, false);
     p.smem_bytes_emit = 4u * smem_words(lib.cmax, p.W, p.WS, groups, upc, p.list_cap, true);
     // Window walk: whole warps only; the query carries banded masks; the working set fits.
+    // Window walk: whole warps only; the query carries banded masks; the band is narrow. The walk scans the words of a band
+    // window, which pays while the window is a few words: measured with an all-allowed mask on 2000 nt (band 1999, the working
+    // set still fits two CTAs per SM) it is 10x SLOWER than the rank-space passes, which step from match to match
+    // (c4b_all 32.6 vs 3.4 ms, profiles/r02_variants_g1.jsonl) — so wide-band sequences stay with the ordinary passes.
     const int widest    = known_band == INT32_MIN ? kWindowBandMax : std::min(std::max(known_band, 0), kWindowBandMax);
+    p.window_band       = kWindowBandMax;
     p.window_kw         = (uint32_t)band_words(widest);
     p.window_qcap       = std::max(64u, ((uint32_t)widest + 1u + 31u) & ~31u);
     p.smem_bytes_window = 4u * window_smem_words(lib.cmax, p.W, p.WS, kWinThreads, p.window_qcap, p.window_kw);
-    p.window = (p.group == 32 && n_window_units > 0 && q.bmask != nullptr && p.smem_bytes_window <= 160u * 1024u && tuning.window != 0) ? 1u : 0u;
+    p.window = (p.group == 32 && n_window_units > 0 && q.bmask != nullptr && p.smem_bytes_window <= 110u * 1024u && tuning.window != 0 &&
+                (known_band == INT32_MIN || known_band <= kWindowBandMax)) ? 1u : 0u;
     p.window_draw  = tuning.window_draw > 0 ? (uint32_t)tuning.window_draw : 1u;   // (measured on c4: 1 -> 0.146 ms, 4 -> 0.166, 32 -> 0.53: balance beats atomics)
     // Pattern table: worth it when the library shares patterns and the table of this query stays small (it is rebuilt by every search)
     const uint64_t table_bytes = 4ull * n_seqs * ((uint64_t)lib.n_slots * (p.W + p.WS) + (uint64_t)lib.n_tslots * p.W);
@@ -1746,13 +1751,13 @@ cudaError_t launch_pattern(const DevLibrary& lib, const DevQuery& q, const Plan&
     return cudaGetLastError();
 }
 
-cudaError_t launch_route(const DevLibrary& lib, const DevQuery& q, const Work& work, uint32_t dict, int sm_count, cudaStream_t s)
+cudaError_t launch_route(const DevLibrary& lib, const DevQuery& q, const Work& work, uint32_t dict, int window_band, int sm_count, cudaStream_t s)
 {
     const uint64_t n_items = (uint64_t)q.n_seqs * lib.n_units;
     if (n_items == 0) return cudaSuccess;
     uint64_t grid = (n_items + 255) / 256;
     if (grid > (uint64_t)sm_count * 64) grid = (uint64_t)sm_count * 64;
-    route_kernel<<<(uint32_t)grid, 256, 0, s>>>(lib, q, work, n_items, dict);
+    route_kernel<<<(uint32_t)grid, 256, 0, s>>>(lib, q, work, n_items, dict, window_band);
     BSS_SYNC_CHECK("route_kernel", s);
     return cudaGetLastError();
 }
@@ -1761,7 +1766,7 @@ cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& p
 {
     cudaError_t e = cudaSuccess;
     if (plan.dict) e = launch_pattern(lib, q, plan, work, sm_count, s);
-    if (plan.window && e == cudaSuccess) e = launch_route(lib, q, work, plan.dict, sm_count, s);
+    if (plan.window && e == cudaSuccess) e = launch_route(lib, q, work, plan.dict, plan.window_band, sm_count, s);
     else if (work.prefilter) e = launch_prefilter(lib, q, work, sm_count, s);
     if (ordinary) {
         if (e == cudaSuccess) e = launch_search<kModeCount>(lib, q, plan, work, nullptr, 0, 0, 0, s);

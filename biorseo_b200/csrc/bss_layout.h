@@ -30,7 +30,7 @@ constexpr uint32_t kNoSlot      = 0xFFFFu;     // unit_slots entry: the componen
 constexpr uint32_t kSlotMinUses = 3;           // a pattern gets a slot when at least this many components of searched units share it
 constexpr uint32_t kSlotMax     = 0xFFF0u;     // slots per library
 constexpr uint32_t kBlobStageWords = 64;       // unit descriptor words staged in shared memory per warp; larger descriptors are read in place
-constexpr int      kWindowBandMax = 255;       // widest pair (v - u) a sequence's mask may allow for the window walk
+constexpr int      kWindowBandMax = 255;       // widest pair (v - u) a sequence's mask may allow for the window walk (beyond, the rank-space passes win)
 
 // Unit descriptor ("blob"), u32 words, one per unit, addressed by unit_off[unit]:
 //   [0] module index

@@ -65,26 +65,27 @@ __global__ void __launch_bounds__(256) bandmask_kernel(const DevQuery query, uin
 {
     const uint32_t qi   = blockIdx.x;
     const int      band = query.band[qi];
-    if (band > kWindowBandMax) return;   // (band < 0: K = 0, nothing to write)
     const int       K  = band_words(band);
     const uint64_t  sb = query.seq_begin[qi];
     const int       n  = (int)(query.seq_begin[qi + 1] - sb);
     const int       Wm = (n + 31) >> 5;
     const uint32_t* mask = query.masks + query.mask_begin[qi];
-    uint32_t*       out  = bmask + (size_t)kBandWordsMax * sb;
+    uint32_t*       out  = bmask + (size_t)query.bm_stride * sb;
     const int       warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int u = blockIdx.y * 8 + warp; u < n; u += gridDim.y * 8) {
-        if (lane >= K) continue;
-        const int w = (u >> 5) + lane;
-        uint32_t  x = w < Wm ? __ldg(mask + (size_t)u * Wm + w) : 0u;
-        if (lane == 0) x &= (u & 31) == 31 ? 0u : (0xFFFFFFFFu << ((u & 31) + 1));   // strictly above the diagonal
-        if (w == Wm - 1 && (n & 31)) x &= (1u << (n & 31)) - 1u;                       // inside the sequence
-        out[(size_t)u * K + lane] = x;
+        for (int j = lane; j < K; j += 32) {   // (band < 0: K = 0, nothing to write)
+            const int w = (u >> 5) + j;
+            uint32_t  x = w < Wm ? __ldg(mask + (size_t)u * Wm + w) : 0u;
+            if (j == 0) x &= (u & 31) == 31 ? 0u : (0xFFFFFFFFu << ((u & 31) + 1));   // strictly above the diagonal
+            if (w == Wm - 1 && (n & 31)) x &= (1u << (n & 31)) - 1u;                    // inside the sequence
+            out[(size_t)u * K + j] = x;
+        }
     }
 }
 
 // One thread per item. See the header of this file.
-__global__ void __launch_bounds__(256) route_kernel(const DevLibrary lib, const DevQuery query, const Work work, uint64_t n_items, uint32_t plan_dict)
+__global__ void __launch_bounds__(256) route_kernel(const DevLibrary lib, const DevQuery query, const Work work, uint64_t n_items, uint32_t plan_dict,
+                                                    int window_band)
 {
     __shared__ uint32_t warp_win[8], warp_old[8], base_win;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) route_kernel(const DevLibrary lib, const 
                 }
             }
             if (!alive) work.counts[item] = 0;
-            window = alive && (__ldg(lib.unit_flags + u) & kUnitWindow) && __ldg(query.band + qi) <= kWindowBandMax;
+            window = alive && (__ldg(lib.unit_flags + u) & kUnitWindow) && __ldg(query.band + qi) <= window_band;
         }
         const uint32_t wbal = __ballot_sync(0xFFFFFFFFu, window), obal = __ballot_sync(0xFFFFFFFFu, alive && !window);
         if (lane == 0 && item < ((n_items + 31) & ~31ull)) work.prefilter[item >> 5] = obal;
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
             cx.blob = blob; cx.rows = g_rows;
             cx.band = sq.band;
             cx.K    = min(band_words(sq.band), (int)kw);
-            cx.bm   = STAGE ? s_bm : query.bmask + (size_t)kBandWordsMax * query.seq_begin[qi];
+            cx.bm   = STAGE ? s_bm : query.bmask + (size_t)query.bm_stride * query.seq_begin[qi];
             cx.lp = g_lp; cx.ctl = g_ctl; cx.Q = g_Q; cx.stash = g_stash; cx.qcap = (int)qcap;
             cx.ovl  = ovl;
             cx.W = W; cx.WS = WS; cx.n = n; cx.C = C; cx.delay = (int)(blob[1] >> 16);

@@ -112,7 +112,8 @@ int window_host_search(const bss_table* t, const char* seq_bytes, uint32_t n_u, 
             if ((mask[(size_t)u * Wm + (v >> 5)] >> (v & 31)) & 1u) band = std::max(band, v - u);
     *band_out = band;
     std::vector<uint32_t> out;
-    const bool            narrow = band <= bss::kWindowBandMax;
+    const char*           limit_env = std::getenv("WINDOW_HOST_BAND_LIMIT");   // (the kernel's limit is its shared-memory budget; tests may set one)
+    const bool            narrow = band <= (limit_env ? std::atoi(limit_env) : 1 << 20);
     const int             K = narrow ? band_words(band) : 0;
     std::vector<uint32_t> bm((size_t)std::max(1, n * K), 0u);
     if (narrow)

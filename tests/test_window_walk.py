@@ -173,11 +173,18 @@ def test_generic_random_tables(harness, seed):
     check(harness, table, seq, mask, min_window=5)
 
 
-def test_wide_band_is_left_to_the_ordinary_passes(harness):
+def test_wide_bands(harness, monkeypatch):
+    """An all-allowed mask on 400 nt (band 399): the walk takes it like any other band — queues of band + 1 entries, a stash
+    of one band window per lane — and a harness-side limit (the kernel's is its shared-memory budget) leaves it alone."""
     rng = np.random.default_rng(1)
-    table = tables.window_table(rng, 10, [ord(c) for c in "ACGU"], max_comp=3, max_len=4)
+    table = tables.window_table(rng, 10, [ord(c) for c in "ACGU"], max_comp=3, max_len=4, min_len=2)
     seq = synth.sequence(400, 9)
-    got, flags, band = window_search(harness, table, seq, synth.mask_all(400))
+    mask = synth.mask_all(400)
+    got, flags, band = window_search(harness, table, seq, mask)
+    assert band > 255 and flags.all()
+    assert np.array_equal(got, expected_of_window_units(table, seq, mask, flags)) and got.size > 0
+    monkeypatch.setenv("WINDOW_HOST_BAND_LIMIT", "255")
+    got, flags, band = window_search(harness, table, seq, mask)
     assert band > 255 and not flags.any() and got.size == 0
 
 

@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 TAG=${1:-d1}
-timeout 600 python tools/window_variants.py c4 c4b c4a c1 > gpurun_out/r2_variants_$TAG.jsonl 2> gpurun_out/r2_variants_$TAG.err; echo "variants rc $?"
+timeout 600 python tools/window_variants.py c4 c4b_all c2 c1 > gpurun_out/r2_variants_$TAG.jsonl 2> gpurun_out/r2_variants_$TAG.err; echo "variants rc $?"
 python - <<P
 import json
 for l in open('gpurun_out/r2_variants_$TAG.jsonl'):
