@@ -1653,7 +1653,10 @@ Plan make_plan(const DevLibrary& lib, const DevQuery& q, int sm_count, const Tun
     p.window_kw         = (uint32_t)band_words(widest);
     p.window_qcap       = std::max(64u, ((uint32_t)widest + 1u + 31u) & ~31u);
     p.smem_bytes_window = 4u * window_smem_words(lib.cmax, p.W, p.WS, kWinThreads, p.window_qcap, p.window_kw);
-    p.window = (p.group == 32 && n_window_units > 0 && q.bmask != nullptr && p.smem_bytes_window <= 110u * 1024u && tuning.window != 0 &&
+    // (a library with only a few window units — CaRNAval RINs, whose strands are mostly tied by non-row links — is not worth the four
+    //  extra launches: c2 0.207 ms with the window pass for 18 of 400 units, 0.177 ms without)
+    const bool enough = tuning.window > 0 || (uint64_t)n_window_units * 8 >= lib.n_units;
+    p.window = (p.group == 32 && n_window_units > 0 && enough && q.bmask != nullptr && p.smem_bytes_window <= 110u * 1024u && tuning.window != 0 &&
                 (known_band == INT32_MIN || known_band <= kWindowBandMax)) ? 1u : 0u;
     p.window_draw  = tuning.window_draw > 0 ? (uint32_t)tuning.window_draw : 1u;   // (measured on c4: 1 -> 0.146 ms, 4 -> 0.166, 32 -> 0.53: balance beats atomics)
     // Pattern table: worth it when the library shares patterns and the table of this query stays small (it is rebuilt by every search)
