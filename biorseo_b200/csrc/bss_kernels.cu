@@ -806,6 +806,14 @@ __device__ __forceinline__ uint32_t leaf_run(const RankCtx& rc, int& j, int jb, 
     }
     const bool sparse = (cx.ovl >> L) & 1u;   // some list entries are not in the thinned set
     uint32_t   done   = 0;
+    // Three-component units write 16-byte records: when the lane's output range starts on a 16-byte boundary (always, in a library
+    // of such units) a record is ONE vector store of registers — the upper placement is fixed for the whole run of leaves.
+    const bool vec4 = EMIT && R == 4 && (reinterpret_cast<uintptr_t>(slot_base) & 15u) == 0;
+    uint32_t   up0 = 0, up1 = 0;
+    if (vec4) {
+        up0 = cx.stack[0];
+        up1 = cx.stack[kThreads];
+    }
     for (; j < jb && done < quota; j++) {
         if (sparse && !in_range_live(rc.N[bL + j])) continue;
         const uint32_t p  = rc.mpos[bL + j];
@@ -819,10 +827,14 @@ __device__ __forceinline__ uint32_t leaf_run(const RankCtx& rc, int& j, int jb, 
         done++;
         if (ok) {
             if (EMIT) {
-                uint32_t* rec = slot_base + fill * R;
-                rec[0]        = module;
-                for (int c = 0; c < L; c++) rec[1 + c] = cx.stack[c * kThreads];
-                rec[C] = p;
+                if (vec4) {
+                    reinterpret_cast<uint4*>(slot_base)[fill] = make_uint4(module, up0, up1, p);
+                } else {
+                    uint32_t* rec = slot_base + fill * R;
+                    rec[0]        = module;
+                    for (int c = 0; c < L; c++) rec[1 + c] = cx.stack[c * kThreads];
+                    rec[C] = p;
+                }
             }
             fill++;
         }
