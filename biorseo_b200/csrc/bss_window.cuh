@@ -396,7 +396,8 @@ __global__ void __launch_bounds__(STAGE ? kWinThreadsStaged : kWinThreads, STAGE
         if (!BSS_WIN_CHECK(blen >= 6 && blen <= kBlobStage, 22)) break;
         // (window-walk units always fit the staging area: the library builder only flags those that do, so every
         //  descriptor read of the walk is a shared-memory load)
-        for (uint32_t i = lane; i < blen; i += 32) g_blob[i] = __ldg(gblob + i);
+        // (streamed once per search: evict-first, so that the descriptors do not push the pattern-table rows and the banded mask out of L1)
+        for (uint32_t i = lane; i < blen; i += 32) g_blob[i] = __ldcs(gblob + i);
         const uint32_t* blob = g_blob;
         __syncwarp();
         const uint32_t module = blob[0] + lib.module_base;
