@@ -116,7 +116,8 @@ typedef struct bss_stats {
     float    total_ms;            /* first launch to last kernel end                           */
     uint64_t window_items;        /* items that took the window walk (route_kernel's list)     */
     uint64_t ordinary_items;      /* items left to the ordinary (rank-space / depth-first) passes */
-    uint64_t heavy_items;         /* ordinary items parked and walked block by block           */
+    uint64_t heavy_items;         /* ordinary items parked to be walked block by block; above 1024 (the
+                                     parking list's capacity) the rest were walked by the warp that found them */
     uint64_t placements_enumerated; /* set by bss_placements_enumerated (0 until it is called)  */
 } bss_stats;
 
@@ -219,7 +220,9 @@ int  bss_search_batch_resident(bss_library* lib, uint32_t n_seqs, const char* se
  * range (its records carry global module indices) and searches it on the replicated query; the ranges' records come
  * back as ONE stream in canonical (sequence, module, placement) order in pinned host memory — the very stream
  * bss_search_batch gives on one GPU, bit for bit. One host thread per GPU inside; no torch, no NCCL, no IPC.
- * devices == NULL selects devices 0 .. n_gpus - 1. Units must come module by module (unit_module non-decreasing). */
+ * devices == NULL selects devices 0 .. n_gpus - 1. Units must come module by module (unit_module non-decreasing).
+ * Like a library, a sharded handle is used by one host thread at a time; the per-range handles of bss_sharded_library
+ * are for statistics and tuning between searches, not for searches of their own. */
 typedef struct bss_sharded bss_sharded;
 int          bss_sharded_create(const bss_table* table, const int* devices, uint32_t n_gpus, uint32_t typical_len, bss_sharded** out);
 void         bss_sharded_destroy(bss_sharded* s);
