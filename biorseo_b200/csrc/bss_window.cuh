@@ -22,7 +22,10 @@ __device__ int g_win_skip;   // debug build: 1 skip the walk, 2 skip thin + walk
 
 // One item per warp at a time. 4 warps per CTA, 8 CTAs per SM; with staged tables 16 warps per CTA, 2 CTAs per SM,
 // so that the 46 KB copy of the query's tables is shared by 16 warps and 32 warps stay resident.
-constexpr int kWinThreads = 128, kWinThreadsStaged = 512;
+#ifndef BSS_WIN_THREADS
+#define BSS_WIN_THREADS 128
+#endif
+constexpr int kWinThreads = BSS_WIN_THREADS, kWinThreadsStaged = 512;
 
 // 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier (sm_90+; UBLKCP in SASS).
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
