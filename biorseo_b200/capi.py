@@ -16,7 +16,7 @@ KIND_JSON, KIND_RIN, KIND_DESC = 0, 1, 2
 C3_COMPONENT_LESS_LINKS, C3_INTERIOR = 0, 1
 IDX_SECTIONS = ("var_begin", "var_first", "var_second", "var_c3_terms", "overlap_begin", "overlap_vars", "pair_begin", "pair_partner",
                 "row_first_pair")
-TUNE = {"group": 0, "units_per_chunk": 1, "heavy_ranks": 2, "list_cap": 3, "window": 4, "window_stage": 5, "window_draw": 6, "pattern_table": 7}
+TUNE = {"group": 0, "units_per_chunk": 1, "heavy_ranks": 2, "list_cap": 3, "window": 4, "window_stage": 5, "window_draw": 6, "pattern_table": 7, "phase_events": 8}
 KIND_OF_SOURCE = {"jsonfolder": KIND_JSON, "rinfolder": KIND_RIN, "descfolder": KIND_DESC}
 
 u32p = C.POINTER(C.c_uint32)

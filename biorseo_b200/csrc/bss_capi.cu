@@ -364,6 +364,7 @@ int bss_library_set_tuning(bss_library* lib, int knob, int64_t value)
         t.window_draw = value;
         break;
     case BSS_TUNE_PATTERN_TABLE: t.dict = value; break;
+    case BSS_TUNE_PHASE_EVENTS: t.phase_events = value; break;
     default: return fail(BSS_ERR_INVALID, "unknown tuning knob");
     }
     lib->dev_serial++;   // a cached launch graph was built for the old plan
@@ -695,6 +696,7 @@ int prepare_search(bss_library* lib, const bss_query* q, bss::Plan& plan, bss::W
 // Timing events: inside a stream capture they must be recorded as external events to stay usable.
 cudaError_t record_event(bss_library* lib, int i, bool capturing)
 {
+    if ((i == 1 || i == 2) && lib->tuning.phase_events == 0) return cudaSuccess;   // (only the whole search is timed)
     return capturing ? cudaEventRecordWithFlags(lib->ev[i], lib->stream, cudaEventRecordExternal) : cudaEventRecord(lib->ev[i], lib->stream);
 }
 
@@ -771,9 +773,11 @@ int run_emit(bss_library* lib, const bss_query* q, const bss::Plan& plan, const 
 int finish_stats(bss_library* lib)
 {
     BSS_CUDA(cudaEventSynchronize(lib->ev[3]));
-    cudaEventElapsedTime(&lib->stats.count_ms, lib->ev[0], lib->ev[1]);
-    cudaEventElapsedTime(&lib->stats.scan_ms, lib->ev[1], lib->ev[2]);
-    cudaEventElapsedTime(&lib->stats.emit_ms, lib->ev[2], lib->ev[3]);
+    if (lib->tuning.phase_events != 0) {
+        cudaEventElapsedTime(&lib->stats.count_ms, lib->ev[0], lib->ev[1]);
+        cudaEventElapsedTime(&lib->stats.scan_ms, lib->ev[1], lib->ev[2]);
+        cudaEventElapsedTime(&lib->stats.emit_ms, lib->ev[2], lib->ev[3]);
+    }
     cudaEventElapsedTime(&lib->stats.total_ms, lib->ev[0], lib->ev[3]);
     return BSS_OK;
 }

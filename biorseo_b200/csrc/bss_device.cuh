@@ -140,7 +140,7 @@ constexpr uint32_t kTotalsWords = 16;
 // Developer knobs (bss_library_set_tuning): force rarely taken paths on small inputs (tests), compare variants
 // (benchmarks). A negative value means automatic.
 struct Tuning {
-    int64_t group = -1, units_per_chunk = -1, heavy_ranks = -1, list_cap = -1, window = -1, window_stage = -1, window_draw = -1, dict = -1;
+    int64_t group = -1, units_per_chunk = -1, heavy_ranks = -1, list_cap = -1, window = -1, window_stage = -1, window_draw = -1, dict = -1, phase_events = -1;
 };
 
 __host__ __device__ inline int band_words(int band) { return band < 0 ? 0 : ((31 + band) >> 5) + 1; }

@@ -143,6 +143,7 @@ int  bss_library_set_module_base(bss_library* lib, uint32_t base);
 #define BSS_TUNE_WINDOW_STAGE     5   /* 1: window kernel stages occurrence table + banded mask in shared memory (cp.async.bulk) */
 #define BSS_TUNE_WINDOW_DRAW      6   /* list entries a warp of the window count pass draws per atomic (1..1024)        */
 #define BSS_TUNE_PATTERN_TABLE    7   /* 0: no pattern table (every unit matches its own patterns)                         */
+#define BSS_TUNE_PHASE_EVENTS     8   /* 0: no CUDA events between the phases of a search (count_ms / scan_ms / emit_ms stay 0)   */
 int  bss_library_set_tuning(bss_library* lib, int knob, int64_t value);
 uint32_t bss_library_units(const bss_library* lib);
 uint32_t bss_library_window_units(const bss_library* lib);   /* units every component of which is tied by a pair to an earlier one */

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import biorseo_b200 as b  # noqa: E402
 
-VARIANTS = [("ordinary", {"window": 0}), ("window", {}), ("window_no_pattern_table", {"pattern_table": 0}), ("window_staged", {"window_stage": 1})]
+VARIANTS = [("ordinary", {"window": 0}), ("window", {}), ("window_no_pattern_table", {"pattern_table": 0}), ("window_staged", {"window_stage": 1}), ("window_no_phase_events", {"phase_events": 0})]
 if os.environ.get("DRAW_SWEEP"):
     VARIANTS = [(f"draw{d}", {"window_draw": d}) for d in (1, 2, 4, 8, 16, 32)]
 
