@@ -705,7 +705,7 @@ int enqueue_count(bss_library* lib, const bss_query* q, const bss::Plan& plan, c
                   uint64_t* d_seq_out = nullptr)
 {
     cudaStream_t st = lib->stream;
-    BSS_CUDA(bss::launch_reset(plan, work, q->dev.n_seqs, st));
+    if (!bss::reset_is_folded(lib->dev, q->dev, plan)) BSS_CUDA(bss::launch_reset(plan, work, q->dev.n_seqs, st));
     BSS_CUDA(record_event(lib, 0, capturing));
     BSS_CUDA(bss::launch_count(lib->dev, q->dev, plan, work, ordinary, lib->sm_count, st));
     BSS_CUDA(record_event(lib, 1, capturing));
@@ -721,7 +721,7 @@ constexpr size_t kTotalsFetch = 64;   // bytes of the totals the host reads: [0]
 uint32_t count_launches(const bss_library* lib, const bss_query* q, const bss::Plan& plan, bool ordinary)
 {
     if (!plan.n_chunks) return 2u;   // reset + the scan alone
-    uint32_t n = 2u;                 // reset, scan
+    uint32_t n = bss::reset_is_folded(lib->dev, q->dev, plan) ? 1u : 2u;   // [reset], scan
     if (plan.window || (lib->dev.unit_probe && q->dev.kmers)) n++;
     if (ordinary) n += 1u + (plan.group == 32 && plan.list_cap ? 1u : 0u);
     if (plan.window) n++;

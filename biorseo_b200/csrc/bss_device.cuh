@@ -159,8 +159,9 @@ cudaError_t launch_occ(const DevLibrary& lib, const DevQuery& q, uint32_t* occ, 
 cudaError_t launch_count(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, bool ordinary, int sm_count, cudaStream_t s);
 // seq_out (may be null): device copy of the per-sequence word offsets for the caller, written by the scan itself
 cudaError_t launch_scan(const DevQuery& q, const Plan& plan, const Work& work, uint64_t* seq_out, cudaStream_t s);
-// totals, chunk totals and per-sequence offsets zeroed by one kernel
+// totals, chunk totals and per-sequence offsets zeroed by one kernel — or by the pattern kernel when it is the first kernel of the search
 cudaError_t launch_reset(const Plan& plan, const Work& work, uint32_t n_seqs, cudaStream_t s);
+inline bool reset_is_folded(const DevLibrary& lib, const DevQuery& q, const Plan& plan) { return plan.dict && lib.n_slots > 0 && q.n_seqs > 0; }
 
 cudaError_t launch_emit(const DevLibrary& lib, const DevQuery& q, const Plan& plan, const Work& work, uint32_t* records,
                         uint32_t n_alive, uint32_t n_heavy, uint64_t capacity_words, bool ordinary, int sm_count, cudaStream_t s);

@@ -1111,13 +1111,18 @@ __global__ void __launch_bounds__(1024) scan_kernel(const Plan plan, const Work 
     scan_chunks(plan, work, n_seqs, warp_sums, seq_out);
 }
 
-// One kernel instead of three memsets at the head of a search: totals, chunk totals, per-sequence offsets.
-__global__ void __launch_bounds__(256) reset_kernel(const Work work, uint32_t n_chunks, uint32_t n_seqs)
+// The head of a search: totals, chunk totals and per-sequence offsets zeroed by the threads [0, stride) of a grid — one kernel
+// instead of three memsets, or no kernel of its own at all when the pattern table is built first (pattern_kernel does it).
+__device__ __forceinline__ void reset_work(const Work& work, uint32_t n_chunks, uint32_t n_seqs, uint32_t i, uint32_t stride)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     if (i < kTotalsWords) work.totals[i] = 0;
     for (uint32_t j = i; j < 2 * (n_chunks + 1); j += stride) work.chunk_sites[j] = 0;   // (chunk_words follows chunk_sites)
     for (uint32_t j = i; j <= n_seqs; j += stride) work.seq_word_begin[j] = 0;
+}
+
+__global__ void __launch_bounds__(256) reset_kernel(const Work work, uint32_t n_chunks, uint32_t n_seqs)
+{
+    reset_work(work, n_chunks, n_seqs, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 #include "bss_window.cuh"
@@ -1761,7 +1766,7 @@ cudaError_t launch_pattern(const DevLibrary& lib, const DevQuery& q, const Plan&
     cudaError_t    e    = cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t grid = std::min<uint64_t>((tasks + kThreads / 32 - 1) / (kThreads / 32), (uint64_t)sm_count * 16);
-    pattern_kernel<<<(uint32_t)grid, kThreads, smem, s>>>(lib, q, plan, work);
+    pattern_kernel<<<(uint32_t)grid, kThreads, smem, s>>>(lib, q, plan, work);   // (also zeroes the search's totals: reset_is_folded)
     BSS_SYNC_CHECK("pattern_kernel", s);
     return cudaGetLastError();
 }

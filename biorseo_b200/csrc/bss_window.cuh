@@ -268,6 +268,9 @@ __global__ void __launch_bounds__(kThreads) pattern_kernel(const DevLibrary lib,
     uint32_t* g_T  = g_SM + WS;
     uint32_t* g_ST = g_T + W;
     const uint64_t n_tasks = (uint64_t)query.n_seqs * lib.n_slots;
+    // first kernel of the search: its first CTAs zero the totals, chunk totals and offsets (no reset kernel of its own)
+    constexpr uint32_t kResetCtas = 16;
+    if (blockIdx.x < kResetCtas) reset_work(work, plan.n_chunks, query.n_seqs, blockIdx.x * kThreads + threadIdx.x, min(gridDim.x, kResetCtas) * kThreads);
     for (uint64_t task = (uint64_t)blockIdx.x * warps + warp; task < n_tasks; task += (uint64_t)gridDim.x * warps) {
         const uint32_t  qi = (uint32_t)(task / lib.n_slots), slot = (uint32_t)(task - (uint64_t)qi * lib.n_slots);
         const SeqCtx    sq = load_seq(lib, query, qi);
