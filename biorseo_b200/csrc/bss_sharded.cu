@@ -19,6 +19,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -95,15 +96,19 @@ struct SubTable {
         comp_pat_begin.assign(1, 0);
         unit_comp_begin.assign(1, 0);
         unit_check_begin.assign(1, 0);
-        std::vector<uint32_t> gates;   // gate units of the whole table that this range names, in order of first use
+        std::vector<uint32_t>                  gates;   // gate units of the whole table that this range names, in order of first use
+        std::unordered_map<uint32_t, uint32_t> place;   // gate unit -> its index in `gates`
         for (uint32_t u = u0; u < u1; u++) {
             append_unit(t, u, t->unit_module[u] - m0);
             uint32_t g = t->unit_gate[u];
             if (g != bss::kNoGate) {
                 if (g < t->n_units || g >= t->n_units + t->n_gates) return false;
-                auto it = std::find(gates.begin(), gates.end(), g);
-                if (it == gates.end()) { gates.push_back(g); it = gates.end() - 1; }
-                g = (u1 - u0) + (uint32_t)(it - gates.begin());
+                auto it = place.find(g);
+                if (it == place.end()) {
+                    it = place.emplace(g, (uint32_t)gates.size()).first;
+                    gates.push_back(g);
+                }
+                g = (u1 - u0) + it->second;
             }
             unit_gate.push_back(g);
         }
