@@ -141,7 +141,7 @@ struct bss_library {
     bool            graphs_ok  = true;
     uint64_t        dev_serial = 1;   // bumped when launch parameters held by value change (module base, tuning)
     bss_query    oneshot;       // storage of the host-buffer entry points (bss_search, bss_search_batch), reused across calls
-    PinnedBuffer h_totals, h_band;
+    PinnedBuffer h_totals, h_band, h_offsets;
     uint64_t     last_words = 0;         // record words of the previous bss_search_query: the size of the next blind download
     bool         band_pending = false;   // one-shot query: the bands are on their way to h_band (ev_band)
     // one spare set of result buffers, recycled by bss_sites_free
@@ -311,7 +311,7 @@ void bss_library_destroy(bss_library* lib)
                             &lib->d_lane_counts_w, &lib->d_placements, &lib->d_idx_work, &lib->d_idx_hist, &lib->spare_idx_main, &lib->spare_idx_overlap,
                             &lib->d_totals, &lib->d_seq_word_begin, &lib->spare_records})
         b->release();
-    for (PinnedBuffer* b : {&lib->spare_idx_host_main, &lib->spare_idx_host_overlap, &lib->h_idx_totals, &lib->h_totals, &lib->h_band, &lib->spare_host}) b->release();
+    for (PinnedBuffer* b : {&lib->spare_idx_host_main, &lib->spare_idx_host_overlap, &lib->h_idx_totals, &lib->h_totals, &lib->h_band, &lib->h_offsets, &lib->spare_host}) b->release();
     if (lib->own_stream) cudaStreamDestroy(lib->own_stream);
     delete lib;
 }
@@ -826,10 +826,12 @@ int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites*
     uint64_t copied_words = 0;
     bool     offsets_copied = false;
     s->seq_word_begin.assign(q->dev.n_seqs + 1, 0);
+    const size_t offsets_bytes = 8 * (size_t)(q->dev.n_seqs + 1);
     if (emitted && fetch && lib->last_words && lib->last_words <= guess_words &&
-        s->h_records.reserve(std::max<uint64_t>(16, lib->last_words * 4)) == cudaSuccess) {
+        s->h_records.reserve(std::max<uint64_t>(16, lib->last_words * 4)) == cudaSuccess && lib->h_offsets.reserve(offsets_bytes) == cudaSuccess) {
         e = cudaMemcpyAsync(s->h_records.ptr, s->d_records.ptr, lib->last_words * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s->seq_word_begin.data(), work.seq_word_begin, 8 * (size_t)(q->dev.n_seqs + 1), cudaMemcpyDeviceToHost, st);
+        // (into pinned memory: a copy to the pageable vector would make this call wait for the whole search right here)
+        if (e == cudaSuccess) e = cudaMemcpyAsync(lib->h_offsets.ptr, work.seq_word_begin, offsets_bytes, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return bail(cuda_fail(e, "records download"));
         copied_words   = lib->last_words;
         offsets_copied = true;
@@ -837,6 +839,7 @@ int bss_search_query(bss_library* lib, const bss_query* q, int fetch, bss_sites*
     e = cudaMemcpyAsync(lib->h_totals.ptr, work.totals, kTotalsFetch, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return bail(cuda_fail(e, "count pass"));
+    if (offsets_copied) std::memcpy(s->seq_word_begin.data(), lib->h_offsets.ptr, offsets_bytes);
     rc = parse_totals(lib, q, plan, ordinary, n_words, n_sites);
     if (rc != BSS_OK) return bail(rc);
     s->n_words = n_words;
