@@ -126,3 +126,27 @@ def test_c_abi_cut_equals_the_python_cut(tmp_path):
             costs = sharded.module_costs(host.table(), n)
             for world in (1, 2, 3, 4, 8):
                 assert host.shard_ranges(world, n) == sharded.shard_ranges_by_cost(costs, world), (host.kind, n, world)
+
+
+def test_sharded_entry_points_fail_loudly_without_a_gpu_and_validate_their_arguments():
+    """There is no CPU path behind bss_sharded_create / bss_search_sharded: without a CUDA device the create call
+    reports BSS_ERR_NO_DEVICE. Argument validation needs no device."""
+    import ctypes as C
+    from biorseo_b200 import capi
+    lib = capi.load()
+    host = b.HostLibrary.from_json_modules(synth.json_modules(30, 2, "c1"))
+    t = host.raw_table()
+    begin = (C.c_uint32 * 4)()
+    assert lib.bss_shard_ranges(None, 2, 100, begin) == capi.BSS_ERR_INVALID
+    assert lib.bss_shard_ranges(C.byref(t), 0, 100, begin) == capi.BSS_ERR_INVALID
+    assert lib.bss_shard_ranges(C.byref(t), 3, 0, begin) == 0 and begin[0] == 0 and begin[3] == host.n_modules
+    h = C.c_void_p()
+    assert lib.bss_sharded_create(C.byref(t), None, 0, 100, C.byref(h)) == capi.BSS_ERR_INVALID
+    assert lib.bss_sharded_create(C.byref(t), None, 17, 100, C.byref(h)) == capi.BSS_ERR_INVALID
+    assert lib.bss_search_sharded(None, 0, None, None, None, None, C.byref(h)) == capi.BSS_ERR_INVALID
+    assert lib.bss_sharded_gpus(None) == 0 and lib.bss_sharded_range(None, 0, None, None, None) == capi.BSS_ERR_INVALID
+    lib.bss_sharded_destroy(None)
+    if lib.bss_device_count() <= 0:
+        rc = lib.bss_sharded_create(C.byref(t), None, 2, 100, C.byref(h))
+        assert rc == capi.BSS_ERR_NO_DEVICE and not h.value
+        assert b"no CUDA device" in lib.bss_last_error() or b"CUDA" in lib.bss_last_error()
